@@ -1,0 +1,300 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over the C ABI.
+
+Class and method names follow the reference (SRTSolver.SetInput / EstimateTransform /
+EstimateTransformRansac / ResidualError, PartRecognition.PartRecog, Deformation.Deform,
+Model2Depth.SetInput/Run, Alignment.Align ...) so that parity tests read like calls into the
+reference.  Everything here is marshalling: numpy arrays in, ctypes calls into libmvs_b200.so,
+numpy arrays out.  No arithmetic of the path happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._capi import AlignParams, Camera, GNParams, MvsError, check, lib  # noqa: F401
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a, ct):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def _dev(ptr):
+    """device pointer given as int (e.g. torch.Tensor.data_ptr())"""
+    return C.c_void_p(int(ptr))
+
+
+def make_camera(K, R, t, w, h) -> Camera:
+    """[ref: Camera/Camera.h:9-16 SetK/SetRT/SetW/SetH]"""
+    c = Camera()
+    c.K[:] = _f64(K).reshape(9).tolist()
+    c.R[:] = _f64(R).reshape(9).tolist()
+    c.t[:] = _f64(t).reshape(3).tolist()
+    c.w, c.h = int(w), int(h)
+    return c
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().mvs_device_count(C.byref(n)))
+    return n.value
+
+
+class Context:
+    """mvs_ctx: device + stream + profiling/launch accounting."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = C.c_void_p()
+        check(lib().mvs_ctx_create(C.byref(self._h), C.c_int(device),
+                                   C.c_void_p(stream) if stream else None))
+
+    def close(self):
+        if self._h:
+            lib().mvs_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        check(lib().mvs_ctx_sync(self._h))
+
+    def prof_enable(self, on=True):
+        check(lib().mvs_prof_enable(self._h, C.c_int(1 if on else 0)))
+
+    def prof_reset(self):
+        check(lib().mvs_prof_reset(self._h))
+
+    def prof(self) -> dict:
+        need = C.c_int64(0)
+        check(lib().mvs_prof_names(self._h, None, C.c_int64(0), C.byref(need)))
+        buf = C.create_string_buffer(max(1, need.value))
+        check(lib().mvs_prof_names(self._h, buf, C.c_int64(len(buf)), C.byref(need)))
+        out = {}
+        for name in [s for s in buf.value.decode().split("\n") if s]:
+            ms, n = C.c_double(0), C.c_int64(0)
+            check(lib().mvs_prof_get(self._h, name.encode(), C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        check(lib().mvs_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def launch_count_reset(self):
+        check(lib().mvs_launch_count_reset(self._h))
+
+    # ---- multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().mvs_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        check(lib().mvs_comm_init(self._h, C.c_int(nranks), C.c_int(rank), uid))
+
+
+def _ctxh(ctx):
+    return ctx.handle if ctx is not None else None
+
+
+# ============================================================================ exact kNN
+class NNIndex:
+    """Exact kNN index (replaces cv::flann::Index + knnSearch on the path)."""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        check(lib().mvs_nn_index_create(_ctxh(ctx), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mvs_nn_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build(self, pts):
+        pts = np.asarray(pts)
+        if pts.dtype == np.float64:
+            a = _f64(pts).reshape(-1, 3)
+            check(lib().mvs_nn_index_build_host_f64(self._h, _ptr(a, C.c_double), C.c_int64(len(a))))
+        else:
+            a = _f32(pts).reshape(-1, 3)
+            check(lib().mvs_nn_index_build_host(self._h, _ptr(a, C.c_float), C.c_int64(len(a))))
+        return self
+
+    def build_dev(self, ptr_xyzw: int, n: int):
+        check(lib().mvs_nn_index_build_dev(self._h, _dev(ptr_xyzw), C.c_int64(n)))
+        return self
+
+    def knn(self, q, k=1):
+        q = np.asarray(q)
+        nq = q.reshape(-1, 3).shape[0]
+        idx = np.empty((nq, k), np.int32)
+        d2 = np.empty((nq, k), np.float32)
+        if q.dtype == np.float64:
+            a = _f64(q).reshape(-1, 3)
+            check(lib().mvs_nn_knn_host_f64(self._h, _ptr(a, C.c_double), C.c_int64(nq), C.c_int(k),
+                                            _ptr(idx, C.c_int32), _ptr(d2, C.c_float)))
+        else:
+            a = _f32(q).reshape(-1, 3)
+            check(lib().mvs_nn_knn_host(self._h, _ptr(a, C.c_float), C.c_int64(nq), C.c_int(k),
+                                        _ptr(idx, C.c_int32), _ptr(d2, C.c_float)))
+        return idx, d2
+
+    def knn_dev(self, q_ptr: int, nq: int, k: int, out_idx_ptr: int, out_d2_ptr: int):
+        check(lib().mvs_nn_knn_dev(self._h, _dev(q_ptr), C.c_int64(nq), C.c_int(k),
+                                   _dev(out_idx_ptr) if out_idx_ptr else None,
+                                   _dev(out_d2_ptr) if out_d2_ptr else None))
+
+
+def nn_search(q, t, k=1, ctx: Context | None = None):
+    q = _f32(q).reshape(-1, 3)
+    t = _f32(t).reshape(-1, 3)
+    idx = np.empty((len(q), k), np.int32)
+    d2 = np.empty((len(q), k), np.float32)
+    check(lib().mvs_nn_search(_ctxh(ctx), _ptr(q, C.c_float), C.c_int64(len(q)),
+                              _ptr(t, C.c_float), C.c_int64(len(t)), C.c_int(k),
+                              _ptr(idx, C.c_int32), _ptr(d2, C.c_float)))
+    return idx, d2
+
+
+class PartRecognition:
+    """[ref: PartRecognition/PartRecognition.h:32-49]"""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx = ctx
+        self.points = None
+        self.parts = None
+
+    def SetInput(self, points):
+        self.points = _f64(points).reshape(-1, 3)
+
+    def SetLabels(self, parts):
+        """The reference loads these from Template/part/parts (LoadParts); file I/O is the caller's."""
+        self.parts = _i32(parts)
+
+    def GetLabels(self):
+        return self.parts
+
+    def PartRecog(self, points_):
+        q = _f64(points_).reshape(-1, 3)
+        out = np.empty(len(q), np.int32)
+        check(lib().mvs_part_recog(_ctxh(self._ctx), _ptr(self.points, C.c_double),
+                                   C.c_int64(len(self.points)), _ptr(self.parts, C.c_int32),
+                                   _ptr(q, C.c_double), C.c_int64(len(q)), _ptr(out, C.c_int32)))
+        return out
+
+
+# ============================================================================ SRT solver
+class SRTSolver:
+    """[ref: Solver/SRTSolver.h:8-39]"""
+
+    def __init__(self, iter_num: int = 100, ctx: Context | None = None):
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        check(lib().mvs_srt_create(_ctxh(ctx), C.byref(self._h)))
+        check(lib().mvs_srt_set_iteration_num(self._h, C.c_int(iter_num)))
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            lib().mvs_srt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def SetInput(self, p, q, cam1: Camera | None = None, cam2: Camera | None = None):
+        """matches as two n x 3 arrays (first, second). float64 -> double planes on the device;
+        float32 n x 4 -> float4 layout."""
+        p = np.asarray(p)
+        if p.dtype == np.float32 and p.ndim == 2 and p.shape[1] == 4:
+            p4, q4 = _f32(p), _f32(q)
+            check(lib().mvs_srt_set_input_f32(self._h, _ptr(p4, C.c_float), _ptr(q4, C.c_float),
+                                              C.c_int64(len(p4)),
+                                              C.byref(cam1) if cam1 else None,
+                                              C.byref(cam2) if cam2 else None))
+            return
+        pd, qd = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+        check(lib().mvs_srt_set_input(self._h, _ptr(pd, C.c_double), _ptr(qd, C.c_double),
+                                      C.c_int64(len(pd)), C.byref(cam1) if cam1 else None,
+                                      C.byref(cam2) if cam2 else None))
+
+    def SetInputDev(self, p_ptr: int, q_ptr: int, n: int, cam1=None, cam2=None):
+        check(lib().mvs_srt_set_input_dev_f32(self._h, _dev(p_ptr), _dev(q_ptr), C.c_int64(n),
+                                              C.byref(cam1) if cam1 else None,
+                                              C.byref(cam2) if cam2 else None))
+
+    def SetIterationNum(self, it: int):
+        check(lib().mvs_srt_set_iteration_num(self._h, C.c_int(it)))
+
+    def SetPrintFlag(self, on: bool):
+        check(lib().mvs_srt_set_print(self._h, C.c_int(1 if on else 0)))
+
+    def EstimateTransform(self):
+        s = C.c_double()
+        R = np.empty(9, np.float64)
+        t = np.empty(3, np.float64)
+        check(lib().mvs_srt_estimate(self._h, C.byref(s), _ptr(R, C.c_double), _ptr(t, C.c_double)))
+        return s.value, R.reshape(3, 3), t
+
+    def EstimateTransformRansac(self, triples=None, seed: int = 0, full=False):
+        s = C.c_double()
+        R = np.empty(9, np.float64)
+        t = np.empty(3, np.float64)
+        be, bi = C.c_double(), C.c_int32()
+        tr = _i32(triples).reshape(-1, 3) if triples is not None else None
+        if tr is not None:
+            self.SetIterationNum(len(tr))
+        check(lib().mvs_srt_estimate_ransac(self._h, _ptr(tr, C.c_int32), C.c_uint64(seed),
+                                            C.byref(s), _ptr(R, C.c_double), _ptr(t, C.c_double),
+                                            C.byref(be), C.byref(bi)))
+        if full:
+            return s.value, R.reshape(3, 3), t, be.value, bi.value
+        return s.value, R.reshape(3, 3), t
+
+    def ResidualError(self, scale, R, t):
+        R, t = _f64(R).reshape(9), _f64(t).reshape(3)
+        e = C.c_double()
+        check(lib().mvs_srt_residual(self._h, C.c_double(scale), _ptr(R, C.c_double),
+                                     _ptr(t, C.c_double), C.byref(e)))
+        return e.value
+
+
+def srt_draw_triples(n: int, iter_num: int, seed: int):
+    out = np.empty((iter_num, 3), np.int32)
+    check(lib().mvs_srt_draw_triples(C.c_int64(n), C.c_int(iter_num), C.c_uint64(seed),
+                                     _ptr(out, C.c_int32)))
+    return out

@@ -1,0 +1,138 @@
+// common.cuh — context, error handling, device buffers, launch accounting shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mvs_b200.h"
+
+namespace mvs {
+
+void set_error(const char* fmt, ...);
+
+#define MVS_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::mvs::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return MVS_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define MVS_TRY(expr)          \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != MVS_OK) return _s; \
+  } while (0)
+
+#define MVS_REQUIRE(cond, msg)                         \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      ::mvs::set_error("%s: %s", __func__, msg);       \
+      return MVS_ERR_INVALID_ARG;                      \
+    }                                                  \
+  } while (0)
+
+constexpr int kNumSMsB200 = 148;
+
+struct ProfEntry {
+  double total_ms = 0.0;
+  int64_t launches = 0;
+};
+
+struct PendingProf {
+  std::string name;
+  cudaEvent_t start, stop;
+  int64_t launches;
+};
+
+}  // namespace mvs
+
+struct mvs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = mvs::kNumSMsB200;
+  int64_t launch_count = 0;
+  bool prof_on = false;
+  std::map<std::string, mvs::ProfEntry> prof;
+  std::vector<mvs::PendingProf> pending;
+  std::vector<cudaEvent_t> event_pool;
+  // pinned staging for small readbacks (reductions, scalars)
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  // NCCL communicator (opaque here; see comm.cu)
+  void* comm = nullptr;
+  int nranks = 1;
+  int rank = 0;
+};
+
+namespace mvs {
+
+int ctx_resolve_prof(mvs_ctx* ctx);
+int ctx_ensure_device(mvs_ctx* ctx);
+mvs_ctx* default_ctx();
+
+// RAII scope that (optionally) records CUDA events around a kernel family and counts launches.
+struct ProfScope {
+  mvs_ctx* ctx;
+  const char* name;
+  int64_t launches;
+  cudaEvent_t start = nullptr, stop = nullptr;
+  ProfScope(mvs_ctx* c, const char* n, int64_t nlaunch = 1);
+  ~ProfScope();
+};
+
+// Simple owning device buffer (typed), grows but never shrinks.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  int reserve(size_t n) {
+    if (n <= cap) return MVS_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)&p, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      p = nullptr;
+      return MVS_ERR_CUDA;
+    }
+    cap = n ? n : 1;
+    return MVS_OK;
+  }
+};
+
+inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Grid size for a grid-stride kernel: a multiple of the SM count, capped by the work available.
+inline int grid_for(const mvs_ctx* ctx, int64_t work_items, int block, int ctas_per_sm) {
+  int64_t need = (work_items + block - 1) / block;
+  int64_t full = (int64_t)ctx->num_sms * ctas_per_sm;
+  if (need >= full) return (int)full;
+  return (int)(need < 1 ? 1 : need);
+}
+
+int pinned_reserve(mvs_ctx* ctx, size_t bytes);
+
+// Host <-> device helpers on the context stream.
+int h2d(mvs_ctx* ctx, void* dst, const void* src, size_t bytes);
+int d2h_sync(mvs_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+}  // namespace mvs

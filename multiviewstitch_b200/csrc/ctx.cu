@@ -1,0 +1,260 @@
+// ctx.cu — context lifetime, error string, profiling scopes, launch accounting.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mvs {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ctx_ensure_device(mvs_ctx* ctx) {
+  if (!ctx) {
+    set_error("null context");
+    return MVS_ERR_INVALID_ARG;
+  }
+  MVS_CUDA(cudaSetDevice(ctx->device));
+  return MVS_OK;
+}
+
+static mvs_ctx* g_default = nullptr;
+static std::mutex g_default_mu;
+
+mvs_ctx* default_ctx() {
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  if (!g_default) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    mvs_ctx* c = nullptr;
+    if (mvs_ctx_create(&c, dev, nullptr) != MVS_OK) return nullptr;
+    g_default = c;
+  }
+  return g_default;
+}
+
+static cudaEvent_t take_event(mvs_ctx* ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  return e;
+}
+
+ProfScope::ProfScope(mvs_ctx* c, const char* n, int64_t nlaunch)
+    : ctx(c), name(n), launches(nlaunch) {
+  ctx->launch_count += nlaunch;
+  if (ctx->prof_on) {
+    start = take_event(ctx);
+    stop = take_event(ctx);
+    if (start) cudaEventRecord(start, ctx->stream);
+  }
+}
+
+ProfScope::~ProfScope() {
+  if (ctx->prof_on && start && stop) {
+    cudaEventRecord(stop, ctx->stream);
+    PendingProf p;
+    p.name = name;
+    p.start = start;
+    p.stop = stop;
+    p.launches = launches;
+    ctx->pending.push_back(p);
+  }
+}
+
+int ctx_resolve_prof(mvs_ctx* ctx) {
+  if (ctx->pending.empty()) return MVS_OK;
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.start, p.stop) == cudaSuccess) {
+      ProfEntry& e = ctx->prof[p.name];
+      e.total_ms += ms;
+      e.launches += p.launches;
+    }
+    ctx->event_pool.push_back(p.start);
+    ctx->event_pool.push_back(p.stop);
+  }
+  ctx->pending.clear();
+  return MVS_OK;
+}
+
+int pinned_reserve(mvs_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_bytes) return MVS_OK;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_bytes = 0;
+  size_t want = bytes < 4096 ? 4096 : bytes;
+  MVS_CUDA(cudaMallocHost(&ctx->pinned, want));
+  ctx->pinned_bytes = want;
+  return MVS_OK;
+}
+
+int h2d(mvs_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return MVS_OK;
+  MVS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return MVS_OK;
+}
+
+int d2h_sync(mvs_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes) MVS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return MVS_OK;
+}
+
+}  // namespace mvs
+
+extern "C" {
+
+const char* mvs_last_error(void) { return mvs::g_err; }
+
+int mvs_version(void) { return 100; }
+
+int mvs_device_count(int* count) {
+  if (!count) return MVS_ERR_INVALID_ARG;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  return MVS_OK;
+}
+
+int mvs_ctx_create(mvs_ctx** out, int device, void* stream) {
+  if (!out) return MVS_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    mvs::set_error(
+        "no CUDA device visible: this library has no CPU fallback (cudaGetDeviceCount: %s)",
+        e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    return MVS_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    mvs::set_error("device %d out of range (0..%d)", device, n - 1);
+    return MVS_ERR_INVALID_ARG;
+  }
+  MVS_CUDA(cudaSetDevice(device));
+  mvs_ctx* c = new mvs_ctx();
+  c->device = device;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
+  } else {
+    cudaError_t es = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (es != cudaSuccess) {
+      mvs::set_error("cudaStreamCreate: %s", cudaGetErrorString(es));
+      delete c;
+      return MVS_ERR_CUDA;
+    }
+    c->own_stream = true;
+  }
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+    c->num_sms = sms;
+  *out = c;
+  return MVS_OK;
+}
+
+int mvs_ctx_destroy(mvs_ctx* ctx) {
+  if (!ctx) return MVS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  mvs_comm_destroy(ctx);
+  for (auto& p : ctx->pending) {
+    cudaEventDestroy(p.start);
+    cudaEventDestroy(p.stop);
+  }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return MVS_OK;
+}
+
+int mvs_ctx_sync(mvs_ctx* ctx) {
+  MVS_TRY(mvs::ctx_ensure_device(ctx));
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_ctx_stream(mvs_ctx* ctx, void** stream) {
+  if (!ctx || !stream) return MVS_ERR_INVALID_ARG;
+  *stream = (void*)ctx->stream;
+  return MVS_OK;
+}
+
+int mvs_prof_enable(mvs_ctx* ctx, int on) {
+  if (!ctx) return MVS_ERR_INVALID_ARG;
+  if (!on) MVS_TRY(mvs::ctx_resolve_prof(ctx));
+  ctx->prof_on = on != 0;
+  return MVS_OK;
+}
+
+int mvs_prof_reset(mvs_ctx* ctx) {
+  if (!ctx) return MVS_ERR_INVALID_ARG;
+  MVS_TRY(mvs::ctx_resolve_prof(ctx));
+  ctx->prof.clear();
+  return MVS_OK;
+}
+
+int mvs_prof_get(mvs_ctx* ctx, const char* name, double* total_ms, int64_t* launches) {
+  if (!ctx || !name) return MVS_ERR_INVALID_ARG;
+  MVS_TRY(mvs::ctx_resolve_prof(ctx));
+  auto it = ctx->prof.find(name);
+  double ms = 0.0;
+  int64_t n = 0;
+  if (it != ctx->prof.end()) {
+    ms = it->second.total_ms;
+    n = it->second.launches;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  return MVS_OK;
+}
+
+int mvs_prof_names(mvs_ctx* ctx, char* buf, int64_t cap, int64_t* needed) {
+  if (!ctx) return MVS_ERR_INVALID_ARG;
+  MVS_TRY(mvs::ctx_resolve_prof(ctx));
+  std::string s;
+  for (auto& kv : ctx->prof) {
+    if (!s.empty()) s += "\n";
+    s += kv.first;
+  }
+  if (needed) *needed = (int64_t)s.size() + 1;
+  if (buf && cap > 0) {
+    size_t ncopy = s.size() < (size_t)(cap - 1) ? s.size() : (size_t)(cap - 1);
+    memcpy(buf, s.data(), ncopy);
+    buf[ncopy] = 0;
+  }
+  return MVS_OK;
+}
+
+int mvs_launch_count(mvs_ctx* ctx, int64_t* launches) {
+  if (!ctx || !launches) return MVS_ERR_INVALID_ARG;
+  *launches = ctx->launch_count;
+  return MVS_OK;
+}
+
+int mvs_launch_count_reset(mvs_ctx* ctx) {
+  if (!ctx) return MVS_ERR_INVALID_ARG;
+  ctx->launch_count = 0;
+  return MVS_OK;
+}
+
+}  // extern "C"
