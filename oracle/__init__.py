@@ -178,3 +178,114 @@ def sym_eig3(A):
     w, Q = np.empty(3), np.empty(9)
     lib().orc_sym_eig3(_p(A, C.c_double), _p(w, C.c_double), _p(Q, C.c_double))
     return w, Q.reshape(3, 3)
+
+
+# ----------------------------------------------------------------------------- deformation graph
+def uniform_sampling(pts, suppress_k=16):
+    pts = _f32(pts).reshape(-1, 3)
+    out = np.empty(len(pts), np.int32)
+    m = lib().orc_uniform_sampling(_p(pts, C.c_float), C.c_int64(len(pts)), C.c_int(suppress_k),
+                                   _p(out, C.c_int32))
+    return out[:m].copy()
+
+
+def sample_fps(pts, n_nodes, first=0):
+    pts = _f32(pts).reshape(-1, 3)
+    out = np.empty(n_nodes, np.int32)
+    m = lib().orc_sample_fps(_p(pts, C.c_float), C.c_int64(len(pts)), C.c_int64(n_nodes),
+                             C.c_int64(first), _p(out, C.c_int32))
+    return out[:m].copy()
+
+
+def node_graph(nodes, K=8):
+    nodes = _f32(nodes).reshape(-1, 3)
+    out = np.empty((len(nodes), K + 1), np.int32)
+    lib().orc_node_graph(_p(nodes, C.c_float), C.c_int64(len(nodes)), C.c_int(K), _p(out, C.c_int32))
+    return out
+
+
+def node_weights(pts, nodes, k=4):
+    pts, nodes = _f32(pts).reshape(-1, 3), _f32(nodes).reshape(-1, 3)
+    idx = np.empty((len(pts), k), np.int32)
+    w = np.empty((len(pts), k), np.float32)
+    lib().orc_node_weights(_p(pts, C.c_float), C.c_int64(len(pts)), _p(nodes, C.c_float),
+                           C.c_int64(len(nodes)), C.c_int(k), _p(idx, C.c_int32), _p(w, C.c_float))
+    return idx, w
+
+
+def node_targets(nodes, node_normals, tpts, tnormals, graph, proj_len_err=100.0,
+                 proj_dist_err=100.0, smooth_sweeps=2):
+    nodes, node_normals = _f32(nodes).reshape(-1, 3), _f32(node_normals).reshape(-1, 3)
+    tpts, tnormals = _f32(tpts).reshape(-1, 3), _f32(tnormals).reshape(-1, 3)
+    graph = _i32(graph)
+    m = len(nodes)
+    controls = np.empty((m, 3), np.float64)
+    valid = np.empty(m, np.int32)
+    lib().orc_node_targets(_p(nodes, C.c_float), _p(node_normals, C.c_float), C.c_int64(m),
+                           _p(tpts, C.c_float), _p(tnormals, C.c_float), C.c_int64(len(tpts)),
+                           C.c_double(proj_len_err), C.c_double(proj_dist_err),
+                           _p(graph, C.c_int32), C.c_int(graph.shape[1]), C.c_int(smooth_sweeps),
+                           _p(controls, C.c_double), _p(valid, C.c_int32))
+    return controls, valid
+
+
+def gn_assemble_dense(pts, node_ids, widx, w, graph, targets, tweights, prm, x):
+    pts = _f32(pts).reshape(-1, 3)
+    node_ids, widx, w, graph = _i32(node_ids), _i32(widx), _f32(w), _i32(graph)
+    targets = _f64(targets).reshape(-1, 3)
+    tweights = _f32(tweights) if tweights is not None else None
+    x = _f64(x).reshape(-1)
+    m = len(node_ids)
+    H = np.empty((12 * m, 12 * m), np.float64)
+    g = np.empty(12 * m, np.float64)
+    lib().orc_gn_assemble_dense(_p(pts, C.c_float), C.c_int64(len(pts)), _p(node_ids, C.c_int32),
+                                C.c_int64(m), _p(widx, C.c_int32), _p(w, C.c_float),
+                                _p(graph, C.c_int32), C.c_int(graph.shape[1]),
+                                _p(targets, C.c_double), _p(tweights, C.c_float), C.byref(prm),
+                                _p(x, C.c_double), _p(H, C.c_double), _p(g, C.c_double))
+    return H, g
+
+
+def gn_solve(pts, normals, node_ids, widx, w, graph, prm, x0=None, targets=None, tweights=None,
+             tpts=None, tnormals=None):
+    pts = _f32(pts).reshape(-1, 3)
+    normals = _f32(normals).reshape(-1, 3) if normals is not None else None
+    node_ids, widx, w, graph = _i32(node_ids), _i32(widx), _f32(w), _i32(graph)
+    m, n = len(node_ids), len(pts)
+    if x0 is None:
+        x = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float64), (m, 1))
+    else:
+        x = _f64(x0).reshape(m, 12).copy()
+    targets = _f64(targets).reshape(-1, 3) if targets is not None else None
+    tweights = _f32(tweights) if tweights is not None else None
+    tpts = _f32(tpts).reshape(-1, 3) if tpts is not None else None
+    tnormals = _f32(tnormals).reshape(-1, 3) if tnormals is not None else None
+    out = np.empty((n, 3), np.float64)
+    energy = np.zeros(3, np.float64)
+    lib().orc_gn_solve(_p(pts, C.c_float), _p(normals, C.c_float), C.c_int64(n),
+                       _p(node_ids, C.c_int32), C.c_int64(m), _p(widx, C.c_int32),
+                       _p(w, C.c_float), _p(graph, C.c_int32), C.c_int(graph.shape[1]),
+                       _p(targets, C.c_double), _p(tweights, C.c_float), _p(tpts, C.c_float),
+                       _p(tnormals, C.c_float), C.c_int64(len(tpts) if tpts is not None else 0),
+                       C.byref(prm), _p(x, C.c_double), _p(out, C.c_double),
+                       _p(energy, C.c_double))
+    return x, out, energy
+
+
+def deform_vertices(pts, nodes, widx, w, x):
+    pts, nodes = _f32(pts).reshape(-1, 3), _f32(nodes).reshape(-1, 3)
+    widx, w, x = _i32(widx), _f32(w), _f64(x).reshape(-1)
+    out = np.empty((len(pts), 3), np.float64)
+    lib().orc_deform_vertices(_p(pts, C.c_float), C.c_int64(len(pts)), _p(nodes, C.c_float),
+                              C.c_int64(len(nodes)), _p(widx, C.c_int32), _p(w, C.c_float),
+                              _p(x, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def vertex_normals(pts, facets):
+    pts = _f64(pts).reshape(-1, 3)
+    facets = _i32(facets).reshape(-1, 3)
+    out = np.empty_like(pts)
+    lib().orc_vertex_normals(_p(pts, C.c_double), C.c_int64(len(pts)), _p(facets, C.c_int32),
+                             C.c_int64(len(facets)), _p(out, C.c_double))
+    return out

@@ -1,0 +1,187 @@
+"""CPU tests pinning the deformation-graph oracle (oracle/deform.cpp).
+
+No reference lines exist for the Gauss-Newton solve (the reference hands the nodes to CGAL ARAP),
+so the formulation of SURVEY.md §8(a) D7-D9 is pinned here by an INDEPENDENT numpy statement of the
+energy: finite-difference gradient/Gauss-Newton Hessian, and scipy's sparse direct solve for PCG.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import oracle
+from tests import synth
+
+
+def small_problem(nu=24, nv=16, m=24, seed=0):
+    verts, faces = synth.uv_sphere(nu, nv)
+    pts = verts.astype(np.float32)
+    ids = oracle.sample_fps(pts, m, 0)
+    nodes = pts[ids]
+    widx, w = oracle.node_weights(pts, nodes, 4)
+    graph = oracle.node_graph(nodes, 8)
+    return pts, faces, ids, nodes, widx, w, graph
+
+
+def numpy_residuals(x, pts, nodes, widx, w, graph, targets, tw, prm):
+    """Stacked weighted residual vector of the D7 energy, written independently in numpy."""
+    m = len(nodes)
+    X = x.reshape(m, 12)
+    A = np.stack([X[:, 0:3], X[:, 3:6], X[:, 6:9]], axis=2)  # A[j][:, c] = column c
+    t = X[:, 9:12]
+    p = pts.astype(np.float64)
+    g = nodes.astype(np.float64)
+    vt = np.zeros_like(p)
+    for a in range(4):
+        j = widx[:, a]
+        d = p - g[j]
+        vt += w[:, a:a + 1].astype(np.float64) * (np.einsum("nrc,nc->nr", A[j], d) + g[j] + t[j])
+    om = np.ones(len(p)) if tw is None else tw.astype(np.float64)
+    r_fit = (np.sqrt(prm.w_fit * om)[:, None] * (vt - targets)).ravel()
+    a1, a2, a3 = A[:, :, 0], A[:, :, 1], A[:, :, 2]
+    dot = lambda u, v: np.sum(u * v, 1)
+    r_rot = np.sqrt(prm.w_rot) * np.stack(
+        [dot(a1, a2), dot(a1, a3), dot(a2, a3), dot(a1, a1) - 1, dot(a2, a2) - 1, dot(a3, a3) - 1], 1).ravel()
+    r_reg = []
+    for j in range(m):
+        for l in graph[j]:
+            if l < 0 or l == j:
+                continue
+            e = g[l] - g[j]
+            r_reg.append(np.sqrt(prm.w_reg) * (A[j] @ e + g[j] + t[j] - g[l] - t[l]))
+    return np.concatenate([r_fit, r_rot, np.concatenate(r_reg)])
+
+
+def test_fps_and_uniform_sampling_properties():
+    pts, *_ = small_problem()
+    ids = oracle.sample_fps(pts, 20, 3)
+    assert ids[0] == 3 and len(set(ids.tolist())) == 20
+    # numpy re-derivation of FPS with float32 distances
+    mind = np.full(len(pts), np.inf, np.float32)
+    cur, ref = 3, []
+    for _ in range(20):
+        ref.append(cur)
+        d = pts - pts[cur]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + (d[:, 2] * d[:, 2]).astype(np.float32)
+        mind = np.minimum(mind, d2.astype(np.float32))
+        cur = int(np.argmax(mind))
+    assert ids.tolist() == ref
+    # Deformation.cpp:63-106: kept nodes are never within each other's 16-NN *at selection time*
+    s = oracle.uniform_sampling(pts, 16)
+    assert s[0] == 0 and np.all(np.diff(s) > 0)
+    nn, _ = oracle.knn(pts, pts, 16, "kdtree")
+    removed = np.zeros(len(pts), bool)
+    ref = []
+    for i in range(len(pts)):
+        if not removed[i]:
+            ref.append(i)
+            removed[nn[i][nn[i] != i]] = True
+    assert s.tolist() == ref
+
+
+def test_node_weights_properties():
+    pts, faces, ids, nodes, widx, w, graph = small_problem()
+    assert np.allclose(w.sum(1), 1.0, atol=1e-6) and np.all(w >= 0)
+    i5, d5 = oracle.knn(pts, nodes, 5, "kdtree")
+    assert np.array_equal(widx, i5[:, :4])
+    d = np.sqrt(d5)
+    wr = (1 - d[:, :4] / d[:, 4:5]) ** 2
+    wr /= wr.sum(1, keepdims=True)
+    assert np.allclose(w, wr, atol=1e-5)
+    # a node's own vertex has itself as nearest node
+    assert np.array_equal(widx[ids, 0], np.arange(len(ids)))
+    assert np.array_equal(graph[:, 0], np.arange(len(ids)))  # Deformation.cpp:108-153 includes self
+
+
+def test_gn_normal_equations_match_finite_differences():
+    pts, faces, ids, nodes, widx, w, graph = small_problem(m=12)
+    rng = np.random.default_rng(1)
+    m = len(ids)
+    prm = oracle.gn_params(w_rot=1.0, w_reg=10.0, w_fit=100.0, lam=0.0)
+    x = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (m, 1)) + 0.05 * rng.normal(size=(m, 12))
+    targets = synth.bend_twist(pts.astype(np.float64), 0.05)
+    tw = (rng.random(len(pts)) > 0.2).astype(np.float32)
+    H, g = oracle.gn_assemble_dense(pts, ids, widx, w, graph, targets, tw, prm, x)
+    f = lambda xx: numpy_residuals(xx, pts, nodes, widx, w, graph, targets, tw, prm)
+    r0 = f(x.ravel())
+    J = np.empty((len(r0), 12 * m))
+    eps = 1e-6
+    for k in range(12 * m):
+        xp = x.ravel().copy(); xp[k] += eps
+        xm = x.ravel().copy(); xm[k] -= eps
+        J[:, k] = (f(xp) - f(xm)) / (2 * eps)
+    assert np.allclose(H, J.T @ J, rtol=1e-6, atol=1e-6 * np.abs(H).max())
+    assert np.allclose(g, J.T @ r0, rtol=1e-6, atol=1e-6 * np.abs(g).max())
+    assert np.allclose(H, H.T, atol=1e-12 * np.abs(H).max())
+
+
+def test_gn_pcg_converges_to_direct_solve_and_energy_decreases():
+    pts, faces, ids, nodes, widx, w, graph = small_problem(m=24)
+    m = len(ids)
+    targets = synth.bend_twist(pts.astype(np.float64), 0.05)
+    x0 = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (m, 1))
+    prm = oracle.gn_params(gn_iters=1, pcg_iters=400, lam=1e-6)
+    H, g = oracle.gn_assemble_dense(pts, ids, widx, w, graph, targets, None, prm, x0)
+    delta = spla.spsolve(sp.csc_matrix(H), -g)
+    x1, out, en = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, x0, targets=targets)
+    assert np.allclose(x1.ravel() - x0.ravel(), delta, rtol=1e-6, atol=1e-8)
+    # energies over GN iterations decrease monotonically with enough PCG iterations
+    energies = []
+    for it in range(1, 5):
+        prm = oracle.gn_params(gn_iters=it, pcg_iters=200)
+        _, _, e = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, x0, targets=targets)
+        energies.append(e.sum())
+    assert all(b <= a * (1 + 1e-9) for a, b in zip(energies, energies[1:]))
+    # identity target => zero update
+    prm = oracle.gn_params(gn_iters=2, pcg_iters=20)
+    xi, outi, ei = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, x0, targets=pts.astype(np.float64))
+    assert np.allclose(xi, x0, atol=1e-6) and np.allclose(outi, pts, atol=1e-6)  # float32 weights sum to 1 within 1e-7
+
+
+def test_gn_recovers_rigid_motion():
+    pts, faces, ids, nodes, widx, w, graph = small_problem(m=24)
+    R = synth.axis_angle([0.2, 1.0, 0.1], 0.3)
+    tt = np.array([0.1, -0.05, 0.2])
+    targets = pts.astype(np.float64) @ R.T + tt
+    prm = oracle.gn_params(gn_iters=8, pcg_iters=200)
+    x, out, e = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, targets=targets)
+    assert np.abs(out - targets).max() < 1e-4
+    A = x.reshape(-1, 12)[:, :9].reshape(-1, 3, 3).transpose(0, 2, 1)  # columns -> matrix
+    assert np.allclose(A, R[None], atol=1e-3)
+
+
+def test_node_targets_rules():
+    # template = sphere r=1, target = sphere r=1.1 (denser): each node's target lies radially out
+    verts, faces = synth.uv_sphere(40, 30, bumps=0.0)
+    nodes = verts[::37].astype(np.float32)
+    nn = nodes / np.linalg.norm(nodes, axis=1, keepdims=True)
+    tv, tf = synth.uv_sphere(120, 90, radius=1.1, bumps=0.0)
+    tn = tv / np.linalg.norm(tv, axis=1, keepdims=True)
+    graph = oracle.node_graph(nodes, 8)
+    ctrl, valid = oracle.node_targets(nodes, nn, tv, tn, graph, 100.0, 100.0, smooth_sweeps=0)
+    assert valid.mean() > 0.9
+    v = valid.astype(bool)
+    assert np.allclose(np.linalg.norm(ctrl[v], axis=1), 1.1, atol=0.02)
+    cosang = np.sum(ctrl[v] * nn[v], 1) / np.linalg.norm(ctrl[v], axis=1)
+    assert np.all(cosang > 0.99)
+    # normal compatibility (Deformation.cpp:306-312): flipped target normals => nothing valid
+    ctrl2, valid2 = oracle.node_targets(nodes, nn, tv, -tn, graph, 100.0, 100.0, 0)
+    assert valid2.sum() == 0 and np.allclose(ctrl2, nodes)
+    # thresholds (:350)
+    _, valid3 = oracle.node_targets(nodes, nn, tv, tn, graph, 0.05, 100.0, 0)
+    assert valid3.sum() == 0
+    # smoothing (:359-381): numpy re-derivation of the 2 Jacobi sweeps
+    ctrl0, _ = oracle.node_targets(nodes, nn, tv, tn, graph, 100.0, 100.0, 0)
+    ctrl_s, _ = oracle.node_targets(nodes, nn, tv, tn, graph, 100.0, 100.0, 2)
+    c = ctrl0.copy(); o = nodes.astype(np.float64)
+    for _ in range(2):
+        c = o + (c - o)[graph].sum(1) / 9.0
+    assert np.allclose(ctrl_s, c, atol=1e-12)
+
+
+def test_vertex_normals_sphere():
+    verts, faces = synth.uv_sphere(48, 32, bumps=0.0)
+    n = oracle.vertex_normals(verts, faces)
+    radial = verts / np.linalg.norm(verts, axis=1, keepdims=True)
+    assert np.all(np.sum(n * radial, 1) > 0.99)
+    assert np.allclose(n, synth.vertex_normals(verts, faces), atol=1e-12)
