@@ -260,10 +260,12 @@ int mvs_deform_get_normals(mvs_deform* h, double* normals_xyz);
 int mvs_deform_get_vertices_f32(mvs_deform* h, float* pts_xyz);
 int mvs_deform_get_facets(mvs_deform* h, int32_t* facets, int64_t* n_facets);
 int mvs_deform_export_obj(mvs_deform* h, const char* filename);
-/* Assembled normal equations of the last GN step, for tests: diag m x 144, rhs m x 12,
- * block-CSR row_ptr (m+1), col (nnz), blocks nnz x 16 (Kronecker-compressed 4x4). */
-int mvs_deform_get_system(mvs_deform* h, float* diag, float* rhs, int32_t* row_ptr, int32_t* col,
-                          float* blocks, int64_t* nnz);
+/* Assembled normal equations of the last GN step (tests / inspection), Kronecker-compressed:
+ * block-CSR row_ptr (m+1), col (nnz, ascending, diagonal included), blocks nnz x 16 (4x4 factors
+ * B_jl with H_jl = kron(B_jl, I3)), rot m x 81 (dense 9x9 rotation-term blocks), rhs m x 12
+ * (J^T r).  Any pointer may be NULL; *nnz receives the block count. */
+int mvs_deform_get_system(mvs_deform* h, int32_t* row_ptr, int32_t* col, float* blocks, float* rot,
+                          float* rhs, int64_t* nnz);
 
 /* ---------------------------------------------------------------- Model2Depth -------------- */
 /* [ref: Model2Depth/Model2Depth.h:17-54 SetInput/Run, Model2Depth.cpp:93-156] z-buffer render of a

@@ -298,3 +298,203 @@ def srt_draw_triples(n: int, iter_num: int, seed: int):
     check(lib().mvs_srt_draw_triples(C.c_int64(n), C.c_int(iter_num), C.c_uint64(seed),
                                      _ptr(out, C.c_int32)))
     return out
+
+
+# ============================================================================ deformation
+def gn_params(**kw) -> GNParams:
+    """mvs_gn_params with the library defaults, overridden by keyword."""
+    p = GNParams()
+    check(lib().mvs_gn_default_params(C.byref(p)))
+    for k, v in kw.items():
+        if k == "lambda_":
+            k = "lam"
+        if not hasattr(p, k):
+            raise TypeError(f"unknown GN parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+class Deformation:
+    """[ref: Deformation/Deformation.h:224-252]  Deformation(points, normals, facets);
+    UniformSampling(); Deform(tpts, tnormals, projLenErr, projDistErr) / Deform(tpts, tnormals,
+    threshold); the CGAL Polyhedron() accessor is replaced by Vertices()/Normals()/Facets()."""
+
+    def __init__(self, points, normals, facets, ctx: Context | None = None):
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        points = np.asarray(points)
+        f = _i32(facets).reshape(-1) if facets is not None else None
+        nf = 0 if f is None else len(f) // 3
+        if points.dtype == np.float32:
+            p = _f32(points).reshape(-1, 3)
+            nr = _f32(normals).reshape(-1, 3) if normals is not None else None
+            check(lib().mvs_deform_create_f32(_ctxh(ctx), _ptr(p, C.c_float), _ptr(nr, C.c_float),
+                                              C.c_int64(len(p)), _ptr(f, C.c_int32), C.c_int64(nf),
+                                              C.byref(self._h)))
+        else:
+            p = _f64(points).reshape(-1, 3)
+            nr = _f64(normals).reshape(-1, 3) if normals is not None else None
+            check(lib().mvs_deform_create(_ctxh(ctx), _ptr(p, C.c_double), _ptr(nr, C.c_double),
+                                          C.c_int64(len(p)), _ptr(f, C.c_int32), C.c_int64(nf),
+                                          C.byref(self._h)))
+        self.n = len(p)
+        self.nf = nf
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            lib().mvs_deform_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- nodes / graph
+    def UniformSampling(self, suppress_k: int = 16):
+        check(lib().mvs_deform_uniform_sampling(self._h, C.c_int(suppress_k)))
+        return self.Nodes()
+
+    def SampleFPS(self, n_nodes: int, first_vertex: int = 0):
+        check(lib().mvs_deform_sample_fps(self._h, C.c_int64(n_nodes), C.c_int64(first_vertex)))
+        return self.Nodes()
+
+    def SetNodes(self, ids):
+        ids = _i32(ids)
+        check(lib().mvs_deform_set_nodes(self._h, _ptr(ids, C.c_int32), C.c_int64(len(ids))))
+
+    def Nodes(self):
+        m = C.c_int64(0)
+        check(lib().mvs_deform_get_nodes(self._h, None, C.c_int64(0), C.byref(m)))
+        out = np.empty(m.value, np.int32)
+        check(lib().mvs_deform_get_nodes(self._h, _ptr(out, C.c_int32), C.c_int64(m.value), C.byref(m)))
+        return out
+
+    def BuildGraph(self, node_k: int = 4, graph_k: int = 8):
+        check(lib().mvs_deform_build_graph(self._h, C.c_int(node_k), C.c_int(graph_k)))
+        self._graph_k = graph_k
+
+    def Weights(self):
+        idx = np.empty((self.n, 4), np.int32)
+        w = np.empty((self.n, 4), np.float32)
+        check(lib().mvs_deform_get_weights(self._h, _ptr(idx, C.c_int32), _ptr(w, C.c_float)))
+        return idx, w
+
+    def KNearestNeighbor(self, K: int = 8):
+        """[ref: Deformation/Deformation.cpp:108-153] node graph, (K+1) nearest incl. self."""
+        self.BuildGraph(4, K)
+        out = np.empty((len(self.Nodes()), K + 1), np.int32)
+        check(lib().mvs_deform_get_graph(self._h, _ptr(out, C.c_int32)))
+        return out
+
+    # ---- targets
+    def SetTarget(self, tpts, tnormals=None):
+        tpts = np.asarray(tpts)
+        if tpts.dtype == np.float32:
+            p = _f32(tpts).reshape(-1, 3)
+            nr = _f32(tnormals).reshape(-1, 3) if tnormals is not None else None
+            check(lib().mvs_deform_set_target_f32(self._h, _ptr(p, C.c_float), _ptr(nr, C.c_float),
+                                                  C.c_int64(len(p))))
+        else:
+            p = _f64(tpts).reshape(-1, 3)
+            nr = _f64(tnormals).reshape(-1, 3) if tnormals is not None else None
+            check(lib().mvs_deform_set_target(self._h, _ptr(p, C.c_double), _ptr(nr, C.c_double),
+                                              C.c_int64(len(p))))
+
+    def SetTargetDev(self, tpts_ptr: int, tnormals_ptr: int | None, nt: int):
+        check(lib().mvs_deform_set_target_dev_f32(self._h, _dev(tpts_ptr),
+                                                  _dev(tnormals_ptr) if tnormals_ptr else None,
+                                                  C.c_int64(nt)))
+
+    def SetTargets(self, targets, weights=None):
+        t = _f64(targets).reshape(-1, 3)
+        w = _f32(weights) if weights is not None else None
+        check(lib().mvs_deform_set_targets(self._h, _ptr(t, C.c_double), _ptr(w, C.c_float),
+                                           C.c_int64(len(t))))
+
+    def NodeTargets(self, projLenErr=100.0, projDistErr=100.0, smooth_sweeps=2):
+        m = len(self.Nodes())
+        c = np.empty((m, 3), np.float64)
+        v = np.empty(m, np.int32)
+        check(lib().mvs_deform_node_targets(self._h, C.c_double(projLenErr), C.c_double(projDistErr),
+                                            C.c_int(smooth_sweeps), _ptr(c, C.c_double),
+                                            _ptr(v, C.c_int32)))
+        return c, v
+
+    # ---- Deform
+    def Deform(self, tpts, tnormals, *args, params: GNParams | None = None):
+        """Deform(tpts, tnormals, threshold) [ref: Deformation.cpp:155-230] or
+        Deform(tpts, tnormals, projLenErr, projDistErr) [ref: :232-402]."""
+        if tpts is not None:
+            self.SetTarget(tpts, tnormals)
+        pp = C.byref(params) if params is not None else None
+        if len(args) == 1:
+            check(lib().mvs_deform_run_threshold(self._h, C.c_double(args[0]), pp))
+        elif len(args) == 2:
+            check(lib().mvs_deform_run(self._h, C.c_double(args[0]), C.c_double(args[1]), pp))
+        else:
+            raise TypeError("Deform(tpts, tnormals, threshold) or Deform(tpts, tnormals, "
+                            "projLenErr, projDistErr)")
+
+    def GNBegin(self, params: GNParams):
+        check(lib().mvs_deform_gn_begin(self._h, C.byref(params)))
+
+    def GNStep(self):
+        check(lib().mvs_deform_gn_step(self._h))
+
+    def GNEnd(self):
+        check(lib().mvs_deform_gn_end(self._h))
+
+    def Energy(self):
+        e = np.zeros(3, np.float64)
+        check(lib().mvs_deform_get_energy(self._h, _ptr(e, C.c_double)))
+        return e
+
+    def NodeState(self):
+        x = np.empty((len(self.Nodes()), 12), np.float32)
+        check(lib().mvs_deform_get_node_state(self._h, _ptr(x, C.c_float)))
+        return x
+
+    def SetNodeState(self, x):
+        x = _f32(x).reshape(-1, 12)
+        check(lib().mvs_deform_set_node_state(self._h, _ptr(x, C.c_float)))
+
+    def System(self):
+        m = len(self.Nodes())
+        nnz = C.c_int64(0)
+        check(lib().mvs_deform_get_system(self._h, None, None, None, None, None, C.byref(nnz)))
+        rp = np.empty(m + 1, np.int32)
+        col = np.empty(nnz.value, np.int32)
+        B = np.empty((nnz.value, 4, 4), np.float32)
+        rot = np.empty((m, 9, 9), np.float32)
+        rhs = np.empty((m, 12), np.float32)
+        check(lib().mvs_deform_get_system(self._h, _ptr(rp, C.c_int32), _ptr(col, C.c_int32),
+                                          _ptr(B, C.c_float), _ptr(rot, C.c_float),
+                                          _ptr(rhs, C.c_float), C.byref(nnz)))
+        return rp, col, B, rot, rhs
+
+    def SetShard(self, v_begin: int, v_end: int):
+        check(lib().mvs_deform_set_shard(self._h, C.c_int64(v_begin), C.c_int64(v_end)))
+
+    # ---- results
+    def Vertices(self):
+        out = np.empty((self.n, 3), np.float64)
+        check(lib().mvs_deform_get_vertices(self._h, _ptr(out, C.c_double)))
+        return out
+
+    def Normals(self):
+        out = np.empty((self.n, 3), np.float64)
+        check(lib().mvs_deform_get_normals(self._h, _ptr(out, C.c_double)))
+        return out
+
+    def Facets(self):
+        out = np.empty((self.nf, 3), np.int32)
+        check(lib().mvs_deform_get_facets(self._h, _ptr(out, C.c_int32), None))
+        return out
+
+
+def exportOBJ(filename: str, deform: Deformation):
+    """[ref: Deformation/Deformation.h:174-221]"""
+    check(lib().mvs_deform_export_obj(deform._h, filename.encode()))

@@ -1,0 +1,106 @@
+// deform.cuh — device-resident state of one Deformation object (Deformation/Deformation.h:224-252)
+// and the internal interfaces between deform_graph.cu (graph construction, correspondences),
+// gn_assemble.cu (per-vertex passes + normal-equation assembly), pcg.cu (solver) and
+// deform_api.cu (C ABI).
+//
+// Data layout in HBM (all float32, 16-byte records, SoA across arrays):
+//   v[n], nrm[n]          float4  rest vertices / normals in SORTED order: vertices are permuted
+//                                 once at graph-build time so that vertices sharing the same
+//                                 4-node set are adjacent (key = primary node | tuple hash);
+//                                 perm[i] = original vertex id of sorted position i
+//   vidx[n] int4, vw[n] float4    the k=4 nearest nodes of each vertex (ascending node id) and
+//                                 their normalised weights w = (1 - d/d_max)^2
+//   resid[n] float4               (deformed - target, omega) written by the correspondence pass
+//   g[m], gnrm[m] float4          node positions / normals;  x[m][12] node state (a1,a2,a3,t)
+//   normal equations, Kronecker-compressed:  one contiguous float buffer
+//       sys = [ B: nnz x 16 | rhs: m x 12 | Rot: m x 81 ]
+//   block-CSR pattern row_ptr[m+1], col[nnz] (ascending, diagonal included)
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "nn_grid.cuh"
+
+struct mvs_deform {
+  mvs_ctx* ctx = nullptr;
+  int64_t n = 0, nf = 0, m = 0;
+  // original-order inputs
+  mvs::DevBuf<float4> v0, nrm0;  // rest vertices / normals, original order
+  mvs::DevBuf<int> facets;       // 3*nf, original vertex ids
+  // nodes
+  std::vector<int32_t> node_ids;
+  mvs::DevBuf<int> node_ids_d;
+  mvs::DevBuf<float4> g, gnrm;
+  mvs_nn_index* node_index = nullptr;
+  int node_k = 4, graph_k = 8;
+  bool graph_built = false;
+  // sorted per-vertex data
+  mvs::DevBuf<int> perm;      // sorted position -> original id
+  mvs::DevBuf<int> inv_perm;  // original id -> sorted position
+  mvs::DevBuf<float4> v, nrm;
+  mvs::DevBuf<int4> vidx;
+  mvs::DevBuf<float4> vw;
+  mvs::DevBuf<int4> vidx_knn;  // kNN order (nearest first), original vertex order — API view
+  mvs::DevBuf<float4> vw_knn;
+  mvs::DevBuf<int> graph;  // m x (graph_k+1)
+  // pattern + system
+  mvs::DevBuf<int> row_ptr, col;
+  int64_t nnz = 0;
+  mvs::DevBuf<float> sys;
+  mvs::DevBuf<float> Minv;  // m x 144
+  mvs::DevBuf<float> x;     // m x 12
+  mvs::DevBuf<float> pcg;   // r, z, p0, p1, q, delta : 6 x m x 12
+  mvs::DevBuf<double> scal; // PCG scalars + energies
+  mvs::DevBuf<double> partials;
+  mvs::DevBuf<unsigned> ticket;
+  // target scan
+  mvs_nn_index* tgt_index = nullptr;
+  mvs::DevBuf<float4> tp_own, tn_own;
+  const float4* tp = nullptr;
+  const float4* tn = nullptr;
+  int64_t nt = 0;
+  // per-vertex work arrays (sorted order)
+  mvs::DevBuf<float4> resid;    // (v~ - c, omega)
+  mvs::DevBuf<float4> targets;  // (c, omega) for fixed-target modes
+  bool have_targets = false;
+  mvs::DevBuf<float4> cur0;     // deformed vertices, ORIGINAL order
+  mvs::DevBuf<float4> curn0;    // deformed normals, original order
+  bool cur_valid = false;
+  // solver run state
+  mvs_gn_params prm{};
+  bool gn_active = false;
+  int64_t v_begin = 0, v_end = -1;  // shard of sorted positions owned by this rank
+  double energy[3] = {0, 0, 0};
+
+  float* B() { return sys.p; }
+  // rhs before Rot: m*81 floats would break the 16-byte alignment the vector reductions need
+  float* rhs() { return sys.p + (size_t)nnz * 16; }
+  float* Rot() { return sys.p + (size_t)nnz * 16 + (size_t)m * 12; }
+  size_t sys_floats() const { return (size_t)nnz * 16 + (size_t)m * 81 + (size_t)m * 12; }
+  int64_t shard_begin() const { return v_begin; }
+  int64_t shard_end() const { return v_end < 0 ? n : v_end; }
+};
+
+namespace mvs {
+
+// scal[] slots
+enum { S_RZ = 0, S_PQ = 1, S_RZ_NEW = 2, S_BNORM2 = 3, S_RNORM2 = 4, S_EFIT = 8, S_EROT = 9,
+       S_EREG = 10, S_SIZE = 16 };
+
+// deform_graph.cu
+int deform_build_graph(mvs_deform* h, int node_k, int graph_k);
+int deform_node_targets(mvs_deform* h, double proj_len_err, double proj_dist_err,
+                        int smooth_sweeps, DevBuf<double>& controls, DevBuf<int>& valid);
+
+// gn_assemble.cu
+int gn_reset_state(mvs_deform* h);
+int gn_deform_and_correspond(mvs_deform* h);   // writes resid (mode 1: NN; else fixed targets)
+int gn_assemble(mvs_deform* h);                 // zero + fit pass (+ allreduce) + node terms + precond
+int gn_apply_update(mvs_deform* h);             // x += delta
+int gn_final_vertices(mvs_deform* h);           // cur0 / curn0 in original order
+int gn_energy(mvs_deform* h, double energy[3]); // at the current state with the current resid
+
+// pcg.cu
+int pcg_solve(mvs_deform* h);
+
+}  // namespace mvs

@@ -1,0 +1,658 @@
+// deform_api.cu — C ABI of the Deformation object (Deformation/Deformation.h:224-252): lifetime,
+// target upload, the Deform() drivers and the getters.  All arithmetic lives in deform_graph.cu,
+// gn_assemble.cu and pcg.cu.
+#include <stdio.h>
+
+#include <cmath>
+
+#include "deform.cuh"
+
+namespace mvs {
+
+__global__ void k_f4_to_f64xyz(const float4* __restrict__ in, double* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = in[i];
+  out[3 * i] = p.x;
+  out[3 * i + 1] = p.y;
+  out[3 * i + 2] = p.z;
+}
+__global__ void k_f4_to_f32xyz(const float4* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = in[i];
+  out[3 * i] = p.x;
+  out[3 * i + 1] = p.y;
+  out[3 * i + 2] = p.z;
+}
+
+// targets (original vertex order: xyz doubles + float weight) -> sorted float4 (c, omega)
+__global__ void k_targets_permute(const double* __restrict__ t, const float* __restrict__ w,
+                                  const int* __restrict__ perm, int64_t n,
+                                  float4* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int o = perm[i];
+  float om = w ? w[o] : 1.0f;
+  out[i] = make_float4((float)t[3 * (size_t)o], (float)t[3 * (size_t)o + 1],
+                       (float)t[3 * (size_t)o + 2], om);
+}
+
+// node controls (m x 3 doubles) -> per-vertex targets on the node vertices only
+__global__ void k_targets_from_nodes(const double* __restrict__ controls,
+                                     const int* __restrict__ valid, int only_valid,
+                                     const int* __restrict__ node_ids,
+                                     const int* __restrict__ inv_perm, int64_t m,
+                                     float4* __restrict__ targets) {
+  int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  if (only_valid && !valid[j]) return;
+  int pos = inv_perm[node_ids[j]];
+  targets[pos] = make_float4((float)controls[3 * j], (float)controls[3 * j + 1],
+                             (float)controls[3 * j + 2], 1.0f);
+}
+
+// Deformation/Deformation.cpp:186-203: 1-NN target of each node; keep if d2 <= threshold and
+// cos(dir, normal) >= 0.5 (the 6-D tree has scale = 0, i.e. it is a plain position search).
+__global__ void k_node_targets_threshold(GridParams tg, const float4* __restrict__ tsorted,
+                                         const int* __restrict__ cell_start,
+                                         const float4* __restrict__ g,
+                                         const float4* __restrict__ gnrm, int64_t m,
+                                         float threshold, double* __restrict__ controls,
+                                         int* __restrict__ valid) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  float4 q = g[i];
+  float4 nq = gnrm[i];
+  valid[i] = 0;
+  controls[3 * i] = q.x;
+  controls[3 * i + 1] = q.y;
+  controls[3 * i + 2] = q.z;
+  KnnList<1> nn;
+  nn.init(q.x, q.y, q.z);
+  struct V {
+    KnnList<1>* l;
+    float cx, cy, cz;
+    __device__ float worst2() const { return l->worst2(); }
+    __device__ void point(float4 p) {
+      float before = l->d2[0];
+      int bi = l->idx[0];
+      l->point(p);
+      if (l->d2[0] != before || l->idx[0] != bi) {
+        cx = p.x; cy = p.y; cz = p.z;
+      }
+    }
+  } vis{&nn, 0.f, 0.f, 0.f};
+  grid_search(tg, cell_start, tsorted, q.x, q.y, q.z, vis);
+  if (nn.d2[0] > threshold) return;
+  double d0 = __dsub_rn((double)vis.cx, (double)q.x), d1 = __dsub_rn((double)vis.cy, (double)q.y),
+         d2 = __dsub_rn((double)vis.cz, (double)q.z);
+  double n0 = nq.x, n1 = nq.y, n2 = nq.z;
+  double dot = __dadd_rn(__dadd_rn(__dmul_rn(d0, n0), __dmul_rn(d1, n1)), __dmul_rn(d2, n2));
+  double dl = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
+  double nl = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1)), __dmul_rn(n2, n2)));
+  double c = __ddiv_rn(dot, __dmul_rn(dl, nl));
+  if (c < 0.5) return;  // NaN (dl == 0) compares false, as in the reference
+  valid[i] = 1;
+  controls[3 * i] = vis.cx;
+  controls[3 * i + 1] = vis.cy;
+  controls[3 * i + 2] = vis.cz;
+}
+
+static int ensure_graph(mvs_deform* h) {
+  if (h->m <= 0) {
+    // Deformation.cpp:248-250: sample when no nodes exist yet
+    MVS_TRY(mvs_deform_uniform_sampling(h, 16));
+  }
+  if (!h->graph_built) MVS_TRY(deform_build_graph(h, h->node_k, h->graph_k));
+  return MVS_OK;
+}
+
+static int validate_params(const mvs_gn_params* p) {
+  if (!p) {
+    set_error("null mvs_gn_params");
+    return MVS_ERR_INVALID_ARG;
+  }
+  if (p->gn_iters < 0 || p->pcg_iters < 0 || p->corr_mode < 0 || p->corr_mode > 2 ||
+      !(p->w_fit >= 0) || !(p->w_rot >= 0) || !(p->w_reg >= 0) || !(p->lambda >= 0)) {
+    set_error("invalid mvs_gn_params");
+    return MVS_ERR_INVALID_ARG;
+  }
+  return MVS_OK;
+}
+
+static int gn_begin_impl(mvs_deform* h, const mvs_gn_params* p) {
+  MVS_TRY(validate_params(p));
+  MVS_TRY(ensure_graph(h));
+  h->prm = *p;
+  MVS_TRY(gn_reset_state(h));
+  h->gn_active = true;
+  h->cur_valid = false;
+  return MVS_OK;
+}
+
+static int gn_step_impl(mvs_deform* h) {
+  MVS_TRY(gn_deform_and_correspond(h));
+  MVS_TRY(gn_assemble(h));
+  MVS_TRY(pcg_solve(h));
+  MVS_TRY(gn_apply_update(h));
+  return MVS_OK;
+}
+
+// overwrite_initial_geometry() (Deformation.cpp:400): the deformed mesh becomes the rest mesh
+static int bake(mvs_deform* h) {
+  mvs_ctx* ctx = h->ctx;
+  int64_t n = h->n;
+  MVS_CUDA(cudaMemcpyAsync(h->v0.p, h->cur0.p, sizeof(float4) * n, cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  if (h->nf > 0)
+    MVS_CUDA(cudaMemcpyAsync(h->nrm0.p, h->curn0.p, sizeof(float4) * n, cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+  h->graph_built = false;  // rebuilt lazily from the new rest geometry
+  h->have_targets = false;
+  if (h->m > 0) {
+    std::vector<int32_t> ids = h->node_ids;
+    MVS_TRY(mvs_deform_set_nodes(h, ids.data(), (int64_t)ids.size()));
+  }
+  return MVS_OK;
+}
+
+static int set_node_targets(mvs_deform* h, DevBuf<double>& controls, DevBuf<int>& valid,
+                            int only_valid) {
+  mvs_ctx* ctx = h->ctx;
+  MVS_CUDA(cudaMemsetAsync(h->targets.p, 0, sizeof(float4) * h->n, ctx->stream));
+  {
+    ProfScope ps(ctx, "targets_from_nodes");
+    k_targets_from_nodes<<<div_up(h->m, 128), 128, 0, ctx->stream>>>(
+        controls.p, valid.p, only_valid, h->node_ids_d.p, h->inv_perm.p, h->m, h->targets.p);
+  }
+  MVS_CUDA(cudaGetLastError());
+  h->have_targets = true;
+  return MVS_OK;
+}
+
+}  // namespace mvs
+
+using namespace mvs;
+
+extern "C" {
+
+int mvs_gn_default_params(mvs_gn_params* p) {
+  if (!p) return MVS_ERR_INVALID_ARG;
+  p->gn_iters = 10;
+  p->pcg_iters = 20;
+  p->corr_mode = 0;
+  p->outer_rounds = 1;
+  p->w_rot = 1.0;
+  p->w_reg = 10.0;
+  p->w_fit = 100.0;
+  p->lambda = 1e-6;
+  p->pcg_tol = 0.0;
+  p->max_corr_dist2 = 0.0;
+  p->min_corr_cos = -2.0;
+  return MVS_OK;
+}
+
+static int create_common(mvs_ctx* ctx, int64_t n, const int32_t* facets, int64_t nf,
+                         mvs_deform** out, mvs_deform** hp) {
+  if (!out) return MVS_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (n <= 0) {
+    set_error("Deformation: empty mesh");
+    return MVS_ERR_DEGENERATE;
+  }
+  if (nf < 0 || (nf > 0 && !facets)) {
+    set_error("Deformation: bad facet array");
+    return MVS_ERR_INVALID_ARG;
+  }
+  for (int64_t i = 0; i < 3 * nf; ++i)
+    if (facets[i] < 0 || facets[i] >= n) {
+      // the reference aborts on an invalid polyhedron (Deformation.cpp:42-45); we return a code
+      set_error("Deformation: facet index %d out of range", facets[i]);
+      return MVS_ERR_INVALID_ARG;
+    }
+  if (!ctx) ctx = default_ctx();
+  if (!ctx) return MVS_ERR_NO_DEVICE;
+  MVS_TRY(ctx_ensure_device(ctx));
+  mvs_deform* h = new mvs_deform();
+  h->ctx = ctx;
+  h->n = n;
+  h->nf = nf;
+  mvs_gn_default_params(&h->prm);
+  *hp = h;
+  return MVS_OK;
+}
+
+static int finish_create(mvs_deform* h, const int32_t* facets, mvs_deform** out) {
+  mvs_ctx* ctx = h->ctx;
+  int st = h->facets.reserve((size_t)3 * h->nf + 1);
+  if (st == MVS_OK && h->nf > 0) st = h2d(ctx, h->facets.p, facets, sizeof(int) * 3 * h->nf);
+  if (st == MVS_OK) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      set_error("create: %s", cudaGetErrorString(e));
+      st = MVS_ERR_CUDA;
+    }
+  }
+  if (st != MVS_OK) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return MVS_OK;
+}
+
+int mvs_deform_create(mvs_ctx* ctx, const double* pts, const double* normals, int64_t n,
+                      const int32_t* facets, int64_t nf, mvs_deform** out) {
+  MVS_REQUIRE(pts, "null points");
+  mvs_deform* h = nullptr;
+  MVS_TRY(create_common(ctx, n, facets, nf, out, &h));
+  int st = upload_xyz_f64(h->ctx, pts, n, h->v0);
+  if (st == MVS_OK) {
+    if (normals)
+      st = upload_xyz_f64(h->ctx, normals, n, h->nrm0);
+    else {
+      st = h->nrm0.reserve((size_t)n);
+      if (st == MVS_OK) cudaMemsetAsync(h->nrm0.p, 0, sizeof(float4) * n, h->ctx->stream);
+    }
+  }
+  if (st != MVS_OK) {
+    delete h;
+    return st;
+  }
+  return finish_create(h, facets, out);
+}
+
+int mvs_deform_create_f32(mvs_ctx* ctx, const float* pts, const float* normals, int64_t n,
+                          const int32_t* facets, int64_t nf, mvs_deform** out) {
+  MVS_REQUIRE(pts, "null points");
+  mvs_deform* h = nullptr;
+  MVS_TRY(create_common(ctx, n, facets, nf, out, &h));
+  int st = upload_xyz_f32(h->ctx, pts, n, h->v0);
+  if (st == MVS_OK) {
+    if (normals)
+      st = upload_xyz_f32(h->ctx, normals, n, h->nrm0);
+    else {
+      st = h->nrm0.reserve((size_t)n);
+      if (st == MVS_OK) cudaMemsetAsync(h->nrm0.p, 0, sizeof(float4) * n, h->ctx->stream);
+    }
+  }
+  if (st != MVS_OK) {
+    delete h;
+    return st;
+  }
+  return finish_create(h, facets, out);
+}
+
+int mvs_deform_destroy(mvs_deform* h) {
+  if (!h) return MVS_OK;
+  cudaSetDevice(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  if (h->node_index) mvs_nn_index_destroy(h->node_index);
+  if (h->tgt_index) mvs_nn_index_destroy(h->tgt_index);
+  delete h;
+  return MVS_OK;
+}
+
+static int target_common(mvs_deform* h, int64_t nt) {
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  if (nt <= 0) {
+    set_error("set_target: empty target");
+    return MVS_ERR_DEGENERATE;
+  }
+  if (!h->tgt_index) MVS_TRY(mvs_nn_index_create(h->ctx, &h->tgt_index));
+  h->nt = nt;
+  return MVS_OK;
+}
+
+int mvs_deform_set_target(mvs_deform* h, const double* tpts, const double* tnormals, int64_t nt) {
+  MVS_REQUIRE(h && tpts, "null argument");
+  MVS_TRY(target_common(h, nt));
+  MVS_TRY(upload_xyz_f64(h->ctx, tpts, nt, h->tp_own));
+  h->tp = h->tp_own.p;
+  h->tn = nullptr;
+  if (tnormals) {
+    MVS_TRY(upload_xyz_f64(h->ctx, tnormals, nt, h->tn_own));
+    h->tn = h->tn_own.p;
+  }
+  return nn_build(h->tgt_index, h->tp, nt);
+}
+
+int mvs_deform_set_target_f32(mvs_deform* h, const float* tpts, const float* tnormals,
+                              int64_t nt) {
+  MVS_REQUIRE(h && tpts, "null argument");
+  MVS_TRY(target_common(h, nt));
+  MVS_TRY(upload_xyz_f32(h->ctx, tpts, nt, h->tp_own));
+  h->tp = h->tp_own.p;
+  h->tn = nullptr;
+  if (tnormals) {
+    MVS_TRY(upload_xyz_f32(h->ctx, tnormals, nt, h->tn_own));
+    h->tn = h->tn_own.p;
+  }
+  return nn_build(h->tgt_index, h->tp, nt);
+}
+
+int mvs_deform_set_target_dev_f32(mvs_deform* h, const float* tpts_dev, const float* tnormals_dev,
+                                  int64_t nt) {
+  MVS_REQUIRE(h && tpts_dev, "null argument");
+  MVS_TRY(target_common(h, nt));
+  h->tp = reinterpret_cast<const float4*>(tpts_dev);
+  h->tn = reinterpret_cast<const float4*>(tnormals_dev);
+  return nn_build(h->tgt_index, h->tp, nt);
+}
+
+int mvs_deform_set_targets(mvs_deform* h, const double* targets, const float* weights, int64_t n) {
+  MVS_REQUIRE(h && targets, "null argument");
+  if (n != h->n) {
+    set_error("set_targets: expected %lld targets, got %lld", (long long)h->n, (long long)n);
+    return MVS_ERR_INVALID_ARG;
+  }
+  mvs_ctx* ctx = h->ctx;
+  MVS_TRY(ctx_ensure_device(ctx));
+  MVS_TRY(ensure_graph(h));
+  double* dt = nullptr;
+  float* dw = nullptr;
+  MVS_CUDA(cudaMallocAsync((void**)&dt, sizeof(double) * 3 * n, ctx->stream));
+  int st = h2d(ctx, dt, targets, sizeof(double) * 3 * n);
+  if (st == MVS_OK && weights) {
+    cudaError_t e = cudaMallocAsync((void**)&dw, sizeof(float) * n, ctx->stream);
+    if (e != cudaSuccess) st = MVS_ERR_CUDA;
+    if (st == MVS_OK) st = h2d(ctx, dw, weights, sizeof(float) * n);
+  }
+  if (st == MVS_OK) {
+    ProfScope ps(ctx, "targets_permute");
+    k_targets_permute<<<div_up(n, 256), 256, 0, ctx->stream>>>(dt, dw, h->perm.p, n, h->targets.p);
+  }
+  cudaFreeAsync(dt, ctx->stream);
+  if (dw) cudaFreeAsync(dw, ctx->stream);
+  MVS_TRY(st);
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  h->have_targets = true;
+  return MVS_OK;
+}
+
+int mvs_deform_node_targets(mvs_deform* h, double proj_len_err, double proj_dist_err,
+                            int smooth_sweeps, double* controls_xyz, int32_t* valid) {
+  MVS_REQUIRE(h, "null handle");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  MVS_TRY(ensure_graph(h));
+  DevBuf<double> c;
+  DevBuf<int> v;
+  MVS_TRY(deform_node_targets(h, proj_len_err, proj_dist_err, smooth_sweeps, c, v));
+  if (controls_xyz)
+    MVS_CUDA(cudaMemcpyAsync(controls_xyz, c.p, sizeof(double) * 3 * h->m, cudaMemcpyDeviceToHost,
+                             h->ctx->stream));
+  if (valid)
+    MVS_CUDA(cudaMemcpyAsync(valid, v.p, sizeof(int) * h->m, cudaMemcpyDeviceToHost,
+                             h->ctx->stream));
+  MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_deform_gn_begin(mvs_deform* h, const mvs_gn_params* params) {
+  MVS_REQUIRE(h, "null handle");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  return gn_begin_impl(h, params);
+}
+
+int mvs_deform_gn_step(mvs_deform* h) {
+  MVS_REQUIRE(h, "null handle");
+  if (!h->gn_active) {
+    set_error("gn_step before gn_begin");
+    return MVS_ERR_STATE;
+  }
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  return gn_step_impl(h);
+}
+
+int mvs_deform_gn_end(mvs_deform* h) {
+  MVS_REQUIRE(h, "null handle");
+  if (!h->gn_active) {
+    set_error("gn_end before gn_begin");
+    return MVS_ERR_STATE;
+  }
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  MVS_TRY(gn_final_vertices(h));
+  MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  h->gn_active = false;
+  return MVS_OK;
+}
+
+int mvs_deform_run(mvs_deform* h, double proj_len_err, double proj_dist_err,
+                   const mvs_gn_params* params) {
+  MVS_REQUIRE(h, "null handle");
+  mvs_gn_params def;
+  if (!params) {
+    mvs_gn_default_params(&def);
+    params = &def;
+  }
+  MVS_TRY(validate_params(params));
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  int rounds = params->outer_rounds > 0 ? params->outer_rounds : 1;
+  for (int round = 0; round < rounds; ++round) {  // Deformation.cpp:252-253 `while(counter--)`
+    MVS_TRY(ensure_graph(h));
+    if (params->corr_mode == 0) {
+      DevBuf<double> c;
+      DevBuf<int> v;
+      // Deformation.cpp:266-381; every node becomes a constraint, valid or not (:384 commented)
+      MVS_TRY(deform_node_targets(h, proj_len_err, proj_dist_err, 2, c, v));
+      MVS_TRY(set_node_targets(h, c, v, 0));
+    }
+    MVS_TRY(gn_begin_impl(h, params));
+    for (int it = 0; it < params->gn_iters; ++it) MVS_TRY(gn_step_impl(h));
+    MVS_TRY(gn_final_vertices(h));
+    h->gn_active = false;
+    MVS_TRY(bake(h));
+  }
+  MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_params* params) {
+  MVS_REQUIRE(h, "null handle");
+  mvs_gn_params def;
+  if (!params) {
+    mvs_gn_default_params(&def);
+    params = &def;
+  }
+  MVS_TRY(validate_params(params));
+  mvs_ctx* ctx = h->ctx;
+  MVS_TRY(ctx_ensure_device(ctx));
+  if (!h->tgt_index || !h->tgt_index->built) {
+    set_error("run_threshold: target not set");
+    return MVS_ERR_STATE;
+  }
+  if (h->m <= 0) {
+    set_error("run_threshold: no nodes (the reference leaves sampIdx empty here, "
+              "Deformation.cpp:184)");
+    return MVS_ERR_STATE;
+  }
+  MVS_TRY(ensure_graph(h));
+  DevBuf<double> c;
+  DevBuf<int> v;
+  MVS_TRY(c.reserve((size_t)h->m * 3));
+  MVS_TRY(v.reserve((size_t)h->m));
+  {
+    ProfScope ps(ctx, "node_targets_threshold");
+    k_node_targets_threshold<<<div_up(h->m, 64), 64, 0, ctx->stream>>>(
+        h->tgt_index->g, h->tgt_index->pts_sorted.p, h->tgt_index->cell_start.p, h->g.p,
+        h->gnrm.p, h->m, (float)threshold, c.p, v.p);
+  }
+  MVS_TRY(set_node_targets(h, c, v, 1));
+  mvs_gn_params p = *params;
+  p.corr_mode = 2;
+  MVS_TRY(gn_begin_impl(h, &p));
+  for (int it = 0; it < p.gn_iters; ++it) MVS_TRY(gn_step_impl(h));
+  MVS_TRY(gn_final_vertices(h));
+  h->gn_active = false;
+  MVS_TRY(bake(h));
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_deform_get_energy(mvs_deform* h, double energy[3]) {
+  MVS_REQUIRE(h && energy, "null argument");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  if (!h->graph_built) {
+    set_error("get_energy: no solver state");
+    return MVS_ERR_STATE;
+  }
+  MVS_TRY(gn_deform_and_correspond(h));
+  return gn_energy(h, energy);
+}
+
+int mvs_deform_get_node_state(mvs_deform* h, float* A_t) {
+  MVS_REQUIRE(h && A_t, "null argument");
+  if (!h->graph_built) {
+    set_error("get_node_state: graph not built");
+    return MVS_ERR_STATE;
+  }
+  return d2h_sync(h->ctx, A_t, h->x.p, sizeof(float) * 12 * h->m);
+}
+
+int mvs_deform_set_node_state(mvs_deform* h, const float* A_t) {
+  MVS_REQUIRE(h && A_t, "null argument");
+  MVS_TRY(ensure_graph(h));
+  MVS_TRY(h2d(h->ctx, h->x.p, A_t, sizeof(float) * 12 * h->m));
+  MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  h->cur_valid = false;
+  return MVS_OK;
+}
+
+static int get_f4_as_xyz(mvs_deform* h, const float4* src, int64_t n, double* out64, float* out32) {
+  mvs_ctx* ctx = h->ctx;
+  void* tmp = nullptr;
+  size_t bytes = (out64 ? sizeof(double) : sizeof(float)) * 3 * n;
+  MVS_CUDA(cudaMallocAsync(&tmp, bytes, ctx->stream));
+  {
+    ProfScope ps(ctx, "unpack_xyz");
+    if (out64)
+      k_f4_to_f64xyz<<<div_up(n, 256), 256, 0, ctx->stream>>>(src, (double*)tmp, n);
+    else
+      k_f4_to_f32xyz<<<div_up(n, 256), 256, 0, ctx->stream>>>(src, (float*)tmp, n);
+  }
+  cudaError_t e = cudaMemcpyAsync(out64 ? (void*)out64 : (void*)out32, tmp, bytes,
+                                  cudaMemcpyDeviceToHost, ctx->stream);
+  cudaFreeAsync(tmp, ctx->stream);
+  if (e != cudaSuccess) {
+    set_error("get vertices: %s", cudaGetErrorString(e));
+    return MVS_ERR_CUDA;
+  }
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_deform_get_vertices(mvs_deform* h, double* pts) {
+  MVS_REQUIRE(h && pts, "null argument");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  return get_f4_as_xyz(h, h->cur_valid ? h->cur0.p : h->v0.p, h->n, pts, nullptr);
+}
+
+int mvs_deform_get_vertices_f32(mvs_deform* h, float* pts) {
+  MVS_REQUIRE(h && pts, "null argument");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  return get_f4_as_xyz(h, h->cur_valid ? h->cur0.p : h->v0.p, h->n, nullptr, pts);
+}
+
+int mvs_deform_get_normals(mvs_deform* h, double* normals) {
+  MVS_REQUIRE(h && normals, "null argument");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  return get_f4_as_xyz(h, (h->cur_valid && h->nf > 0) ? h->curn0.p : h->nrm0.p, h->n, normals,
+                       nullptr);
+}
+
+int mvs_deform_get_facets(mvs_deform* h, int32_t* facets, int64_t* n_facets) {
+  MVS_REQUIRE(h, "null handle");
+  if (n_facets) *n_facets = h->nf;
+  if (facets && h->nf > 0) return d2h_sync(h->ctx, facets, h->facets.p, sizeof(int) * 3 * h->nf);
+  return MVS_OK;
+}
+
+int mvs_deform_get_weights(mvs_deform* h, int32_t* node_idx, float* weights) {
+  MVS_REQUIRE(h, "null handle");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  MVS_TRY(ensure_graph(h));
+  if (node_idx)
+    MVS_CUDA(cudaMemcpyAsync(node_idx, h->vidx_knn.p, sizeof(int4) * h->n, cudaMemcpyDeviceToHost,
+                             h->ctx->stream));
+  if (weights)
+    MVS_CUDA(cudaMemcpyAsync(weights, h->vw_knn.p, sizeof(float4) * h->n, cudaMemcpyDeviceToHost,
+                             h->ctx->stream));
+  MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_deform_get_graph(mvs_deform* h, int32_t* nbr_idx) {
+  MVS_REQUIRE(h && nbr_idx, "null argument");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  MVS_TRY(ensure_graph(h));
+  return d2h_sync(h->ctx, nbr_idx, h->graph.p, sizeof(int) * h->m * (h->graph_k + 1));
+}
+
+int mvs_deform_get_system(mvs_deform* h, int32_t* row_ptr, int32_t* col, float* blocks,
+                          float* rot, float* rhs, int64_t* nnz) {
+  MVS_REQUIRE(h, "null handle");
+  if (!h->graph_built) {
+    set_error("get_system: graph not built");
+    return MVS_ERR_STATE;
+  }
+  mvs_ctx* ctx = h->ctx;
+  MVS_TRY(ctx_ensure_device(ctx));
+  if (nnz) *nnz = h->nnz;
+  cudaStream_t st = ctx->stream;
+  if (row_ptr)
+    MVS_CUDA(cudaMemcpyAsync(row_ptr, h->row_ptr.p, sizeof(int) * (h->m + 1), cudaMemcpyDeviceToHost, st));
+  if (col)
+    MVS_CUDA(cudaMemcpyAsync(col, h->col.p, sizeof(int) * h->nnz, cudaMemcpyDeviceToHost, st));
+  if (blocks)
+    MVS_CUDA(cudaMemcpyAsync(blocks, h->B(), sizeof(float) * 16 * h->nnz, cudaMemcpyDeviceToHost, st));
+  if (rot)
+    MVS_CUDA(cudaMemcpyAsync(rot, h->Rot(), sizeof(float) * 81 * h->m, cudaMemcpyDeviceToHost, st));
+  if (rhs)
+    MVS_CUDA(cudaMemcpyAsync(rhs, h->rhs(), sizeof(float) * 12 * h->m, cudaMemcpyDeviceToHost, st));
+  MVS_CUDA(cudaStreamSynchronize(st));
+  return MVS_OK;
+}
+
+int mvs_deform_set_shard(mvs_deform* h, int64_t v_begin, int64_t v_end) {
+  MVS_REQUIRE(h, "null handle");
+  if (v_begin < 0 || (v_end >= 0 && (v_end < v_begin || v_end > h->n))) {
+    set_error("set_shard: bad range");
+    return MVS_ERR_INVALID_ARG;
+  }
+  h->v_begin = v_begin;
+  h->v_end = v_end;
+  return MVS_OK;
+}
+
+// Deformation/Deformation.h:174-221 exportOBJ -> PlyObj/PlyObj.cpp:77-137 WriteObjCore format
+int mvs_deform_export_obj(mvs_deform* h, const char* filename) {
+  MVS_REQUIRE(h && filename, "null argument");
+  int64_t n = h->n, nf = h->nf;
+  std::vector<float> p((size_t)3 * n);
+  std::vector<double> nr((size_t)3 * n);
+  std::vector<int32_t> f((size_t)3 * nf);
+  MVS_TRY(mvs_deform_get_vertices_f32(h, p.data()));
+  MVS_TRY(mvs_deform_get_normals(h, nr.data()));
+  MVS_TRY(mvs_deform_get_facets(h, f.data(), nullptr));
+  FILE* fp = fopen(filename, "w");
+  if (!fp) {
+    set_error("exportOBJ: Error exporting %s", filename);
+    return MVS_ERR_INVALID_ARG;
+  }
+  fprintf(fp, "####\n#\n# OBJ File Generated by MultiviewStitch Program\n#\n####\n");
+  fprintf(fp, "# Object %s\n#\n# Vertices: %lld\n# Faces: %lld\n#\n####\n", filename, (long long)n,
+          (long long)nf);
+  for (int64_t i = 0; i < n; ++i) {
+    fprintf(fp, "vn %g %g %g\n", (float)nr[3 * i], (float)nr[3 * i + 1], (float)nr[3 * i + 2]);
+    fprintf(fp, "v %g %g %g\n", p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+  }
+  fprintf(fp, "# %lld vertices, %lld vertices normals\n\n", (long long)n, (long long)n);
+  for (int64_t i = 0; i < nf; ++i)
+    fprintf(fp, "f %d//%d %d//%d %d//%d\n", f[3 * i] + 1, f[3 * i] + 1, f[3 * i + 1] + 1,
+            f[3 * i + 1] + 1, f[3 * i + 2] + 1, f[3 * i + 2] + 1);
+  fclose(fp);
+  return MVS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,657 @@
+// gn_assemble.cu — per-vertex passes of one Gauss-Newton iteration of the embedded-deformation
+// solve (formulation: SURVEY.md §8(a) D7-D8):
+//
+//   k_deform_corr   v~_i = sum_j w_ij [A_j (v_i - g_j) + g_j + t_j]; exact 1-NN of v~_i in the
+//                   target grid; resid_i = (v~_i - c_i, omega_i)            48 B/vertex in, 16 out
+//   k_assemble_fit  fused residual + Jacobian + J^T J / J^T r assembly.  The fit Jacobian of a
+//                   vertex w.r.t. node j is w_ij [d^T (x) I3 | I3], so every 12x12 block pair is
+//                   kron(b_j b_l^T, I3) with b_j = w_ij (d, 1) in R^4: only the 4x4 factor is
+//                   accumulated (16 MACs instead of 432).  Vertices are pre-sorted so that equal
+//                   node 4-tuples are adjacent; a warp finds the groups of equal tuples among its
+//                   32 vertices with __match_any_sync, stages the per-vertex records in shared
+//                   memory, reduces each group in registers (14 4x4 tiles x 2 half-warps) and
+//                   flushes one vector atomic per tile row.                  64 B/vertex in
+//   k_node_terms    rotation (dense 9x9 per node) and smoothness (graph edges) terms
+//   k_precond       12x12 block-Jacobi preconditioner: Cholesky inverse of each diagonal block
+#include <cmath>
+
+#include "comm.cuh"
+#include "deform.cuh"
+#include "reduce.cuh"
+
+namespace mvs {
+
+// ------------------------------------------------------------------ helpers
+struct NodeX {
+  float a[12];  // a1 (0..2), a2 (3..5), a3 (6..8), t (9..11)
+};
+
+__device__ __forceinline__ NodeX load_node(const float* __restrict__ x, int j) {
+  NodeX n;
+  const float4* p = reinterpret_cast<const float4*>(x + (size_t)j * 12);
+  float4 u0 = __ldg(p), u1 = __ldg(p + 1), u2 = __ldg(p + 2);
+  n.a[0] = u0.x; n.a[1] = u0.y; n.a[2] = u0.z; n.a[3] = u0.w;
+  n.a[4] = u1.x; n.a[5] = u1.y; n.a[6] = u1.z; n.a[7] = u1.w;
+  n.a[8] = u2.x; n.a[9] = u2.y; n.a[10] = u2.z; n.a[11] = u2.w;
+  return n;
+}
+
+__device__ __forceinline__ float3 deform_point(float4 v, int4 id, float4 w,
+                                               const float4* __restrict__ g,
+                                               const float* __restrict__ x) {
+  int ids[4] = {id.x, id.y, id.z, id.w};
+  float ws[4] = {w.x, w.y, w.z, w.w};
+  float3 out = make_float3(0.f, 0.f, 0.f);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (ids[a] < 0) continue;
+    float4 gj = __ldg(g + ids[a]);
+    NodeX n = load_node(x, ids[a]);
+    float d0 = v.x - gj.x, d1 = v.y - gj.y, d2 = v.z - gj.z;
+    float px = n.a[0] * d0 + n.a[3] * d1 + n.a[6] * d2 + gj.x + n.a[9];
+    float py = n.a[1] * d0 + n.a[4] * d1 + n.a[7] * d2 + gj.y + n.a[10];
+    float pz = n.a[2] * d0 + n.a[5] * d1 + n.a[8] * d2 + gj.z + n.a[11];
+    out.x += ws[a] * px;
+    out.y += ws[a] * py;
+    out.z += ws[a] * pz;
+  }
+  return out;
+}
+
+__global__ void k_reset_state(float* __restrict__ x, int64_t m) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= m * 12) return;
+  int k = (int)(t % 12);
+  x[t] = (k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f;
+}
+
+int gn_reset_state(mvs_deform* h) {
+  ProfScope ps(h->ctx, "gn_reset");
+  k_reset_state<<<div_up(h->m * 12, 256), 256, 0, h->ctx->stream>>>(h->x.p, h->m);
+  MVS_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+// ------------------------------------------------------------------ deform + correspondences
+struct Best1 {
+  float qx, qy, qz;
+  float d2;
+  int idx;
+  float cx, cy, cz;
+  __device__ __forceinline__ float worst2() const { return d2; }
+  __device__ __forceinline__ void point(float4 p) {
+    float d = dist2_rn(p.x, p.y, p.z, qx, qy, qz);
+    int id = __float_as_int(p.w);
+    if (d < d2 || (d == d2 && id < idx)) {
+      d2 = d;
+      idx = id;
+      cx = p.x; cy = p.y; cz = p.z;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(128)
+    k_deform_corr(GridParams tg, const float4* __restrict__ tsorted,
+                  const int* __restrict__ cell_start, const float4* __restrict__ tnrm,
+                  const float4* __restrict__ v, const float4* __restrict__ nrm,
+                  const int4* __restrict__ vidx, const float4* __restrict__ vw,
+                  const float4* __restrict__ g, const float* __restrict__ x, int64_t begin,
+                  int64_t end, float max_d2, float min_cos, float4* __restrict__ resid) {
+  int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= end) return;
+  float4 vi = __ldg(v + i);
+  float3 q = deform_point(vi, __ldg(vidx + i), __ldg(vw + i), g, x);
+  Best1 b;
+  b.qx = q.x; b.qy = q.y; b.qz = q.z;
+  b.d2 = INFINITY;
+  b.idx = 0x7fffffff;
+  b.cx = b.cy = b.cz = 0.f;
+  grid_search(tg, cell_start, tsorted, q.x, q.y, q.z, b);
+  float om = 1.0f;
+  if (max_d2 > 0.f && b.d2 > max_d2) om = 0.0f;
+  if (min_cos > -1.0f && tnrm) {
+    float4 ni = __ldg(nrm + i);
+    float4 nt = __ldg(tnrm + b.idx);
+    // double, FMA-free: the accept/reject decision is reproducible on the host
+    double dn = __dadd_rn(__dadd_rn(__dmul_rn((double)ni.x, (double)nt.x),
+                                    __dmul_rn((double)ni.y, (double)nt.y)),
+                          __dmul_rn((double)ni.z, (double)nt.z));
+    if (dn < (double)min_cos) om = 0.0f;
+  }
+  resid[i] = make_float4(q.x - b.cx, q.y - b.cy, q.z - b.cz, om);
+}
+
+__global__ void k_deform_resid(const float4* __restrict__ v, const int4* __restrict__ vidx,
+                               const float4* __restrict__ vw, const float4* __restrict__ g,
+                               const float* __restrict__ x, const float4* __restrict__ targets,
+                               int64_t begin, int64_t end, float4* __restrict__ resid) {
+  int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= end) return;
+  float4 t = __ldg(targets + i);
+  if (!(t.w > 0.f)) {
+    resid[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float3 q = deform_point(__ldg(v + i), __ldg(vidx + i), __ldg(vw + i), g, x);
+  resid[i] = make_float4(q.x - t.x, q.y - t.y, q.z - t.z, t.w);
+}
+
+int gn_deform_and_correspond(mvs_deform* h) {
+  mvs_ctx* ctx = h->ctx;
+  int64_t b = h->shard_begin(), e = h->shard_end();
+  if (e <= b) return MVS_OK;
+  if (h->prm.corr_mode == 1) {
+    if (!h->tgt_index || !h->tgt_index->built) {
+      set_error("corr_mode 1 needs a target (mvs_deform_set_target*)");
+      return MVS_ERR_STATE;
+    }
+    ProfScope ps(ctx, "gn_deform_corr");
+    k_deform_corr<<<div_up(e - b, 128), 128, 0, ctx->stream>>>(
+        h->tgt_index->g, h->tgt_index->pts_sorted.p, h->tgt_index->cell_start.p, h->tn, h->v.p,
+        h->nrm.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, b, e, (float)h->prm.max_corr_dist2,
+        (float)h->prm.min_corr_cos, h->resid.p);
+  } else {
+    if (!h->have_targets) {
+      set_error("fixed-target mode needs per-vertex targets");
+      return MVS_ERR_STATE;
+    }
+    ProfScope ps(ctx, "gn_deform_resid");
+    k_deform_resid<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(
+        h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, h->targets.p, b, e, h->resid.p);
+  }
+  MVS_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+// ------------------------------------------------------------------ fit assembly
+constexpr int kAsmWarps = 4;
+constexpr int kRecStride = 20;
+
+__device__ __forceinline__ int find_slot(const int* __restrict__ row_ptr,
+                                         const int* __restrict__ col, int j, int l) {
+  int lo = __ldg(row_ptr + j), hi = __ldg(row_ptr + j + 1) - 1;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(col + mid) < l) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float c, float d) {
+  // one 16-byte vector reduction (sm_90+): red.global.add.v4.f32
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kAsmWarps * 32)
+    k_assemble_fit(const float4* __restrict__ v, const int4* __restrict__ vidx,
+                   const float4* __restrict__ vw, const float4* __restrict__ resid,
+                   const float4* __restrict__ g, const int* __restrict__ row_ptr,
+                   const int* __restrict__ col, float* __restrict__ B, float* __restrict__ rhs,
+                   int64_t begin, int64_t end, float w_fit) {
+  __shared__ __align__(16) float rec[kAsmWarps][32][kRecStride];
+  const unsigned full = 0xffffffffu;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t nwarps = (int64_t)gridDim.x * kAsmWarps;
+  int64_t wg = (int64_t)blockIdx.x * kAsmWarps + warp;
+  // tile table: 10 (a,b) block tiles (a<=b) then 4 rhs tiles
+  int half = lane >> 4, t = lane & 15;
+  int ta, tb;
+  switch (t) {
+    case 0: ta = 0; tb = 0; break;
+    case 1: ta = 1; tb = 1; break;
+    case 2: ta = 2; tb = 2; break;
+    case 3: ta = 3; tb = 3; break;
+    case 4: ta = 0; tb = 1; break;
+    case 5: ta = 0; tb = 2; break;
+    case 6: ta = 0; tb = 3; break;
+    case 7: ta = 1; tb = 2; break;
+    case 8: ta = 1; tb = 3; break;
+    case 9: ta = 2; tb = 3; break;
+    default: ta = (t - 10) & 3; tb = 4; break;  // rhs tiles read the residual slot (cols 16..19)
+  }
+  for (int64_t base = begin + wg * 32; base < end; base += nwarps * 32) {
+    int64_t i = base + lane;
+    bool in = i < end;
+    int4 id = make_int4(-1, -1, -1, -1);
+    float s = 0.f;
+    float r0[kRecStride];
+#pragma unroll
+    for (int k = 0; k < kRecStride; ++k) r0[k] = 0.f;
+    if (in) {
+      float4 rs = __ldg(resid + i);
+      if (rs.w > 0.f) {
+        s = sqrtf(w_fit * rs.w);
+        float4 vi = __ldg(v + i);
+        float4 w = __ldg(vw + i);
+        id = __ldg(vidx + i);
+        int ids[4] = {id.x, id.y, id.z, id.w};
+        float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          if (ids[a] >= 0) {
+            float4 gj = __ldg(g + ids[a]);
+            float sw = s * ws[a];
+            r0[4 * a + 0] = sw * (vi.x - gj.x);
+            r0[4 * a + 1] = sw * (vi.y - gj.y);
+            r0[4 * a + 2] = sw * (vi.z - gj.z);
+            r0[4 * a + 3] = sw;
+          }
+        }
+        r0[16] = s * rs.x;
+        r0[17] = s * rs.y;
+        r0[18] = s * rs.z;
+      }
+    }
+    unsigned long long k0 = ((unsigned long long)(unsigned)id.x << 32) | (unsigned)id.y;
+    unsigned long long k1 = ((unsigned long long)(unsigned)id.z << 32) | (unsigned)id.w;
+    unsigned act = __ballot_sync(full, s > 0.f);
+    unsigned grp = __match_any_sync(full, k0) & __match_any_sync(full, k1) & act;
+    unsigned remaining = act;
+    while (remaining) {
+      int leader = __ffs(remaining) - 1;
+      unsigned gmask = __shfl_sync(full, grp, leader);
+      int cnt = __popc(gmask);
+      if ((gmask >> lane) & 1u) {
+        int rank = __popc(gmask & ((1u << lane) - 1u));
+        float4* dst = reinterpret_cast<float4*>(&rec[warp][rank][0]);
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          dst[k] = make_float4(r0[4 * k], r0[4 * k + 1], r0[4 * k + 2], r0[4 * k + 3]);
+      }
+      __syncwarp();
+      int j0 = __shfl_sync(full, id.x, leader), j1 = __shfl_sync(full, id.y, leader);
+      int j2 = __shfl_sync(full, id.z, leader), j3 = __shfl_sync(full, id.w, leader);
+      float acc[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+      if (t < 14) {
+        for (int mi = half; mi < cnt; mi += 2) {
+          const float4 ba = *reinterpret_cast<const float4*>(&rec[warp][mi][4 * ta]);
+          const float4 bb = *reinterpret_cast<const float4*>(&rec[warp][mi][4 * tb]);
+          acc[0] += ba.x * bb.x; acc[1] += ba.x * bb.y; acc[2] += ba.x * bb.z; acc[3] += ba.x * bb.w;
+          acc[4] += ba.y * bb.x; acc[5] += ba.y * bb.y; acc[6] += ba.y * bb.z; acc[7] += ba.y * bb.w;
+          acc[8] += ba.z * bb.x; acc[9] += ba.z * bb.y; acc[10] += ba.z * bb.z; acc[11] += ba.z * bb.w;
+          acc[12] += ba.w * bb.x; acc[13] += ba.w * bb.y; acc[14] += ba.w * bb.z; acc[15] += ba.w * bb.w;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] += __shfl_xor_sync(full, acc[k], 16);
+      if (half == 0 && t < 14) {
+        int js[4] = {j0, j1, j2, j3};
+        int ja = js[ta];
+        if (t < 10) {
+          int jb = js[tb];
+          if (ja >= 0 && jb >= 0) {
+            float* dst = B + (size_t)find_slot(row_ptr, col, ja, jb) * 16;
+            red_add_f4(dst, acc[0], acc[1], acc[2], acc[3]);
+            red_add_f4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+            red_add_f4(dst + 8, acc[8], acc[9], acc[10], acc[11]);
+            red_add_f4(dst + 12, acc[12], acc[13], acc[14], acc[15]);
+            if (ta != tb) {
+              float* d2 = B + (size_t)find_slot(row_ptr, col, jb, ja) * 16;
+              red_add_f4(d2, acc[0], acc[4], acc[8], acc[12]);
+              red_add_f4(d2 + 4, acc[1], acc[5], acc[9], acc[13]);
+              red_add_f4(d2 + 8, acc[2], acc[6], acc[10], acc[14]);
+              red_add_f4(d2 + 12, acc[3], acc[7], acc[11], acc[15]);
+            }
+          }
+        } else if (ja >= 0) {
+          // rhs_j[3c + r] += sum b_a[c] * r[r]   (acc[4c + r], r < 3)
+          float* dst = rhs + (size_t)ja * 12;
+          red_add_f4(dst, acc[0], acc[1], acc[2], acc[4]);
+          red_add_f4(dst + 4, acc[5], acc[6], acc[8], acc[9]);
+          red_add_f4(dst + 8, acc[10], acc[12], acc[13], acc[14]);
+        }
+      }
+      remaining &= ~gmask;
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ node terms
+__global__ void __launch_bounds__(64)
+    k_node_terms(const float4* __restrict__ g, const float* __restrict__ x,
+                 const int* __restrict__ graph, int gk1, int64_t m,
+                 const int* __restrict__ row_ptr, const int* __restrict__ col,
+                 float* __restrict__ B, float* __restrict__ Rot, float* __restrict__ rhs,
+                 float w_rot, float w_reg) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  NodeX n = load_node(x, j);
+  const float* a1 = n.a;
+  const float* a2 = n.a + 3;
+  const float* a3 = n.a + 6;
+  float res[6];
+  float J[6][9];
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int p = 0; p < 9; ++p) J[k][p] = 0.f;
+  res[0] = a1[0] * a2[0] + a1[1] * a2[1] + a1[2] * a2[2];
+  res[1] = a1[0] * a3[0] + a1[1] * a3[1] + a1[2] * a3[2];
+  res[2] = a2[0] * a3[0] + a2[1] * a3[1] + a2[2] * a3[2];
+  res[3] = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2] - 1.0f;
+  res[4] = a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2] - 1.0f;
+  res[5] = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2] - 1.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    J[0][r] = a2[r]; J[0][3 + r] = a1[r];
+    J[1][r] = a3[r]; J[1][6 + r] = a1[r];
+    J[2][3 + r] = a3[r]; J[2][6 + r] = a2[r];
+    J[3][r] = 2.f * a1[r];
+    J[4][3 + r] = 2.f * a2[r];
+    J[5][6 + r] = 2.f * a3[r];
+  }
+  float gl[12];
+#pragma unroll
+  for (int p = 0; p < 12; ++p) gl[p] = 0.f;
+  float* R = Rot + (size_t)j * 81;
+#pragma unroll
+  for (int p = 0; p < 9; ++p) {
+    float gp = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) gp += J[k][p] * res[k];
+    gl[p] = w_rot * gp;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += J[k][p] * J[k][q];
+      R[9 * p + q] = w_rot * s;
+    }
+  }
+  // smoothness edges j -> l
+  float Bjj[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) Bjj[k] = 0.f;
+  float4 gj = __ldg(g + j);
+  for (int e = 0; e < gk1; ++e) {
+    int l = __ldg(graph + (size_t)j * gk1 + e);
+    if (l < 0 || l == j) continue;
+    float4 gv = __ldg(g + l);
+    NodeX nl = load_node(x, l);
+    float ev[3] = {gv.x - gj.x, gv.y - gj.y, gv.z - gj.z};
+    float r[3];
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+      r[rr] = (n.a[rr] * ev[0] + n.a[3 + rr] * ev[1] + n.a[6 + rr] * ev[2] - ev[rr]) +
+              (n.a[9 + rr] - nl.a[9 + rr]);
+    float a[4] = {ev[0], ev[1], ev[2], 1.0f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int d = 0; d < 4; ++d) Bjj[4 * c + d] += w_reg * a[c] * a[d];
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) gl[3 * c + rr] += w_reg * a[c] * r[rr];
+    }
+    float* Bjl = B + (size_t)find_slot(row_ptr, col, j, l) * 16;
+    float* Blj = B + (size_t)find_slot(row_ptr, col, l, j) * 16;
+    float* Bll = B + (size_t)find_slot(row_ptr, col, l, l) * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      atomicAdd(Bjl + 4 * c + 3, -w_reg * a[c]);
+      atomicAdd(Blj + 12 + c, -w_reg * a[c]);
+    }
+    atomicAdd(Bll + 15, w_reg);
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) atomicAdd(rhs + (size_t)l * 12 + 9 + rr, -w_reg * r[rr]);
+  }
+  float* Bd = B + (size_t)find_slot(row_ptr, col, j, j) * 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) atomicAdd(Bd + k, Bjj[k]);
+#pragma unroll
+  for (int p = 0; p < 12; ++p) atomicAdd(rhs + (size_t)j * 12 + p, gl[p]);
+}
+
+// ------------------------------------------------------------------ preconditioner
+__global__ void __launch_bounds__(64)
+    k_precond(const int* __restrict__ row_ptr, const int* __restrict__ col,
+              const float* __restrict__ B, const float* __restrict__ Rot, int64_t m, double lambda,
+              float* __restrict__ Minv) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double D[144];
+  for (int k = 0; k < 144; ++k) D[k] = 0.0;
+  const float* Bd = B + (size_t)find_slot(row_ptr, col, j, j) * 16;
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b)
+      for (int r = 0; r < 3; ++r) D[(3 * a + r) * 12 + 3 * b + r] += (double)Bd[4 * a + b];
+  const float* R = Rot + (size_t)j * 81;
+  for (int p = 0; p < 9; ++p)
+    for (int q = 0; q < 9; ++q) D[p * 12 + q] += (double)R[9 * p + q];
+  for (int k = 0; k < 12; ++k) D[k * 12 + k] += lambda;
+  // Cholesky D = L L^T (in place, lower), then inverse via L^-1
+  double L[144];
+  bool ok = true;
+  for (int i = 0; i < 12 && ok; ++i)
+    for (int c = 0; c <= i; ++c) {
+      double s = D[i * 12 + c];
+      for (int k = 0; k < c; ++k) s -= L[i * 12 + k] * L[c * 12 + k];
+      if (i == c) {
+        if (!(s > 0.0)) {
+          ok = false;
+          break;
+        }
+        L[i * 12 + i] = sqrt(s);
+      } else {
+        L[i * 12 + c] = s / L[c * 12 + c];
+      }
+    }
+  float* out = Minv + (size_t)j * 144;
+  if (!ok) {
+    for (int k = 0; k < 144; ++k) out[k] = 0.f;
+    for (int k = 0; k < 12; ++k) out[13 * k] = (float)(1.0 / D[13 * k]);
+    return;
+  }
+  double Li[144];
+  for (int k = 0; k < 144; ++k) Li[k] = 0.0;
+  for (int c = 0; c < 12; ++c) {
+    Li[c * 12 + c] = 1.0 / L[c * 12 + c];
+    for (int i = c + 1; i < 12; ++i) {
+      double s = 0.0;
+      for (int k = c; k < i; ++k) s -= L[i * 12 + k] * Li[k * 12 + c];
+      Li[i * 12 + c] = s / L[i * 12 + i];
+    }
+  }
+  for (int i = 0; i < 12; ++i)
+    for (int c = 0; c < 12; ++c) {
+      double s = 0.0;
+      for (int k = (i > c ? i : c); k < 12; ++k) s += Li[k * 12 + i] * Li[k * 12 + c];
+      out[i * 12 + c] = (float)s;
+    }
+}
+
+int gn_assemble(mvs_deform* h) {
+  mvs_ctx* ctx = h->ctx;
+  cudaStream_t st = ctx->stream;
+  MVS_CUDA(cudaMemsetAsync(h->sys.p, 0, sizeof(float) * h->sys_floats(), st));
+  int64_t b = h->shard_begin(), e = h->shard_end();
+  if (e > b) {
+    ProfScope ps(ctx, "gn_assemble_fit");
+    int64_t warps_needed = (e - b + 31) / 32;
+    int grid = (int)std::min<int64_t>((warps_needed + kAsmWarps - 1) / kAsmWarps,
+                                      (int64_t)ctx->num_sms * 8);
+    k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(h->v.p, h->vidx.p, h->vw.p, h->resid.p, h->g.p,
+                                                    h->row_ptr.p, h->col.p, h->B(), h->rhs(), b, e,
+                                                    (float)h->prm.w_fit);
+  }
+  MVS_CUDA(cudaGetLastError());
+  if (ctx->comm && ctx->nranks > 1) {
+    // vertex-sharded solve: sum the partial J^T J blocks and J^T r over ranks (NVLink/NVSwitch)
+    ProfScope ps(ctx, "gn_allreduce", 0);
+    MVS_TRY(comm_allreduce_sum_f32(ctx, h->sys.p, h->sys_floats()));
+  }
+  {
+    ProfScope ps(ctx, "gn_node_terms");
+    k_node_terms<<<div_up(h->m, 64), 64, 0, st>>>(h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m,
+                                                  h->row_ptr.p, h->col.p, h->B(), h->Rot(),
+                                                  h->rhs(), (float)h->prm.w_rot,
+                                                  (float)h->prm.w_reg);
+  }
+  {
+    ProfScope ps(ctx, "gn_precond");
+    k_precond<<<div_up(h->m, 64), 64, 0, st>>>(h->row_ptr.p, h->col.p, h->B(), h->Rot(), h->m,
+                                               h->prm.lambda, h->Minv.p);
+  }
+  MVS_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+__global__ void k_axpy1(float* __restrict__ x, const float* __restrict__ d, int64_t n) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) x[t] += d[t];
+}
+
+int gn_apply_update(mvs_deform* h) {
+  ProfScope ps(h->ctx, "gn_update");
+  float* delta = h->pcg.p + (size_t)h->m * 12 * 5;
+  k_axpy1<<<div_up(h->m * 12, 256), 256, 0, h->ctx->stream>>>(h->x.p, delta, h->m * 12);
+  MVS_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+// ------------------------------------------------------------------ final vertices + normals
+__global__ void k_deform_final(const float4* __restrict__ v, const int4* __restrict__ vidx,
+                               const float4* __restrict__ vw, const float4* __restrict__ g,
+                               const float* __restrict__ x, int64_t n, float4* __restrict__ cur0) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 vi = __ldg(v + i);
+  float3 q = deform_point(vi, __ldg(vidx + i), __ldg(vw + i), g, x);
+  cur0[__float_as_int(vi.w)] = make_float4(q.x, q.y, q.z, 0.f);
+}
+
+// Deformation/Deformation.h:111-128 FacetNormal + :86-109 VertexNormal
+__global__ void k_facet_normals(const float4* __restrict__ p, const int* __restrict__ facets,
+                                int64_t nf, float* __restrict__ nacc /* n x 4 */) {
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  int a = facets[3 * f], b = facets[3 * f + 1], c = facets[3 * f + 2];
+  float4 p1 = __ldg(p + a), p2 = __ldg(p + b), p3 = __ldg(p + c);
+  float ux = p2.x - p1.x, uy = p2.y - p1.y, uz = p2.z - p1.z;
+  float vx = p3.x - p1.x, vy = p3.y - p1.y, vz = p3.z - p1.z;
+  float cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+  float l = sqrtf(cx * cx + cy * cy + cz * cz);
+  if (!(l > 0.f)) return;
+  float il = 1.0f / l;
+  cx *= il; cy *= il; cz *= il;
+  int vs[3] = {a, b, c};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    atomicAdd(nacc + 4 * (size_t)vs[k], cx);
+    atomicAdd(nacc + 4 * (size_t)vs[k] + 1, cy);
+    atomicAdd(nacc + 4 * (size_t)vs[k] + 2, cz);
+  }
+}
+
+__global__ void k_normalize(float4* __restrict__ nrm, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q = nrm[i];
+  float l = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+  if (l > 0.f) nrm[i] = make_float4(q.x / l, q.y / l, q.z / l, 0.f);
+}
+
+int gn_final_vertices(mvs_deform* h) {
+  mvs_ctx* ctx = h->ctx;
+  cudaStream_t st = ctx->stream;
+  int64_t n = h->n;
+  {
+    ProfScope ps(ctx, "deform_final");
+    k_deform_final<<<div_up(n, 256), 256, 0, st>>>(h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, n,
+                                                   h->cur0.p);
+  }
+  MVS_CUDA(cudaMemsetAsync(h->curn0.p, 0, sizeof(float4) * n, st));
+  if (h->nf > 0) {
+    ProfScope ps(ctx, "vertex_normals", 2);
+    k_facet_normals<<<div_up(h->nf, 256), 256, 0, st>>>(h->cur0.p, h->facets.p, h->nf,
+                                                        reinterpret_cast<float*>(h->curn0.p));
+    k_normalize<<<div_up(n, 256), 256, 0, st>>>(h->curn0.p, n);
+  }
+  MVS_CUDA(cudaGetLastError());
+  h->cur_valid = true;
+  return MVS_OK;
+}
+
+// ------------------------------------------------------------------ energies
+__global__ void __launch_bounds__(256)
+    k_energy_fit(const float4* __restrict__ resid, int64_t begin, int64_t end, double w_fit,
+                 double* partials, unsigned* ticket, double* out) {
+  __shared__ double smem[32];
+  double v[1] = {0.0};
+  int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < end; i += stride) {
+    float4 r = __ldg(resid + i);
+    if (r.w > 0.f)
+      v[0] += w_fit * (double)r.w * ((double)r.x * r.x + (double)r.y * r.y + (double)r.z * r.z);
+  }
+  grid_reduce_sum<1>(v, smem, partials, ticket, out);
+}
+
+__global__ void __launch_bounds__(128)
+    k_energy_nodes(const float4* __restrict__ g, const float* __restrict__ x,
+                   const int* __restrict__ graph, int gk1, int64_t m, double w_rot, double w_reg,
+                   double* partials, unsigned* ticket, double* out) {
+  __shared__ double smem[64];
+  double v[2] = {0.0, 0.0};
+  int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; j < m; j += stride) {
+    NodeX n = load_node(x, (int)j);
+    double a[9];
+    for (int k = 0; k < 9; ++k) a[k] = n.a[k];
+    double r0 = a[0] * a[3] + a[1] * a[4] + a[2] * a[5];
+    double r1 = a[0] * a[6] + a[1] * a[7] + a[2] * a[8];
+    double r2 = a[3] * a[6] + a[4] * a[7] + a[5] * a[8];
+    double r3 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2] - 1.0;
+    double r4 = a[3] * a[3] + a[4] * a[4] + a[5] * a[5] - 1.0;
+    double r5 = a[6] * a[6] + a[7] * a[7] + a[8] * a[8] - 1.0;
+    v[0] += w_rot * (r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 + r5 * r5);
+    float4 gj = __ldg(g + j);
+    for (int e = 0; e < gk1; ++e) {
+      int l = __ldg(graph + (size_t)j * gk1 + e);
+      if (l < 0 || l == j) continue;
+      float4 gv = __ldg(g + l);
+      NodeX nl = load_node(x, l);
+      double ev[3] = {(double)gv.x - gj.x, (double)gv.y - gj.y, (double)gv.z - gj.z};
+      for (int rr = 0; rr < 3; ++rr) {
+        double r = (a[rr] * ev[0] + a[3 + rr] * ev[1] + a[6 + rr] * ev[2] - ev[rr]) +
+                   ((double)n.a[9 + rr] - (double)nl.a[9 + rr]);
+        v[1] += w_reg * r * r;
+      }
+    }
+  }
+  grid_reduce_sum<2>(v, smem, partials, ticket, out);
+}
+
+int gn_energy(mvs_deform* h, double energy[3]) {
+  mvs_ctx* ctx = h->ctx;
+  cudaStream_t st = ctx->stream;
+  int64_t b = h->shard_begin(), e = h->shard_end();
+  MVS_CUDA(cudaMemsetAsync(h->scal.p + S_EFIT, 0, sizeof(double) * 3, st));
+  if (e > b) {
+    ProfScope ps(ctx, "energy_fit");
+    int grid = grid_for(ctx, e - b, 256, 4);
+    MVS_TRY(h->partials.reserve((size_t)grid * 2 + 16));
+    k_energy_fit<<<grid, 256, 0, st>>>(h->resid.p, b, e, h->prm.w_fit, h->partials.p, h->ticket.p,
+                                       h->scal.p + S_EFIT);
+  }
+  if (ctx->comm && ctx->nranks > 1) MVS_TRY(comm_allreduce_sum_f64(ctx, h->scal.p + S_EFIT, 1));
+  {
+    ProfScope ps(ctx, "energy_nodes");
+    int grid = grid_for(ctx, h->m, 128, 2);
+    MVS_TRY(h->partials.reserve((size_t)grid * 2 + 16));
+    k_energy_nodes<<<grid, 128, 0, st>>>(h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m,
+                                         h->prm.w_rot, h->prm.w_reg, h->partials.p, h->ticket.p,
+                                         h->scal.p + S_EROT);
+  }
+  MVS_CUDA(cudaGetLastError());
+  MVS_TRY(d2h_sync(ctx, energy, h->scal.p + S_EFIT, sizeof(double) * 3));
+  return MVS_OK;
+}
+
+}  // namespace mvs

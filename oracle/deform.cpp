@@ -472,7 +472,9 @@ void orc_node_targets(const float* nodes, const float* node_normals, int64_t m, 
     std::sort(cands.begin(), cands.end(), [](const Cand& a, const Cand& b) {
       return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx);
     });
-    if ((int)cands.size() > maxResult) cands.resize(maxResult);  // quirk 6: cap instead of skip
+    // :286-297,315: when all maxResult slots fill, no -1 sentinel is found, newSize stays 0 and
+    // the node is skipped.  Replicated.
+    if ((int)cands.size() >= maxResult) continue;
     double nrm[3] = {node_normals[3 * i], node_normals[3 * i + 1], node_normals[3 * i + 2]};
     double nlen = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
     struct Item {

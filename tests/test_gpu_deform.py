@@ -1,0 +1,303 @@
+"""GPU parity tests: deformation graph + embedded-deformation Gauss-Newton through the C ABI vs the
+CPU oracle (oracle/deform.cpp).
+
+Bars: node sampling ids, kNN node indices and node-graph indices bit-exact;
+node weights bit-exact (FMA-free float32 on both sides); node-correspondence valid flags exact;
+deformed vertex positions within 1e-4 x bounding-box diagonal of the float64 oracle after the same
+fixed number of GN x PCG iterations.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from multiviewstitch_b200 import api
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-4  # x bbox diagonal (north_star)
+
+
+def mesh(nu=64, nv=48):
+    verts, faces = synth.uv_sphere(nu, nv)
+    pts = verts.astype(np.float32)
+    nrm = synth.vertex_normals(verts, faces).astype(np.float32)
+    return pts, nrm, faces
+
+
+def diag(p):
+    return float(np.linalg.norm(p.max(0) - p.min(0)))
+
+
+def oracle_graph(pts, ids, K=8):
+    nodes = pts[ids]
+    widx, w = oracle.node_weights(pts, nodes, 4)
+    graph = oracle.node_graph(nodes, K)
+    return nodes, widx, w, graph
+
+
+def expand_system(rp, col, B, rot, rhs, lam=0.0):
+    m = len(rp) - 1
+    H = np.zeros((12 * m, 12 * m))
+    I3 = np.eye(3)
+    for j in range(m):
+        for s in range(rp[j], rp[j + 1]):
+            l = col[s]
+            H[12 * j:12 * j + 12, 12 * l:12 * l + 12] += np.kron(B[s].astype(np.float64), I3)
+        H[12 * j:12 * j + 9, 12 * j:12 * j + 9] += rot[j]
+    H += lam * np.eye(12 * m)
+    return H, rhs.astype(np.float64).ravel()
+
+
+def test_sampling_matches_oracle(ctx):
+    pts, nrm, faces = mesh()
+    d = api.Deformation(pts, nrm, faces, ctx)
+    ids = d.SampleFPS(100, 7)
+    assert np.array_equal(ids, oracle.sample_fps(pts, 100, 7))
+    ids = d.UniformSampling(16)  # Deformation.cpp:63-106
+    assert np.array_equal(ids, oracle.uniform_sampling(pts, 16))
+    assert ids[0] == 0 and np.all(np.diff(ids) > 0)
+
+
+def test_weights_and_graph_bit_exact(ctx):
+    pts, nrm, faces = mesh()
+    d = api.Deformation(pts, nrm, faces, ctx)
+    ids = d.SampleFPS(150, 0)
+    nodes, widx, w, graph = oracle_graph(pts, ids)
+    g = d.KNearestNeighbor(8)  # Deformation.cpp:108-153
+    assert np.array_equal(g, graph)
+    gi, gw = d.Weights()
+    assert np.array_equal(gi, widx)
+    assert np.array_equal(gw, w)
+    assert np.allclose(gw.sum(1), 1.0, atol=1e-6)
+
+
+def test_weights_fewer_nodes_than_k(ctx):
+    pts, nrm, faces = mesh(16, 12)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    d.SetNodes([0, 50, 100])
+    d.BuildGraph(4, 8)
+    gi, gw = d.Weights()
+    widx, w = oracle.node_weights(pts, pts[[0, 50, 100]], 4)
+    assert np.array_equal(gi, widx) and np.array_equal(gw, w)
+
+
+def test_normal_equations_match_oracle(ctx):
+    pts, nrm, faces = mesh(32, 24)
+    rng = np.random.default_rng(3)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    ids = d.SampleFPS(40, 0)
+    m = len(ids)
+    nodes, widx, w, graph = oracle_graph(pts, ids)
+    d.BuildGraph(4, 8)
+    targets = synth.bend_twist(pts.astype(np.float64), 0.05)
+    tw = (rng.random(len(pts)) > 0.2).astype(np.float32)
+    x = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (m, 1)) + 0.05 * rng.normal(size=(m, 12))
+    x = x.astype(np.float32)
+    d.SetTargets(targets, tw)
+    prm = api.gn_params(gn_iters=1, pcg_iters=0, corr_mode=2, lam=0.0)
+    d.GNBegin(prm)
+    d.SetNodeState(x)
+    d.GNStep()  # assembles at x; 0 PCG iterations leave x unchanged
+    assert np.array_equal(d.NodeState(), x)
+    H, g = expand_system(*d.System())
+    oprm = oracle.gn_params(lam=0.0)
+    Ho, go = oracle.gn_assemble_dense(pts, ids, widx, w, graph, targets, tw, oprm, x.astype(np.float64))
+    assert np.allclose(H, Ho, rtol=1e-4, atol=2e-5 * np.abs(Ho).max())
+    assert np.allclose(g, go, rtol=1e-4, atol=2e-5 * np.abs(go).max())
+    # block pattern covers every structurally non-zero block of the oracle's dense matrix
+    assert np.all((np.abs(Ho) > 0) <= ((np.abs(H) > 0) | (np.abs(Ho) < 1e-7 * np.abs(Ho).max())))
+    d.GNEnd()
+
+
+def test_energy_matches_oracle(ctx):
+    pts, nrm, faces = mesh(32, 24)
+    rng = np.random.default_rng(5)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    ids = d.SampleFPS(40, 0)
+    m = len(ids)
+    nodes, widx, w, graph = oracle_graph(pts, ids)
+    targets = synth.bend_twist(pts.astype(np.float64), 0.05)
+    x = (np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (m, 1))
+         + 0.05 * rng.normal(size=(m, 12))).astype(np.float32)
+    d.SetTargets(targets)
+    d.GNBegin(api.gn_params(corr_mode=2))
+    d.SetNodeState(x)
+    e = d.Energy()
+    # oracle energies are evaluated by the assembly at the entry state of a GN iteration
+    _, _, eo = oracle.gn_solve(pts, None, ids, widx, w, graph,
+                               oracle.gn_params(gn_iters=1, pcg_iters=0), x.astype(np.float64),
+                               targets=targets)
+    assert np.allclose(e, eo, rtol=1e-5)
+    d.GNEnd()
+
+
+@pytest.mark.parametrize("shape", [(64, 48, 120), (160, 120, 400)])
+def test_gn_fixed_targets_parity(ctx, shape):
+    nu, nv, m = shape
+    pts, nrm, faces = mesh(nu, nv)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    ids = d.SampleFPS(m, 0)
+    nodes, widx, w, graph = oracle_graph(pts, ids)
+    targets = synth.bend_twist(pts.astype(np.float64), 0.05)
+    d.SetTargets(targets)
+    d.GNBegin(api.gn_params(gn_iters=10, pcg_iters=20, corr_mode=2))
+    for _ in range(10):
+        d.GNStep()
+    d.GNEnd()
+    out = d.Vertices()
+    xo, oo, eo = oracle.gn_solve(pts, None, ids, widx, w, graph,
+                                 oracle.gn_params(gn_iters=10, pcg_iters=20), targets=targets)
+    err = np.abs(out - oo).max()
+    assert err <= POS_TOL * diag(pts), err
+    # the fit actually moved the mesh onto the target
+    assert np.abs(oo - targets).max() < 0.3 * np.abs(pts - targets).max()
+    assert np.allclose(d.NodeState(), xo, atol=2e-3)
+
+
+def test_gn_nn_correspondence_parity(ctx):
+    # corr_mode 1: exact-NN correspondences re-derived every GN iteration (north_star)
+    pts, nrm, faces = mesh(96, 72)
+    tv = synth.bend_twist(synth.uv_sphere(200, 150)[0], 0.03).astype(np.float32)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    ids = d.SampleFPS(200, 0)
+    nodes, widx, w, graph = oracle_graph(pts, ids)
+    d.SetTarget(tv)
+    prm = api.gn_params(gn_iters=6, pcg_iters=20, corr_mode=1)
+    d.GNBegin(prm)
+    for _ in range(6):
+        d.GNStep()
+    d.GNEnd()
+    out = d.Vertices()
+    xo, oo, eo = oracle.gn_solve(pts, None, ids, widx, w, graph,
+                                 oracle.gn_params(gn_iters=6, pcg_iters=20, corr_mode=1), tpts=tv)
+    err = np.abs(out - oo).max()
+    assert err <= POS_TOL * diag(pts), err
+
+
+def test_rigid_motion_recovered(ctx):
+    pts, nrm, faces = mesh()
+    R = synth.axis_angle([0.2, 1.0, 0.1], 0.3)
+    tt = np.array([0.1, -0.05, 0.2])
+    targets = pts.astype(np.float64) @ R.T + tt
+    d = api.Deformation(pts, nrm, faces, ctx)
+    d.SampleFPS(60, 0)
+    d.SetTargets(targets)
+    d.GNBegin(api.gn_params(gn_iters=8, pcg_iters=200, corr_mode=2))
+    for _ in range(8):
+        d.GNStep()
+    d.GNEnd()
+    assert np.abs(d.Vertices() - targets).max() < 2e-4
+    A = d.NodeState()[:, :9].reshape(-1, 3, 3).transpose(0, 2, 1)
+    assert np.allclose(A, R[None], atol=2e-3)
+    # identity targets: zero update
+    d2 = api.Deformation(pts, nrm, faces, ctx)
+    d2.SampleFPS(60, 0)
+    d2.SetTargets(pts.astype(np.float64))
+    d2.GNBegin(api.gn_params(gn_iters=2, pcg_iters=20, corr_mode=2))
+    d2.GNStep(); d2.GNStep(); d2.GNEnd()
+    assert np.abs(d2.Vertices() - pts).max() < 1e-5
+
+
+def test_node_targets_match_oracle(ctx):
+    # Deformation.cpp:266-381
+    verts, faces = synth.uv_sphere(40, 30, bumps=0.0)
+    pts = verts.astype(np.float32)
+    nrm = (verts / np.linalg.norm(verts, axis=1, keepdims=True)).astype(np.float32)
+    tv, tf = synth.uv_sphere(120, 90, radius=1.1, bumps=0.02)
+    tv = tv.astype(np.float32)
+    tn = synth.vertex_normals(tv.astype(np.float64), tf).astype(np.float32)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    ids = np.arange(0, len(pts), 37, dtype=np.int32)
+    d.SetNodes(ids)
+    graph = d.KNearestNeighbor(8)
+    d.SetTarget(tv, tn)
+    for sweeps in (0, 2):
+        c, v = d.NodeTargets(100.0, 100.0, sweeps)
+        co, vo = oracle.node_targets(pts[ids], nrm[ids], tv, tn, graph, 100.0, 100.0, sweeps)
+        assert np.array_equal(v, vo)
+        assert v.mean() > 0.9
+        assert np.allclose(c, co, rtol=0, atol=1e-12)
+    c, v = d.NodeTargets(0.05, 100.0, 0)
+    co, vo = oracle.node_targets(pts[ids], nrm[ids], tv, tn, graph, 0.05, 100.0, 0)
+    assert np.array_equal(v, vo) and np.allclose(c, co, atol=1e-12)
+    d.SetTarget(tv, -tn)  # flipped normals: nothing is compatible (Deformation.cpp:306-312)
+    c, v = d.NodeTargets(100.0, 100.0, 0)
+    assert v.sum() == 0 and np.allclose(c, pts[ids])
+
+
+def test_deform_reference_signature(ctx):
+    """Deformation(points,normals,facets); Deform(tpts,tnormals,100,100) — the Processor.cpp:1135-1137
+    call sequence — against the oracle pipeline: node targets -> smoothing -> ED Gauss-Newton."""
+    verts, faces = synth.uv_sphere(60, 45, bumps=0.0)
+    pts = verts.astype(np.float32)
+    nrm = synth.vertex_normals(verts, faces).astype(np.float32)
+    tv, tf = synth.uv_sphere(150, 110, radius=1.08, bumps=0.03)
+    tv = tv.astype(np.float32)
+    tn = synth.vertex_normals(tv.astype(np.float64), tf).astype(np.float32)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    ids = d.UniformSampling()
+    prm = api.gn_params(gn_iters=5, pcg_iters=30, corr_mode=0)
+    d.Deform(tv, tn, 100.0, 100.0, params=prm)
+    out = d.Vertices()
+    nodes, widx, w, graph = oracle_graph(pts, ids)
+    ctrl, valid = oracle.node_targets(nodes, nrm[ids], tv, tn, graph, 100.0, 100.0, 2)
+    targets = np.zeros((len(pts), 3))
+    tw = np.zeros(len(pts), np.float32)
+    targets[ids] = ctrl.astype(np.float32)
+    tw[ids] = 1.0
+    xo, oo, eo = oracle.gn_solve(pts, None, ids, widx, w, graph,
+                                 oracle.gn_params(gn_iters=5, pcg_iters=30), targets=targets,
+                                 tweights=tw)
+    err = np.abs(out - oo).max()
+    assert err <= POS_TOL * diag(pts), err
+    # the template moved outwards towards the r=1.08 target
+    assert np.linalg.norm(out, axis=1).mean() > 1.04
+    # normals recomputed as in exportOBJ (Deformation.h:86-128)
+    no = oracle.vertex_normals(out, faces)
+    assert np.abs(d.Normals() - no).max() < 2e-3
+    assert np.array_equal(d.Facets(), faces)
+
+
+def test_deform_threshold_variant(ctx):
+    # Deformation.cpp:155-230: 1-NN target per node, reject d2 > threshold or cos < 0.5
+    verts, faces = synth.uv_sphere(40, 30, bumps=0.0)
+    pts = verts.astype(np.float32)
+    nrm = synth.vertex_normals(verts, faces).astype(np.float32)
+    tv = (synth.uv_sphere(100, 80, radius=1.05, bumps=0.0)[0]).astype(np.float32)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    d.SampleFPS(80, 0)
+    d.Deform(tv, None, 0.05, params=api.gn_params(gn_iters=4, pcg_iters=30))
+    r = np.linalg.norm(d.Vertices(), axis=1)
+    assert 1.03 < r.mean() < 1.06
+    with pytest.raises(api.MvsError):
+        api.Deformation(pts, nrm, faces, ctx).Deform(tv, None, 0.05)  # no nodes: Deformation.cpp:184
+
+
+def test_error_codes_instead_of_exit(ctx):
+    pts, nrm, faces = mesh(16, 12)
+    bad = faces.copy()
+    bad[0, 0] = len(pts) + 5
+    with pytest.raises(api.MvsError) as e:
+        api.Deformation(pts, nrm, bad, ctx)  # the reference exits on an invalid mesh (:42-45)
+    assert e.value.status == -1
+    d = api.Deformation(pts, nrm, faces, ctx)
+    with pytest.raises(api.MvsError):
+        d.GNStep()  # before GNBegin
+    d.SampleFPS(10, 0)
+    with pytest.raises(api.MvsError):
+        d.GNBegin(api.gn_params(corr_mode=1)); d.GNStep()  # no target set
+
+
+def test_export_obj_format(ctx, tmp_path):
+    pts, nrm, faces = mesh(12, 8)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    f = tmp_path / "deform.obj"
+    api.exportOBJ(str(f), d)
+    lines = [l for l in f.read_text().splitlines() if l and not l.startswith("#")]
+    assert lines[0].startswith("vn ") and lines[1].startswith("v ")
+    assert sum(l.startswith("v ") for l in lines) == len(pts)
+    fl = [l for l in lines if l.startswith("f ")]
+    assert len(fl) == len(faces)
+    a = faces[0] + 1
+    assert fl[0] == f"f {a[0]}//{a[0]} {a[1]}//{a[1]} {a[2]}//{a[2]}"
