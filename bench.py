@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the non-rigid alignment hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], "C3"): one closed 1,000,002-vertex mesh (UV sphere with
+bumps), a 4096-node deformation graph (farthest-point sampling, k = 4 node weights, 8-neighbour
+node graph), target = the mesh warped by a smooth bend+twist (5 % of the bbox diagonal), exact-NN
+correspondences re-derived in every Gauss-Newton iteration, 10 GN iterations x 20 block-Jacobi PCG
+iterations, then the vertex update (deformed vertices + recomputed normals).
+
+A "step" is one such 10-iteration solve starting from the identity node state.
+  value  = GN iterations / s with every input resident in HBM (K steps, device-timed)
+  e2e    = the same metric through the host-buffer C ABI a reference caller would use:
+           mvs_deform_set_target_f32(host) -> gn_begin -> 10 x gn_step -> gn_end ->
+           mvs_deform_get_vertices_f32(host), H2D/D2H inside the timed region
+  --gpus N: one process per GPU, every rank solves its own mesh (independent objects, as the
+           reference's independent view pairs — no data-path collective), scaling "weak".
+  --mode shard: ONE mesh vertex-sharded over the ranks with an NCCL all-reduce of the J^T J / J^T r
+           node blocks (configs[4] layout), scaling "strong".
+  --impl reference: the CPU oracle (oracle/, single thread like the reference) on the same
+           workload, bounded to --steps solves of --ref-gn-iters iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "deformation_gn_iters_per_s"
+UNIT = "GN iters/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="objects", choices=["objects", "shard"])
+    ap.add_argument("--nu", type=int, default=1000, help="UV-sphere longitudes (verts = nu*nu+2)")
+    ap.add_argument("--nodes", type=int, default=4096)
+    ap.add_argument("--gn-iters", type=int, default=10)
+    ap.add_argument("--pcg-iters", type=int, default=20)
+    ap.add_argument("--ref-gn-iters", type=int, default=10)
+    ap.add_argument("--ref-budget-s", type=float, default=120.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--nn-sweep", action="store_true", help="also time NN-corr/s + SRT at 1e7 points")
+    return ap.parse_args()
+
+
+def workload(args, seed_shift=0):
+    from multiviewstitch_b200 import synth
+    verts, faces = synth.uv_sphere(args.nu, args.nu + 1, seed=seed_shift)
+    if seed_shift:
+        # independent objects per rank: a different similarity of the same shape
+        R = synth.axis_angle([1, 2 + seed_shift, 3], 0.1 * seed_shift)
+        verts = (1.0 + 0.01 * seed_shift) * verts @ R.T
+    pts = verts.astype(np.float32)
+    nrm = synth.vertex_normals(verts, faces).astype(np.float32)
+    tgt = synth.bend_twist(verts, 0.05).astype(np.float32)
+    return pts, nrm, faces, tgt
+
+
+def workload_name(args, n):
+    return (f"C3: {n}-vertex mesh, {args.nodes}-node graph (k=4, K=8), NN correspondences per "
+            f"iteration, {args.gn_iters} GN x {args.pcg_iters} PCG + vertex update")
+
+
+# ------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8:
+                self.samples.append(f)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for f in self.samples:
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------- reference (CPU) arm
+def cpu_solve(args, pts, tgt, gn_iters):
+    import oracle
+    t0 = time.perf_counter()
+    ids = oracle.sample_fps(pts, args.nodes, 0)
+    nodes = pts[ids]
+    widx, w = oracle.node_weights(pts, nodes, 4)
+    graph = oracle.node_graph(nodes, 8)
+    t_setup = time.perf_counter() - t0
+    prm = oracle.gn_params(gn_iters=gn_iters, pcg_iters=args.pcg_iters, corr_mode=1)
+    t0 = time.perf_counter()
+    x, out, e = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, tpts=tgt)
+    t_solve = time.perf_counter() - t0
+    return t_setup, t_solve, out, (ids, widx, w, graph)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pts, nrm, faces, tgt = workload(args)
+    import oracle
+    ids = oracle.sample_fps(pts, args.nodes, 0)
+    nodes = pts[ids]
+    widx, w = oracle.node_weights(pts, nodes, 4)
+    graph = oracle.node_graph(nodes, 8)
+    prm = oracle.gn_params(gn_iters=args.ref_gn_iters, pcg_iters=args.pcg_iters, corr_mode=1)
+    times = []
+    t_begin = time.perf_counter()
+    for s in range(args.warmup + args.steps):
+        if s < args.warmup and s > 0:
+            continue  # one warm-up pass is enough to page the arrays in; the CPU has no JIT
+        if times and time.perf_counter() - t_begin > args.ref_budget_s:
+            break  # bounded sample: keep the whole run within a few minutes
+        t0 = time.perf_counter()
+        oracle.gn_solve(pts, None, ids, widx, w, graph, prm, tpts=tgt)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    val = args.ref_gn_iters * len(times) / tot
+    sample = (f"{len(times)} solve(s) of {args.ref_gn_iters} GN x {args.pcg_iters} PCG iterations on the "
+              f"full {len(pts)}-vertex / {args.nodes}-node workload (kd-tree NN, no vertex update)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, len(pts)), "l2": "inputs larger than L2"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": sample,
+                             "note": "single thread because the reference is single-threaded; "
+                                     "the reference itself (MSVC + CGAL/OpenCV/Eigen) cannot be "
+                                     "built here, so this is the oracle port"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_cores": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- B200 arm
+ALGO_BYTES_DOC = {
+    # per GN iteration, n vertices, nt target points, m nodes, nnz pattern blocks
+    "gn_deform_corr": "n*(16 v + 16 idx + 16 w + 16 resid) + nt*16 target cells",
+    "gn_assemble_fit": "n*(16 v + 16 idx + 16 w + 16 resid) + (nnz*64 + m*48) system write",
+    "pcg_iterations": "iters*((nnz*64 + m*324) matrix + m*576 Minv + 10*m*48 vectors)",
+}
+
+
+def algo_bytes(name, n, nt, m, nnz, pcg_iters):
+    if name == "gn_deform_corr":
+        return n * 64 + nt * 16
+    if name == "gn_assemble_fit":
+        return n * 64 + nnz * 64 + m * 48
+    if name == "pcg_iterations":
+        return pcg_iters * (nnz * 64 + m * 324 + m * 576 + 10 * m * 48)
+    if name == "deform_final":
+        return n * (48 + 16) + 0
+    return None
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from multiviewstitch_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    ctx = api.Context(local, stream.cuda_stream)
+    shard = args.mode == "shard" and world > 1
+
+    pts, nrm, faces, tgt = workload(args, 0 if (shard or world == 1) else rank)
+    n, nt = len(pts), len(tgt)
+    if shard:
+        uid = [api.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+
+    with torch.cuda.stream(stream):
+        d = api.Deformation(pts, nrm, faces, ctx)
+        d.SampleFPS(args.nodes, 0)
+        d.BuildGraph(4, 8)
+        m = len(d.Nodes())
+        rp, col, *_ = d.System()
+        nnz = len(col)
+        if shard:
+            per = (n + world - 1) // world
+            d.SetShard(rank * per, min(n, (rank + 1) * per))
+        # device-resident target (float4 records) for the HBM-resident leg
+        tgt4 = torch.zeros((nt, 4), dtype=torch.float32, device="cuda")
+        tgt4[:, :3] = torch.from_numpy(tgt).cuda()
+        stream.synchronize()
+        d.SetTargetDev(tgt4.data_ptr(), None, nt)
+        prm = api.gn_params(gn_iters=args.gn_iters, pcg_iters=args.pcg_iters, corr_mode=1)
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+        def solve():
+            d.GNBegin(prm)
+            for _ in range(args.gn_iters):
+                d.GNStep()
+            d.GNEnd()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(max(3, args.warmup)):
+            solve()
+        # ---- timed: device-resident
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(args.steps)]
+        ctx.prof_enable(True)
+        ctx.prof_reset()
+        ctx.launch_count_reset()
+        clocks = Clocks(local)
+        if rank == 0:
+            clocks.start()
+        barrier()
+        t_wall0 = time.perf_counter()
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)  # L2 flush between timed steps (outside the event pair)
+            ev[s][0].record(stream)
+            solve()
+            ev[s][1].record(stream)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        launches = ctx.launch_count()
+        prof = ctx.prof()
+        ctx.prof_enable(False)
+        clk = clocks.stop() if rank == 0 else None
+        out_dev = d.Vertices()
+
+        # ---- timed: end to end through the host-buffer C ABI
+        e2e_ms = None
+        if not args.no_e2e and not shard:
+            tgt_pin = torch.from_numpy(tgt).pin_memory()
+            out_pin = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+            tgt_h, out_h = tgt_pin.numpy(), out_pin.numpy()
+            import ctypes as C
+
+            def solve_e2e():
+                d.SetTarget(tgt_h)  # H2D + NN grid build
+                solve()
+                api.check(api.lib().mvs_deform_get_vertices_f32(
+                    d._h, out_h.ctypes.data_as(C.POINTER(C.c_float))))  # D2H
+
+            for _ in range(2):
+                solve_e2e()
+            ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(args.steps)]
+            barrier()
+            for s in range(args.steps):
+                flush.fill_(s & 0xFF)
+                ev2[s][0].record(stream)
+                solve_e2e()
+                ev2[s][1].record(stream)
+            barrier()
+            e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+            # float32 atomics make the block sums order-dependent: equal within the parity bar
+            dg = float(np.linalg.norm(pts.max(0) - pts.min(0)))
+            e2e_diff = float(np.abs(out_h - out_dev).max() / dg)
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_max = t[0].item(), t[1].item()
+        if e2e_ms is not None:
+            e2e_ms = e2e_max
+    solves_total = args.steps * (1 if shard else world)
+    value = args.gn_iters * solves_total / (dev_ms * 1e-3)
+
+    if rank == 0:
+        # roofline of the dominant kernel family over the timed region
+        fam = {k: v for k, v in prof.items() if algo_bytes(k, n, nt, m, nnz, args.pcg_iters)}
+        top = max(fam, key=lambda k: fam[k][0])
+        calls = args.steps * args.gn_iters
+        avg_ms = fam[top][0] / calls
+        peaks = {}
+        pk_file = ROOT / "MEASURED_PEAKS.json"
+        if pk_file.exists():
+            peaks = json.loads(pk_file.read_text())
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        n_local = (min(n, (rank + 1) * ((n + world - 1) // world)) - rank * ((n + world - 1) // world)) if shard else n
+        ab = algo_bytes(top, n_local, nt, m, nnz, args.pcg_iters)
+        achieved = ab / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get(top)
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch_group": ab, "avg_ms": avg_ms,
+                    "launches_per_group": (2 * args.pcg_iters if top == "pcg_iterations" else 1),
+                    "bytes_formula": ALGO_BYTES_DOC.get(top)}
+        families = {}
+        for k, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            b = algo_bytes(k, n_local, nt, m, nnz, args.pcg_iters)
+            per = ms / calls if k.startswith(("gn_", "pcg_")) else ms / args.steps
+            families[k] = {"ms_per_step": ms / args.steps, "launches": cnt,
+                           "share": ms / dev_ms if world == 1 or True else None}
+            if b:
+                families[k]["GBps"] = b / (per * 1e-3) / 1e9
+                families[k]["frac_hbm"] = families[k]["GBps"] / peak
+
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            t_setup, t_solve, out_cpu, _ = cpu_solve(args, pts, tgt, args.ref_gn_iters)
+            diag = float(np.linalg.norm(pts.max(0) - pts.min(0)))
+            cpu = {"value": args.ref_gn_iters / t_solve, "unit": UNIT, "cores": 1, "kind": "port",
+                   "host_cores": os.cpu_count(),
+                   "sample": f"1 solve of {args.ref_gn_iters} GN x {args.pcg_iters} PCG iterations on the "
+                             f"full workload ({t_solve:.1f} s; graph setup {t_setup:.1f} s not counted)"}
+            if args.ref_gn_iters == args.gn_iters:
+                cpu["max_abs_diff_vs_gpu_over_bbox_diag"] = float(np.abs(out_cpu - out_dev).max() / diag)
+
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "strong" if shard else "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args, n), "verts": n, "target_points": nt,
+                           "nodes": m, "pattern_blocks": nnz, "mode": args.mode,
+                           "step": f"one {args.gn_iters}-iteration solve",
+                           "l2": "512 MiB flush write between timed steps; per-iteration working "
+                                 "set ~100 MB"},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": None if e2e_ms is None else {
+                    "value": args.gn_iters * args.steps * world / (e2e_ms * 1e-3), "unit": UNIT,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(nt * 12), "d2h_bytes_per_step": int(n * 12),
+                    "max_abs_diff_vs_resident_over_bbox_diag": e2e_diff},
+                "gpu_launches": int(launches), "clocks": clk,
+                "wall_s_timed_region": t_wall, "families": families}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

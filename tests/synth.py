@@ -1,109 +1,2 @@
-"""Seeded synthetic inputs shared by the tests, bench.py and the golden-vector generator.
-
-Shapes/constants follow SURVEY.md §8(d): C1 cameras 640x480, fx=fy=525, cx=319.5, cy=239.5; planted
-similarity s=1.37, R=axis-angle(0.4 rad, (1,2,3)/sqrt(14)), t=(0.3,-0.2,0.5).
-"""
-from __future__ import annotations
-
-import numpy as np
-
-PLANTED_S = 1.37
-PLANTED_T = np.array([0.3, -0.2, 0.5])
-
-
-def axis_angle(axis, angle):
-    a = np.asarray(axis, np.float64)
-    a = a / np.linalg.norm(a)
-    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
-    return np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * (K @ K)
-
-
-PLANTED_R = axis_angle([1, 2, 3], 0.4)
-
-
-def c1_intrinsics():
-    return np.array([[525.0, 0, 319.5], [0, 525.0, 239.5], [0, 0, 1.0]])
-
-
-def sphere_points(n, seed, noise=0.0, radius=1.0, center=(0, 0, 0)):
-    rng = np.random.default_rng(seed)
-    v = rng.normal(size=(n, 3))
-    v /= np.linalg.norm(v, axis=1, keepdims=True)
-    v = v * radius + np.asarray(center)
-    if noise:
-        v = v + rng.normal(scale=noise, size=v.shape)
-    return v
-
-
-def planted_pairs(n, seed=1234, noise=1e-3, center=(0.0, 0.0, 5.0)):
-    """C2-style pairs: p on a sphere (in front of camera 1), q = s R p + t (+ noise)."""
-    rng = np.random.default_rng(seed + 1)
-    p = sphere_points(n, seed, noise=noise, center=center)
-    q = PLANTED_S * p @ PLANTED_R.T + PLANTED_T
-    if noise:
-        q = q + rng.normal(scale=noise, size=q.shape)
-    return p, q
-
-
-def camera_pair():
-    """cam1 at the origin looking down +z; cam2 sees the transformed frame: x2 = s R x1 + t, so a
-    camera with pose [R2|t2] = [R^T/.. ] keeps the scene in front.  We simply look at the mapped
-    sphere centre from 5 units away along -z of the second frame."""
-    K = c1_intrinsics()
-    R1, t1 = np.eye(3), np.zeros(3)
-    c2 = PLANTED_S * PLANTED_R @ np.array([0, 0, 5.0]) + PLANTED_T
-    R2 = axis_angle([0, 1, 0], np.deg2rad(10.0))
-    # place camera 2 so that the mapped centre sits at depth 5*s on its optical axis
-    t2 = np.array([0, 0, 5.0 * PLANTED_S]) - R2 @ c2
-    return (K, R1, t1, 640, 480), (K, R2, t2, 640, 480)
-
-
-def uv_sphere(nu, nv, radius=1.0, bumps=0.05, seed=0):
-    """Closed genus-0 triangle mesh (UV sphere with low-frequency bumps): (nu*(nv-1)+2) verts."""
-    th = np.linspace(0, np.pi, nv + 1)[1:-1]
-    ph = np.linspace(0, 2 * np.pi, nu, endpoint=False)
-    T, P = np.meshgrid(th, ph, indexing="ij")
-    r = radius * (1 + bumps * (np.sin(3 * T) * np.cos(2 * P) + 0.5 * np.cos(5 * T + 1.0) * np.sin(3 * P)))
-    x = r * np.sin(T) * np.cos(P)
-    y = r * np.sin(T) * np.sin(P)
-    z = r * np.cos(T)
-    ring = np.stack([x, y, z], -1).reshape(-1, 3)
-    verts = np.concatenate([[[0, 0, radius]], ring, [[0, 0, -radius]]], 0)
-    nr = nv - 1
-    faces = []
-    idx = lambda i, j: 1 + i * nu + (j % nu)
-    j = np.arange(nu)
-    # caps
-    faces.append(np.stack([np.zeros(nu, int), idx(0, j), idx(0, j + 1)], 1))
-    south = 1 + nr * nu
-    faces.append(np.stack([np.full(nu, south), idx(nr - 1, j + 1), idx(nr - 1, j)], 1))
-    for i in range(nr - 1):
-        a, b, c, d = idx(i, j), idx(i, j + 1), idx(i + 1, j), idx(i + 1, j + 1)
-        faces.append(np.stack([a, c, b], 1))
-        faces.append(np.stack([b, c, d], 1))
-    faces = np.concatenate(faces, 0).astype(np.int32)
-    return verts.astype(np.float64), faces
-
-
-def vertex_normals(verts, faces):
-    v = verts
-    n = np.cross(v[faces[:, 1]] - v[faces[:, 0]], v[faces[:, 2]] - v[faces[:, 0]])
-    ln = np.linalg.norm(n, axis=1, keepdims=True)
-    n = n / np.where(ln > 0, ln, 1)
-    out = np.zeros_like(v)
-    for k in range(3):
-        np.add.at(out, faces[:, k], n)
-    ln = np.linalg.norm(out, axis=1, keepdims=True)
-    return out / np.where(ln > 0, ln, 1)
-
-
-def bend_twist(verts, amp=0.05):
-    """Smooth bend+twist warp, amplitude as a fraction of the bbox diagonal (C3 target)."""
-    v = np.asarray(verts, np.float64)
-    diag = np.linalg.norm(v.max(0) - v.min(0))
-    z = v[:, 2] / (np.abs(v[:, 2]).max() + 1e-12)
-    ang = 0.6 * amp * 10 * z  # twist about z
-    c, s = np.cos(ang), np.sin(ang)
-    out = np.stack([c * v[:, 0] - s * v[:, 1], s * v[:, 0] + c * v[:, 1], v[:, 2]], 1)
-    out[:, 0] += amp * diag * z * z  # bend
-    return out
+"""Seeded synthetic inputs — shared with bench.py; the definitions live in the package."""
+from multiviewstitch_b200.synth import *  # noqa: F401,F403
