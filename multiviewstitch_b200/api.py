@@ -498,3 +498,207 @@ class Deformation:
 def exportOBJ(filename: str, deform: Deformation):
     """[ref: Deformation/Deformation.h:174-221]"""
     check(lib().mvs_deform_export_obj(deform._h, filename.encode()))
+
+
+# ============================================================================ point sets / alignment
+def apply_srt(pts, normals, scale, R, t, inverse=False, ctx: Context | None = None):
+    """v = s R p + t, n = R n [ref: Alignment/Alignment.cpp:31-34, Processor.cpp:1025-1026];
+    inverse: p_k = (1/s) R^T (p - t), n_k = R^T n [ref: Processor/Processor.cpp:1177-1189]."""
+    p = _f64(pts).reshape(-1, 3).copy()
+    nr = _f64(normals).reshape(-1, 3).copy() if normals is not None else None
+    R, t = _f64(R).reshape(9), _f64(t).reshape(3)
+    fn = lib().mvs_apply_srt_inverse if inverse else lib().mvs_apply_srt
+    check(fn(_ctxh(ctx), _ptr(p, C.c_double), _ptr(nr, C.c_double), C.c_int64(len(p)),
+             C.c_double(scale), _ptr(R, C.c_double), _ptr(t, C.c_double)))
+    return p, nr
+
+
+def apply_srt_dev(in_ptr: int, out_ptr: int, n: int, scale, R, t, ctx: Context | None = None):
+    R, t = _f64(R).reshape(9), _f64(t).reshape(3)
+    check(lib().mvs_apply_srt_dev_f32(_ctxh(ctx), _dev(in_ptr), _dev(out_ptr), C.c_int64(n),
+                                      C.c_double(scale), _ptr(R, C.c_double), _ptr(t, C.c_double)))
+
+
+class PointSetUtils:
+    """[ref: SetUtils/PointSetUtils.h / .cpp:3-62]"""
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx = ctx
+
+    def SetInput(self, points):
+        self.points = _f64(points).reshape(-1, 3)
+        b, mn, mx, pv, ev = (np.empty(3), np.empty(3), np.empty(3), np.empty(9), np.empty(3))
+        check(lib().mvs_pointset_stats(_ctxh(self._ctx), _ptr(self.points, C.c_double),
+                                       C.c_int64(len(self.points)), _ptr(b, C.c_double),
+                                       _ptr(mn, C.c_double), _ptr(mx, C.c_double),
+                                       _ptr(pv, C.c_double), _ptr(ev, C.c_double)))
+        self._b, self._mn, self._mx, self._pv, self._ev = b, mn, mx, pv.reshape(3, 3), ev
+
+    def GetBarycenter(self):
+        return self._b
+
+    def GetBoundingBox(self):
+        return self._mn, self._mx
+
+    def CalcPivots(self, pivot_num: int = 3):
+        return self._pv[:, :pivot_num].copy()
+
+    def Eigenvalues(self):
+        return self._ev
+
+
+def project_range(pts, origin, axis, labels=None, label=0, ctx: Context | None = None):
+    p = _f64(pts).reshape(-1, 3)
+    lb = _i32(labels) if labels is not None else None
+    o, a = _f64(origin).reshape(3), _f64(axis).reshape(3)
+    tmin, tmax = C.c_double(), C.c_double()
+    imin, imax = C.c_int64(), C.c_int64()
+    check(lib().mvs_project_range(_ctxh(ctx), _ptr(p, C.c_double), C.c_int64(len(p)),
+                                  _ptr(lb, C.c_int32), C.c_int32(label), _ptr(o, C.c_double),
+                                  _ptr(a, C.c_double), C.byref(tmin), C.byref(tmax),
+                                  C.byref(imin), C.byref(imax)))
+    return tmin.value, tmax.value, imin.value, imax.value
+
+
+def align_params(**kw) -> AlignParams:
+    p = AlignParams()
+    check(lib().mvs_align_default_params(C.byref(p)))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown alignment parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+class Alignment:
+    """[ref: Alignment/Alignment.h:21-36].  The reference mutates its std::vector arguments in
+    place; here the updated arrays are returned."""
+
+    def __init__(self, ctx: Context | None = None, params: AlignParams | None = None):
+        self._ctx = ctx
+        self.params = params or align_params()
+
+    def Align(self, src, s_normals, s_labels, tgt, t_normals, t_facets, viewRay,
+              ground_ray=None):
+        """Returns (src, s_normals, tgt, t_normals, t_facets, t_labels, groundRay)."""
+        s = _f64(src).reshape(-1, 3).copy()
+        sn = _f64(s_normals).reshape(-1, 3).copy() if s_normals is not None else None
+        sl = _i32(s_labels)
+        t = _f64(tgt).reshape(-1, 3).copy()
+        tn = _f64(t_normals).reshape(-1, 3).copy() if t_normals is not None else None
+        tf = _i32(t_facets).reshape(-1).copy()
+        nt, ntf = C.c_int64(len(t)), C.c_int64(len(tf) // 3)
+        vr = _f64(viewRay).reshape(3)
+        gr = _f64(ground_ray).reshape(3).copy() if ground_ray is not None else np.zeros(3)
+        tl = np.empty(len(t), np.int32)
+        check(lib().mvs_align(_ctxh(self._ctx), _ptr(s, C.c_double), _ptr(sn, C.c_double),
+                              C.c_int64(len(s)), _ptr(sl, C.c_int32), _ptr(t, C.c_double),
+                              _ptr(tn, C.c_double), C.byref(nt), _ptr(tf, C.c_int32),
+                              C.byref(ntf), _ptr(vr, C.c_double), C.byref(self.params),
+                              _ptr(tl, C.c_int32), _ptr(gr, C.c_double)))
+        n, f = nt.value, ntf.value
+        return (s, sn, t[:n].copy(), tn[:n].copy() if tn is not None else None,
+                tf[:3 * f].reshape(-1, 3).copy(), tl[:n].copy(), gr)
+
+    def RemoveGround(self, points, normals, facets):
+        """[ref: Alignment/Alignment.cpp:79-233] -> (points, normals, facets, groundRay)"""
+        p = _f64(points).reshape(-1, 3).copy()
+        nr = _f64(normals).reshape(-1, 3).copy() if normals is not None else None
+        f = _i32(facets).reshape(-1).copy()
+        n, nf = C.c_int64(len(p)), C.c_int64(len(f) // 3)
+        gr = np.zeros(3)
+        check(lib().mvs_remove_ground(_ctxh(self._ctx), _ptr(p, C.c_double), _ptr(nr, C.c_double),
+                                      C.byref(n), _ptr(f, C.c_int32), C.byref(nf),
+                                      C.byref(self.params), _ptr(gr, C.c_double)))
+        return (p[:n.value].copy(), nr[:n.value].copy() if nr is not None else None,
+                f[:3 * nf.value].reshape(-1, 3).copy(), gr)
+
+    def RetainConnectRegion(self, points, normals, facets):
+        """[ref: Alignment/Alignment.cpp:618-654]"""
+        p = _f64(points).reshape(-1, 3).copy()
+        nr = _f64(normals).reshape(-1, 3).copy() if normals is not None else None
+        f = _i32(facets).reshape(-1).copy()
+        n, nf = C.c_int64(len(p)), C.c_int64(len(f) // 3)
+        check(lib().mvs_retain_connected(_ptr(p, C.c_double), _ptr(nr, C.c_double), C.byref(n),
+                                         _ptr(f, C.c_int32), C.byref(nf)))
+        return (p[:n.value].copy(), nr[:n.value].copy() if nr is not None else None,
+                f[:3 * nf.value].reshape(-1, 3).copy())
+
+
+# ============================================================================ Model2Depth
+class Model2Depth:
+    """[ref: Model2Depth/Model2Depth.h:17-54] SetInput(points, normals, facets, cameras, path) then
+    Run(): renders mesh[seq] into every camera of sequence seq and writes
+    <path[seq]>DATA/Render/_depth<frame>.raw (float32 inverse depth).  Run() returns the images."""
+
+    znear = 0.01   # Model2Depth.cpp:19
+    zfar = 2000.0  # Model2Depth.cpp:20
+
+    def __init__(self, ctx: Context | None = None):
+        self._ctx = ctx
+        self.points, self.facets, self.cameras, self.path = [], [], [], []
+
+    def SetInput(self, points, normals, facets, cameras, path=None):
+        self.points = [_f32(p).reshape(-1, 3) for p in points]   # Model2Depth.h:35-39 float cast
+        self.facets = [_i32(f).reshape(-1) for f in facets]
+        self.cameras = [list(c) for c in cameras]
+        self.path = list(path) if path is not None else [None] * len(self.points)
+
+    def render(self, seq: int):
+        cams = self.cameras[seq]
+        arr = (Camera * len(cams))(*cams)
+        w, h = cams[0].w, cams[0].h
+        out = np.empty((len(cams), h, w), np.float32)
+        p, f = self.points[seq], self.facets[seq]
+        check(lib().mvs_model2depth(_ctxh(self._ctx), _ptr(p, C.c_float), C.c_int64(len(p)),
+                                    _ptr(f, C.c_int32), C.c_int64(len(f) // 3), arr,
+                                    C.c_int(len(cams)), C.c_float(self.znear), C.c_float(self.zfar),
+                                    _ptr(out, C.c_float)))
+        return out
+
+    def Run(self):
+        import os
+        images = []
+        for seq in range(len(self.points)):
+            out = self.render(seq)
+            images.append(out)
+            if self.path[seq] is not None:
+                d = os.path.join(self.path[seq], "DATA", "Render")
+                os.makedirs(d, exist_ok=True)
+                for frm in range(out.shape[0]):
+                    save_depth_raw(os.path.join(d, f"_depth{frm}.raw"), out[frm])
+        return images
+
+
+def model2depth_dev(pts_ptr: int, n: int, facets_ptr: int, nf: int, cams, out_ptr: int,
+                    znear=0.0, zfar=0.0, ctx: Context | None = None):
+    arr = (Camera * len(cams))(*cams)
+    check(lib().mvs_model2depth_dev(_ctxh(ctx), _dev(pts_ptr), C.c_int64(n), _dev(facets_ptr),
+                                    C.c_int64(nf), arr, C.c_int(len(cams)), C.c_float(znear),
+                                    C.c_float(zfar), _dev(out_ptr)))
+
+
+def save_depth_raw(filename: str, inv_depth):
+    """[ref: Common/Utils.h:177-185 SaveDepth]"""
+    a = _f32(inv_depth)
+    h, w = a.shape
+    check(lib().mvs_save_depth_raw(filename.encode(), _ptr(a, C.c_float), C.c_int(w), C.c_int(h)))
+
+
+def load_depth_raw(filename: str, w: int, h: int):
+    """[ref: Common/Utils.h:166-176 LoadDepth]"""
+    a = np.empty((h, w), np.float32)
+    check(lib().mvs_load_depth_raw(filename.encode(), _ptr(a, C.c_float), C.c_int(w), C.c_int(h)))
+    return a
+
+
+def unproject_depth(inv_depth, cam: Camera, min_dsp: float, max_dsp: float,
+                    ctx: Context | None = None):
+    """[ref: Image3D/Image3D.cpp:92-106 SolveUnProjectionD] -> (points h*w x 3, valid h*w)"""
+    a = _f32(inv_depth).reshape(cam.h, cam.w)
+    out = np.empty((cam.h * cam.w, 3), np.float64)
+    valid = np.empty(cam.h * cam.w, np.int32)
+    check(lib().mvs_unproject_depth(_ctxh(ctx), _ptr(a, C.c_float), C.byref(cam),
+                                    C.c_double(min_dsp), C.c_double(max_dsp),
+                                    _ptr(out, C.c_double), _ptr(valid, C.c_int32)))
+    return out, valid

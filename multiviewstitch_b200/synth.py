@@ -110,3 +110,80 @@ def bend_twist(verts, amp=0.05):
     out = np.stack([c * v[:, 0] - s * v[:, 1], s * v[:, 0] + c * v[:, 1], v[:, 2]], 1)
     out[:, 0] += amp * diag * z * z  # bend
     return out
+
+
+def grid_disk(radius, n, y, seed=0):
+    """Flat triangulated n x n grid patch in the plane y = const (a 'ground'), clipped to a disk."""
+    xs = np.linspace(-radius, radius, n)
+    X, Z = np.meshgrid(xs, xs, indexing="ij")
+    verts = np.stack([X.ravel(), np.full(X.size, y), Z.ravel()], 1)
+    idx = np.arange(n * n).reshape(n, n)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel()
+    faces = np.concatenate([np.stack([a, b, c], 1), np.stack([b, d, c], 1)], 0)
+    keep = (verts[:, 0] ** 2 + verts[:, 2] ** 2) <= radius * radius
+    remap = -np.ones(len(verts), np.int64)
+    remap[keep] = np.arange(keep.sum())
+    fk = keep[faces].all(1)
+    return verts[keep], remap[faces[fk]].astype(np.int32)
+
+
+def body_on_ground(seed=0):
+    """Tall ellipsoid 'body' (y down, feet at +y) standing on a flat ground patch: the input shape
+    of Alignment::RemoveGround.  Returns (verts, normals, faces, n_body)."""
+    bv, bf = uv_sphere(48, 64, bumps=0.03, seed=seed)
+    bv = bv[:, [0, 2, 1]] * np.array([0.35, 1.0, 0.22])   # long axis -> y
+    bf = bf[:, [0, 2, 1]]
+    gv, gf = grid_disk(0.7, 60, y=bv[:, 1].max() - 0.005)
+    verts = np.concatenate([bv, gv], 0)
+    faces = np.concatenate([bf, gf + len(bv)], 0).astype(np.int32)
+    return verts, vertex_normals(verts, faces), faces, len(bv)
+
+
+# PART enum of PartRecognition/PartRecognition.h:13-30
+PARTS = dict(HEAD=0, NECK=1, LEFT_UPPER_ARM=2, LEFT_LOWER_ARM=3, LEFT_HAND=4, RIGHT_UPPER_ARM=5,
+             RIGHT_LOWER_ARM=6, RIGHT_HAND=7, LEFT_THIGH=8, LEFT_SHANK=9, LEFT_FOOT=10,
+             RIGHT_THIGH=11, RIGHT_SHANK=12, RIGHT_FOOT=13, TRUNCUS=14, HIP=15)
+
+
+def humanoid(n_per_part=400, seed=0, arm_angle=0.5, leg_angle=0.12, scale=1.0):
+    """Labelled point-cloud 'mean body' (y down, facing +z): 16 ellipsoidal parts with the labels of
+    Template/part/parts.  arm_angle / leg_angle: how far the limbs are spread from the body axis."""
+    rng = np.random.default_rng(seed)
+
+    def blob(center, radii, label, axis=None):
+        v = rng.normal(size=(n_per_part, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        v = v * np.asarray(radii)
+        if axis is not None:  # rotate the local +y axis onto `axis`
+            a = np.asarray(axis, np.float64)
+            a = a / np.linalg.norm(a)
+            yv = np.array([0, 1.0, 0])
+            c = np.cross(yv, a)
+            if np.linalg.norm(c) > 1e-12:
+                v = v @ axis_angle(c, np.arccos(np.clip(yv @ a, -1, 1))).T
+        return v + np.asarray(center), np.full(n_per_part, label, np.int32)
+
+    P, L = [], []
+
+    def add(*a, **k):
+        p, l = blob(*a, **k)
+        P.append(p); L.append(l)
+
+    add([0, -0.78, 0], [0.10, 0.12, 0.10], 0)
+    add([0, -0.62, 0], [0.05, 0.05, 0.05], 1)
+    add([0, -0.35, 0], [0.20, 0.25, 0.11], 14)
+    add([0, -0.05, 0], [0.19, 0.10, 0.11], 15)
+    for side, (ua, la, ha) in ((+1, (2, 3, 4)), (-1, (5, 6, 7))):
+        d = np.array([side * np.sin(arm_angle), np.cos(arm_angle), 0.0])
+        sh = np.array([side * 0.24, -0.52, 0.0])
+        add(sh + 0.14 * d, [0.05, 0.15, 0.05], ua, axis=d)
+        add(sh + 0.42 * d, [0.04, 0.14, 0.04], la, axis=d)
+        add(sh + 0.62 * d, [0.04, 0.06, 0.03], ha, axis=d)
+    for side, (th, shk, ft) in ((+1, (8, 9, 10)), (-1, (11, 12, 13))):
+        d = np.array([side * np.sin(leg_angle), np.cos(leg_angle), 0.0])
+        hp = np.array([side * 0.10, 0.05, 0.0])
+        add(hp + 0.22 * d, [0.08, 0.22, 0.08], th, axis=d)
+        add(hp + 0.64 * d, [0.06, 0.21, 0.06], shk, axis=d)
+        add(hp + 0.90 * d + np.array([0, 0, 0.05]), [0.05, 0.04, 0.10], ft)
+    pts = np.concatenate(P, 0) * scale
+    return pts, np.concatenate(L, 0)

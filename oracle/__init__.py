@@ -289,3 +289,114 @@ def vertex_normals(pts, facets):
     lib().orc_vertex_normals(_p(pts, C.c_double), C.c_int64(len(pts)), _p(facets, C.c_int32),
                              C.c_int64(len(facets)), _p(out, C.c_double))
     return out
+
+
+# ----------------------------------------------------------------------------- point sets / alignment
+def apply_srt(pts, normals, scale, R, t, inverse=False):
+    p = _f64(pts).reshape(-1, 3).copy()
+    nr = _f64(normals).reshape(-1, 3).copy() if normals is not None else None
+    R, t = _f64(R).reshape(9), _f64(t).reshape(3)
+    fn = lib().orc_apply_srt_inverse if inverse else lib().orc_apply_srt
+    fn(_p(p, C.c_double), _p(nr, C.c_double), C.c_int64(len(p)), C.c_double(scale),
+       _p(R, C.c_double), _p(t, C.c_double))
+    return p, nr
+
+
+def pointset_stats(pts):
+    p = _f64(pts).reshape(-1, 3)
+    b, mn, mx, pv, ev = np.empty(3), np.empty(3), np.empty(3), np.empty(9), np.empty(3)
+    lib().orc_pointset_stats(_p(p, C.c_double), C.c_int64(len(p)), _p(b, C.c_double),
+                             _p(mn, C.c_double), _p(mx, C.c_double), _p(pv, C.c_double),
+                             _p(ev, C.c_double))
+    return b, mn, mx, pv.reshape(3, 3), ev
+
+
+def project_range(pts, origin, axis, labels=None, label=0):
+    p = _f64(pts).reshape(-1, 3)
+    lb = _i32(labels) if labels is not None else None
+    o, a = _f64(origin).reshape(3), _f64(axis).reshape(3)
+    tmin, tmax = C.c_double(), C.c_double()
+    imin, imax = C.c_int64(), C.c_int64()
+    lib().orc_project_range(_p(p, C.c_double), C.c_int64(len(p)), _p(lb, C.c_int32),
+                            C.c_int32(label), _p(o, C.c_double), _p(a, C.c_double),
+                            C.byref(tmin), C.byref(tmax), C.byref(imin), C.byref(imax))
+    return tmin.value, tmax.value, imin.value, imax.value
+
+
+def retain_connected(pts, normals, facets):
+    p = _f64(pts).reshape(-1, 3).copy()
+    nr = _f64(normals).reshape(-1, 3).copy() if normals is not None else None
+    f = _i32(facets).reshape(-1).copy()
+    n, nf = C.c_int64(len(p)), C.c_int64(len(f) // 3)
+    lib().orc_retain_connected(_p(p, C.c_double), _p(nr, C.c_double), C.byref(n),
+                               _p(f, C.c_int32), C.byref(nf))
+    return (p[:n.value].copy(), nr[:n.value].copy() if nr is not None else None,
+            f[:3 * nf.value].reshape(-1, 3).copy())
+
+
+def remove_ground(pts, normals, facets, dist_thres=0.8, ground_ratio=0.28):
+    p = _f64(pts).reshape(-1, 3).copy()
+    nr = _f64(normals).reshape(-1, 3).copy() if normals is not None else None
+    f = _i32(facets).reshape(-1).copy()
+    n, nf = C.c_int64(len(p)), C.c_int64(len(f) // 3)
+    gr = np.zeros(3)
+    lib().orc_remove_ground(_p(p, C.c_double), _p(nr, C.c_double), C.byref(n), _p(f, C.c_int32),
+                            C.byref(nf), C.c_double(dist_thres), C.c_double(ground_ratio),
+                            _p(gr, C.c_double))
+    return (p[:n.value].copy(), nr[:n.value].copy() if nr is not None else None,
+            f[:3 * nf.value].reshape(-1, 3).copy(), gr)
+
+
+def init_alignment(src, tgt, ground_ray, view_ray):
+    s, t = _f64(src).reshape(-1, 3), _f64(tgt).reshape(-1, 3)
+    gr, vr = _f64(ground_ray).reshape(3), _f64(view_ray).reshape(3)
+    T = np.empty(16)
+    sc = C.c_double()
+    lib().orc_init_alignment(_p(s, C.c_double), C.c_int64(len(s)), _p(t, C.c_double),
+                             C.c_int64(len(t)), _p(gr, C.c_double), _p(vr, C.c_double),
+                             _p(T, C.c_double), C.byref(sc))
+    return T.reshape(4, 4), sc.value
+
+
+def align(src, s_normals, s_labels, tgt, t_normals, t_facets, view_ray, dist_thres=0.8,
+          ground_ratio=0.28, remove_ground=1, local_align=1, neck_label=1, ground_ray=None):
+    s = _f64(src).reshape(-1, 3).copy()
+    sn = _f64(s_normals).reshape(-1, 3).copy() if s_normals is not None else None
+    sl = _i32(s_labels)
+    t = _f64(tgt).reshape(-1, 3).copy()
+    tn = _f64(t_normals).reshape(-1, 3).copy() if t_normals is not None else None
+    tf = _i32(t_facets).reshape(-1).copy()
+    nt, ntf = C.c_int64(len(t)), C.c_int64(len(tf) // 3)
+    vr = _f64(view_ray).reshape(3)
+    gr = _f64(ground_ray).reshape(3).copy() if ground_ray is not None else np.zeros(3)
+    tl = np.empty(len(t), np.int32)
+    lib().orc_align(_p(s, C.c_double), _p(sn, C.c_double), C.c_int64(len(s)), _p(sl, C.c_int32),
+                    _p(t, C.c_double), _p(tn, C.c_double), C.byref(nt), _p(tf, C.c_int32),
+                    C.byref(ntf), _p(vr, C.c_double), C.c_double(dist_thres),
+                    C.c_double(ground_ratio), C.c_int(remove_ground), C.c_int(local_align),
+                    C.c_int(neck_label), _p(tl, C.c_int32), _p(gr, C.c_double))
+    n, f = nt.value, ntf.value
+    return (s, sn, t[:n].copy(), tn[:n].copy() if tn is not None else None,
+            tf[:3 * f].reshape(-1, 3).copy(), tl[:n].copy(), gr)
+
+
+# ----------------------------------------------------------------------------- Model2Depth
+def model2depth(pts, facets, cams, znear=0.0, zfar=0.0):
+    p = _f32(pts).reshape(-1, 3)
+    f = _i32(facets).reshape(-1)
+    arr = (Camera * len(cams))(*cams)
+    w, h = cams[0].w, cams[0].h
+    out = np.empty((len(cams), h, w), np.float32)
+    lib().orc_model2depth(_p(p, C.c_float), C.c_int64(len(p)), _p(f, C.c_int32),
+                          C.c_int64(len(f) // 3), arr, C.c_int(len(cams)), C.c_float(znear),
+                          C.c_float(zfar), _p(out, C.c_float))
+    return out
+
+
+def unproject_depth(inv_depth, cam, min_dsp, max_dsp):
+    a = _f32(inv_depth).reshape(cam.h, cam.w)
+    out = np.empty((cam.h * cam.w, 3), np.float64)
+    valid = np.empty(cam.h * cam.w, np.int32)
+    lib().orc_unproject_depth(_p(a, C.c_float), C.byref(cam), C.c_double(min_dsp),
+                              C.c_double(max_dsp), _p(out, C.c_double), _p(valid, C.c_int32))
+    return out, valid
