@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="objects", choices=["objects", "shard"])
-    ap.add_argument("--nu", type=int, default=1000, help="UV-sphere longitudes (verts = nu*nu+2)")
+    ap.add_argument("--side", type=int, default=408, help="cube-sphere grid side (verts = 6*side^2+2)")
     ap.add_argument("--nodes", type=int, default=4096)
     ap.add_argument("--gn-iters", type=int, default=10)
     ap.add_argument("--pcg-iters", type=int, default=20)
@@ -59,15 +59,21 @@ def parse():
 
 
 def workload(args, seed_shift=0):
+    """Template = cube-sphere mesh with low-frequency bumps (near-uniform vertex density, closed,
+    genus 0); target "scan" = the same shape sampled with its own, turned and finer tessellation
+    (a scan never shares the template's lattice) and warped by a smooth bend + twist of 5 % of the
+    bounding-box diagonal."""
     from multiviewstitch_b200 import synth
-    verts, faces = synth.uv_sphere(args.nu, args.nu + 1, seed=seed_shift)
+    verts, faces = synth.cube_sphere(args.side)
+    tv, _ = synth.cube_sphere(int(round(args.side * 1.027)), rot=synth.axis_angle([1, 2, 3], 0.7))
     if seed_shift:
         # independent objects per rank: a different similarity of the same shape
         R = synth.axis_angle([1, 2 + seed_shift, 3], 0.1 * seed_shift)
         verts = (1.0 + 0.01 * seed_shift) * verts @ R.T
+        tv = (1.0 + 0.01 * seed_shift) * tv @ R.T
     pts = verts.astype(np.float32)
     nrm = synth.vertex_normals(verts, faces).astype(np.float32)
-    tgt = synth.bend_twist(verts, 0.05).astype(np.float32)
+    tgt = synth.bend_twist(tv, 0.05).astype(np.float32)
     return pts, nrm, faces, tgt
 
 
@@ -192,7 +198,7 @@ ALGO_BYTES_DOC = {
     # per GN iteration, n vertices, nt target points, m nodes, nnz pattern blocks
     "gn_deform_corr": "n*(16 v + 16 idx + 16 w + 16 resid) + nt*16 target cells",
     "gn_assemble_fit": "n*(16 v + 16 idx + 16 w + 16 resid) + (nnz*64 + m*48) system write",
-    "pcg_iterations": "iters*((nnz*64 + m*324) matrix + m*576 Minv + 10*m*48 vectors)",
+    "pcg_solve": "iters*((nnz*64 + m*324) matrix + m*576 Minv + 10*m*48 vectors)",
 }
 
 
@@ -201,7 +207,7 @@ def algo_bytes(name, n, nt, m, nnz, pcg_iters):
         return n * 64 + nt * 16
     if name == "gn_assemble_fit":
         return n * 64 + nnz * 64 + m * 48
-    if name == "pcg_iterations":
+    if name == "pcg_solve":
         return pcg_iters * (nnz * 64 + m * 324 + m * 576 + 10 * m * 48)
     if name == "deform_final":
         return n * (48 + 16) + 0
@@ -307,6 +313,8 @@ def run_b200(args):
             ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                    for _ in range(args.steps)]
             barrier()
+            ctx.prof_enable(True)
+            ctx.prof_reset()
             for s in range(args.steps):
                 flush.fill_(s & 0xFF)
                 ev2[s][0].record(stream)
@@ -314,6 +322,8 @@ def run_b200(args):
                 ev2[s][1].record(stream)
             barrier()
             e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+            prof_e2e = ctx.prof()
+            ctx.prof_enable(False)
             # float32 atomics make the block sums order-dependent: equal within the parity bar
             dg = float(np.linalg.norm(pts.max(0) - pts.min(0)))
             e2e_diff = float(np.abs(out_h - out_dev).max() / dg)
@@ -350,7 +360,7 @@ def run_b200(args):
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "algorithmic_bytes_per_launch_group": ab, "avg_ms": avg_ms,
-                    "launches_per_group": (2 * args.pcg_iters if top == "pcg_iterations" else 1),
+                    "launches_per_group": 1,
                     "bytes_formula": ALGO_BYTES_DOC.get(top)}
         families = {}
         for k, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
@@ -389,7 +399,10 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(nt * 12), "d2h_bytes_per_step": int(n * 12),
                     "max_abs_diff_vs_resident_over_bbox_diag": e2e_diff},
                 "gpu_launches": int(launches), "clocks": clk,
-                "wall_s_timed_region": t_wall, "families": families}
+                "wall_s_timed_region": t_wall, "families": families,
+                "e2e_families_ms_per_step": None if e2e_ms is None else {
+                    k: round(v[0] / args.steps, 4) for k, v in
+                    sorted(prof_e2e.items(), key=lambda kv: -kv[1][0])}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -70,6 +70,9 @@ struct mvs_ctx {
   void* comm = nullptr;
   int nranks = 1;
   int rank = 0;
+  // lifetime: handles created on a context (NN index, SRT solver, deformation) keep it alive, so
+  // destroying the context first (e.g. garbage collection order in a binding) is safe
+  int refs = 1;
 };
 
 namespace mvs {
@@ -77,6 +80,8 @@ namespace mvs {
 int ctx_resolve_prof(mvs_ctx* ctx);
 int ctx_ensure_device(mvs_ctx* ctx);
 mvs_ctx* default_ctx();
+void ctx_retain(mvs_ctx* ctx);
+void ctx_release(mvs_ctx* ctx);
 
 // RAII scope that (optionally) records CUDA events around a kernel family and counts launches.
 struct ProfScope {

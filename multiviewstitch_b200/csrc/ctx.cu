@@ -115,6 +115,35 @@ int d2h_sync(mvs_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 }  // namespace mvs
 
+namespace mvs {
+static std::mutex g_ref_mu;
+void ctx_retain(mvs_ctx* ctx) {
+  std::lock_guard<std::mutex> lk(g_ref_mu);
+  ++ctx->refs;
+}
+static void ctx_free(mvs_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  mvs_comm_destroy(ctx);
+  for (auto& p : ctx->pending) {
+    cudaEventDestroy(p.start);
+    cudaEventDestroy(p.stop);
+  }
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void ctx_release(mvs_ctx* ctx) {
+  {
+    std::lock_guard<std::mutex> lk(g_ref_mu);
+    if (--ctx->refs > 0) return;
+  }
+  ctx_free(ctx);
+}
+}  // namespace mvs
+
 extern "C" {
 
 const char* mvs_last_error(void) { return mvs::g_err; }
@@ -173,17 +202,7 @@ int mvs_ctx_create(mvs_ctx** out, int device, void* stream) {
 
 int mvs_ctx_destroy(mvs_ctx* ctx) {
   if (!ctx) return MVS_OK;
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  mvs_comm_destroy(ctx);
-  for (auto& p : ctx->pending) {
-    cudaEventDestroy(p.start);
-    cudaEventDestroy(p.stop);
-  }
-  for (auto e : ctx->event_pool) cudaEventDestroy(e);
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  mvs::ctx_release(ctx);
   return MVS_OK;
 }
 

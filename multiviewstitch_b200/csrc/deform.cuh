@@ -46,6 +46,10 @@ struct mvs_deform {
   // pattern + system
   mvs::DevBuf<int> row_ptr, col;
   int64_t nnz = 0;
+  std::vector<int> h_row_ptr;  // host copy of row_ptr (solver launch planning)
+  bool pcg_plan_valid = false;
+  int pcg_rs = 1, pcg_grid = 0, pcg_stage = 0;
+  size_t pcg_smem = 0;
   mvs::DevBuf<float> sys;
   mvs::DevBuf<float> Minv;  // m x 144
   mvs::DevBuf<float> x;     // m x 12
@@ -61,6 +65,8 @@ struct mvs_deform {
   int64_t nt = 0;
   // per-vertex work arrays (sorted order)
   mvs::DevBuf<float4> resid;    // (v~ - c, omega)
+  mvs::DevBuf<int> corr_prev;   // last correspondence of each vertex (seed of the next search)
+  bool corr_seeded = false;     // corr_prev holds valid seeds for the current target
   mvs::DevBuf<float4> targets;  // (c, omega) for fixed-target modes
   bool have_targets = false;
   mvs::DevBuf<float4> cur0;     // deformed vertices, ORIGINAL order

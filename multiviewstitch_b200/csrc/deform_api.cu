@@ -6,6 +6,7 @@
 #include <cmath>
 
 #include "deform.cuh"
+#include "nn_pyramid.cuh"
 
 namespace mvs {
 
@@ -54,9 +55,7 @@ __global__ void k_targets_from_nodes(const double* __restrict__ controls,
 
 // Deformation/Deformation.cpp:186-203: 1-NN target of each node; keep if d2 <= threshold and
 // cos(dir, normal) >= 0.5 (the 6-D tree has scale = 0, i.e. it is a plain position search).
-__global__ void k_node_targets_threshold(GridParams tg, const float4* __restrict__ tsorted,
-                                         const int* __restrict__ cell_start,
-                                         const float4* __restrict__ g,
+__global__ void k_node_targets_threshold(PyrParams tg, const float4* __restrict__ g,
                                          const float4* __restrict__ gnrm, int64_t m,
                                          float threshold, double* __restrict__ controls,
                                          int* __restrict__ valid) {
@@ -83,7 +82,7 @@ __global__ void k_node_targets_threshold(GridParams tg, const float4* __restrict
       }
     }
   } vis{&nn, 0.f, 0.f, 0.f};
-  grid_search(tg, cell_start, tsorted, q.x, q.y, q.z, vis);
+  pyr_search(tg, q.x, q.y, q.z, vis);
   if (nn.d2[0] > threshold) return;
   double d0 = __dsub_rn((double)vis.cx, (double)q.x), d1 = __dsub_rn((double)vis.cy, (double)q.y),
          d2 = __dsub_rn((double)vis.cz, (double)q.z);
@@ -126,6 +125,9 @@ static int gn_begin_impl(mvs_deform* h, const mvs_gn_params* p) {
   MVS_TRY(ensure_graph(h));
   h->prm = *p;
   MVS_TRY(gn_reset_state(h));
+  // a solve never inherits correspondence seeds from an earlier one
+  MVS_CUDA(cudaMemsetAsync(h->corr_prev.p, 0xff, sizeof(int) * h->n, h->ctx->stream));
+  h->corr_seeded = false;
   h->gn_active = true;
   h->cur_valid = false;
   return MVS_OK;
@@ -134,8 +136,7 @@ static int gn_begin_impl(mvs_deform* h, const mvs_gn_params* p) {
 static int gn_step_impl(mvs_deform* h) {
   MVS_TRY(gn_deform_and_correspond(h));
   MVS_TRY(gn_assemble(h));
-  MVS_TRY(pcg_solve(h));
-  MVS_TRY(gn_apply_update(h));
+  MVS_TRY(pcg_solve(h));  // also applies x += delta
   return MVS_OK;
 }
 
@@ -216,6 +217,7 @@ static int create_common(mvs_ctx* ctx, int64_t n, const int32_t* facets, int64_t
   MVS_TRY(ctx_ensure_device(ctx));
   mvs_deform* h = new mvs_deform();
   h->ctx = ctx;
+  ctx_retain(ctx);
   h->n = n;
   h->nf = nf;
   mvs_gn_default_params(&h->prm);
@@ -235,7 +237,7 @@ static int finish_create(mvs_deform* h, const int32_t* facets, mvs_deform** out)
     }
   }
   if (st != MVS_OK) {
-    delete h;
+    mvs_deform_destroy(h);
     return st;
   }
   *out = h;
@@ -257,7 +259,7 @@ int mvs_deform_create(mvs_ctx* ctx, const double* pts, const double* normals, in
     }
   }
   if (st != MVS_OK) {
-    delete h;
+    mvs_deform_destroy(h);
     return st;
   }
   return finish_create(h, facets, out);
@@ -278,7 +280,7 @@ int mvs_deform_create_f32(mvs_ctx* ctx, const float* pts, const float* normals, 
     }
   }
   if (st != MVS_OK) {
-    delete h;
+    mvs_deform_destroy(h);
     return st;
   }
   return finish_create(h, facets, out);
@@ -290,7 +292,18 @@ int mvs_deform_destroy(mvs_deform* h) {
   cudaStreamSynchronize(h->ctx->stream);
   if (h->node_index) mvs_nn_index_destroy(h->node_index);
   if (h->tgt_index) mvs_nn_index_destroy(h->tgt_index);
+  mvs_ctx* ctx = h->ctx;
   delete h;
+  ctx_release(ctx);
+  return MVS_OK;
+}
+
+static int set_target_index(mvs_deform* h, int64_t nt) {
+  MVS_TRY(nn_build_pyramid(h->tgt_index, h->tp, nt));
+  // correspondences of a previous target are no seeds for this one
+  if (h->corr_prev.p && h->n > 0)
+    MVS_CUDA(cudaMemsetAsync(h->corr_prev.p, 0xff, sizeof(int) * h->n, h->ctx->stream));
+  h->corr_seeded = false;
   return MVS_OK;
 }
 
@@ -315,7 +328,7 @@ int mvs_deform_set_target(mvs_deform* h, const double* tpts, const double* tnorm
     MVS_TRY(upload_xyz_f64(h->ctx, tnormals, nt, h->tn_own));
     h->tn = h->tn_own.p;
   }
-  return nn_build(h->tgt_index, h->tp, nt);
+  return set_target_index(h, nt);
 }
 
 int mvs_deform_set_target_f32(mvs_deform* h, const float* tpts, const float* tnormals,
@@ -329,7 +342,7 @@ int mvs_deform_set_target_f32(mvs_deform* h, const float* tpts, const float* tno
     MVS_TRY(upload_xyz_f32(h->ctx, tnormals, nt, h->tn_own));
     h->tn = h->tn_own.p;
   }
-  return nn_build(h->tgt_index, h->tp, nt);
+  return set_target_index(h, nt);
 }
 
 int mvs_deform_set_target_dev_f32(mvs_deform* h, const float* tpts_dev, const float* tnormals_dev,
@@ -338,7 +351,7 @@ int mvs_deform_set_target_dev_f32(mvs_deform* h, const float* tpts_dev, const fl
   MVS_TRY(target_common(h, nt));
   h->tp = reinterpret_cast<const float4*>(tpts_dev);
   h->tn = reinterpret_cast<const float4*>(tnormals_dev);
-  return nn_build(h->tgt_index, h->tp, nt);
+  return set_target_index(h, nt);
 }
 
 int mvs_deform_set_targets(mvs_deform* h, const double* targets, const float* weights, int64_t n) {
@@ -458,7 +471,7 @@ int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_param
   MVS_TRY(validate_params(params));
   mvs_ctx* ctx = h->ctx;
   MVS_TRY(ctx_ensure_device(ctx));
-  if (!h->tgt_index || !h->tgt_index->built) {
+  if (!h->tgt_index || !h->tgt_index->pyr_built) {
     set_error("run_threshold: target not set");
     return MVS_ERR_STATE;
   }
@@ -475,8 +488,7 @@ int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_param
   {
     ProfScope ps(ctx, "node_targets_threshold");
     k_node_targets_threshold<<<div_up(h->m, 64), 64, 0, ctx->stream>>>(
-        h->tgt_index->g, h->tgt_index->pts_sorted.p, h->tgt_index->cell_start.p, h->g.p,
-        h->gnrm.p, h->m, (float)threshold, c.p, v.p);
+        h->tgt_index->pyr, h->g.p, h->gnrm.p, h->m, (float)threshold, c.p, v.p);
   }
   MVS_TRY(set_node_targets(h, c, v, 1));
   mvs_gn_params p = *params;

@@ -9,6 +9,7 @@
 #include <cmath>
 
 #include "deform.cuh"
+#include "nn_pyramid.cuh"
 
 namespace mvs {
 
@@ -379,6 +380,9 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
   int nnz = 0;
   MVS_TRY(d2h_sync(ctx, &nnz, h->row_ptr.p + m, sizeof(int)));
   h->nnz = nnz;
+  h->h_row_ptr.resize((size_t)m + 1);
+  MVS_TRY(d2h_sync(ctx, h->h_row_ptr.data(), h->row_ptr.p, sizeof(int) * (m + 1)));
+  h->pcg_plan_valid = false;
   MVS_TRY(h->col.reserve((size_t)nnz));
   {
     ProfScope ps(ctx, "pattern_gather");
@@ -396,6 +400,9 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
   MVS_CUDA(cudaMemsetAsync(h->ticket.p, 0, sizeof(unsigned), st));
   MVS_CUDA(cudaMemsetAsync(h->scal.p, 0, sizeof(double) * S_SIZE, st));
   MVS_TRY(h->resid.reserve((size_t)n));
+  MVS_TRY(h->corr_prev.reserve((size_t)n));
+  MVS_CUDA(cudaMemsetAsync(h->corr_prev.p, 0xff, sizeof(int) * n, st));
+  h->corr_seeded = false;
   MVS_TRY(h->targets.reserve((size_t)n));
   MVS_TRY(h->cur0.reserve((size_t)n));
   MVS_TRY(h->curn0.reserve((size_t)n));
@@ -483,8 +490,7 @@ struct RadiusTop8 {
 };
 
 __global__ void __launch_bounds__(64)
-    k_node_targets(GridParams tg, const float4* __restrict__ tpts_sorted,
-                   const int* __restrict__ cell_start, const float4* __restrict__ tpts,
+    k_node_targets(PyrParams tg, const float4* __restrict__ tpts,
                    const float4* __restrict__ tnrm, const float4* __restrict__ g,
                    const float4* __restrict__ gnrm, int64_t m, double proj_len_err,
                    double proj_dist_err, double* __restrict__ controls, int* __restrict__ valid) {
@@ -498,10 +504,10 @@ __global__ void __launch_bounds__(64)
   valid[i] = 0;
   KnnList<1> nn;
   nn.init(q.x, q.y, q.z);
-  grid_search(tg, cell_start, tpts_sorted, q.x, q.y, q.z, nn);
+  pyr_search(tg, q.x, q.y, q.z, nn);
   float radius = __fmul_rn(nn.d2[0], 2.0f);  // Deformation.cpp:288, squared units
   RadiusCount rc{q.x, q.y, q.z, radius, 0};
-  grid_search(tg, cell_start, tpts_sorted, q.x, q.y, q.z, rc);
+  pyr_search(tg, q.x, q.y, q.z, rc);
   if (rc.count >= 10000) return;  // Deformation.cpp:286-297,315: all maxResult slots fill -> skipped
   RadiusTop8 rt;
   rt.qx = q.x; rt.qy = q.y; rt.qz = q.z; rt.r2 = radius;
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(64)
                                  __dmul_rn(rt.nrm[2], rt.nrm[2])));
   rt.tn = tnrm;
   rt.top.init();
-  grid_search(tg, cell_start, tpts_sorted, q.x, q.y, q.z, rt);
+  pyr_search(tg, q.x, q.y, q.z, rt);
   int nb = min(8, rt.top.cnt);
   if (nb == 0) return;
   double mlen = 0.0, mdist = 0.0, mp[3] = {0.0, 0.0, 0.0};
@@ -570,7 +576,7 @@ __global__ void k_smooth_controls(const float4* __restrict__ g, const int* __res
 int deform_node_targets(mvs_deform* h, double proj_len_err, double proj_dist_err,
                         int smooth_sweeps, DevBuf<double>& controls, DevBuf<int>& valid) {
   mvs_ctx* ctx = h->ctx;
-  if (!h->tgt_index || !h->tgt_index->built || !h->tn) {
+  if (!h->tgt_index || !h->tgt_index->pyr_built || !h->tn) {
     set_error("node_targets: target points and normals not set (mvs_deform_set_target)");
     return MVS_ERR_STATE;
   }
@@ -581,8 +587,8 @@ int deform_node_targets(mvs_deform* h, double proj_len_err, double proj_dist_err
   {
     ProfScope ps(ctx, "node_targets");
     k_node_targets<<<div_up(m, 64), 64, 0, ctx->stream>>>(
-        h->tgt_index->g, h->tgt_index->pts_sorted.p, h->tgt_index->cell_start.p, h->tp, h->tn,
-        h->g.p, h->gnrm.p, m, proj_len_err, proj_dist_err, controls.p, valid.p);
+        h->tgt_index->pyr, h->tp, h->tn, h->g.p, h->gnrm.p, m, proj_len_err, proj_dist_err,
+        controls.p, valid.p);
   }
   double* a = controls.p;
   double* b = controls.p + 3 * m;

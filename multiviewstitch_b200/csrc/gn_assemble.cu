@@ -17,6 +17,7 @@
 
 #include "comm.cuh"
 #include "deform.cuh"
+#include "nn_pyramid.cuh"
 #include "reduce.cuh"
 
 namespace mvs {
@@ -90,9 +91,9 @@ struct Best1 {
   }
 };
 
-__global__ void __launch_bounds__(128)
-    k_deform_corr(GridParams tg, const float4* __restrict__ tsorted,
-                  const int* __restrict__ cell_start, const float4* __restrict__ tnrm,
+__global__ void __launch_bounds__(128, 8)
+    k_deform_corr(PyrParams tg, const float4* __restrict__ tpts, int* __restrict__ corr_prev,
+                  const float4* __restrict__ tnrm,
                   const float4* __restrict__ v, const float4* __restrict__ nrm,
                   const int4* __restrict__ vidx, const float4* __restrict__ vw,
                   const float4* __restrict__ g, const float* __restrict__ x, int64_t begin,
@@ -106,7 +107,16 @@ __global__ void __launch_bounds__(128)
   b.d2 = INFINITY;
   b.idx = 0x7fffffff;
   b.cx = b.cy = b.cz = 0.f;
-  grid_search(tg, cell_start, tsorted, q.x, q.y, q.z, b);
+  // seed with the previous iteration's correspondence: the bound starts tight, so the walk only
+  // touches the few cells around the query
+  int prev = corr_prev[i];
+  if (prev >= 0) {
+    float4 c = __ldg(tpts + prev);
+    c.w = __int_as_float(prev);
+    b.point(c);
+  }
+  pyr_search(tg, q.x, q.y, q.z, b);
+  corr_prev[i] = b.idx;
   float om = 1.0f;
   if (max_d2 > 0.f && b.d2 > max_d2) om = 0.0f;
   if (min_cos > -1.0f && tnrm) {
@@ -141,15 +151,15 @@ int gn_deform_and_correspond(mvs_deform* h) {
   int64_t b = h->shard_begin(), e = h->shard_end();
   if (e <= b) return MVS_OK;
   if (h->prm.corr_mode == 1) {
-    if (!h->tgt_index || !h->tgt_index->built) {
+    if (!h->tgt_index || !h->tgt_index->pyr_built) {
       set_error("corr_mode 1 needs a target (mvs_deform_set_target*)");
       return MVS_ERR_STATE;
     }
     ProfScope ps(ctx, "gn_deform_corr");
     k_deform_corr<<<div_up(e - b, 128), 128, 0, ctx->stream>>>(
-        h->tgt_index->g, h->tgt_index->pts_sorted.p, h->tgt_index->cell_start.p, h->tn, h->v.p,
-        h->nrm.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, b, e, (float)h->prm.max_corr_dist2,
-        (float)h->prm.min_corr_cos, h->resid.p);
+        h->tgt_index->pyr, h->tp, h->corr_prev.p, h->tn, h->v.p, h->nrm.p, h->vidx.p, h->vw.p,
+        h->g.p, h->x.p, b, e, (float)h->prm.max_corr_dist2, (float)h->prm.min_corr_cos,
+        h->resid.p);
   } else {
     if (!h->have_targets) {
       set_error("fixed-target mode needs per-vertex targets");
@@ -312,156 +322,192 @@ __global__ void __launch_bounds__(kAsmWarps * 32)
 }
 
 // ------------------------------------------------------------------ node terms
-__global__ void __launch_bounds__(64)
+// 16 lanes per node: lanes 0..8 each build one row of the dense 9x9 rotation block (and its
+// gradient entry); every lane takes the graph edges e = lane, lane+16, ... of the smoothness term.
+// The node's own 4x4 diagonal factor and gradient are reduced over the 16 lanes with shuffles and
+// flushed once; the (j,l), (l,j), (l,l) contributions of an edge go out as atomics.
+constexpr int kNodeLanes = 16;
+
+__global__ void __launch_bounds__(128)
     k_node_terms(const float4* __restrict__ g, const float* __restrict__ x,
                  const int* __restrict__ graph, int gk1, int64_t m,
                  const int* __restrict__ row_ptr, const int* __restrict__ col,
                  float* __restrict__ B, float* __restrict__ Rot, float* __restrict__ rhs,
                  float w_rot, float w_reg) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
-  NodeX n = load_node(x, j);
+  const unsigned full = 0xffffffffu;
+  int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kNodeLanes;
+  int k = threadIdx.x & (kNodeLanes - 1);
+  bool on = j < m;
+  int jj = on ? (int)j : 0;
+  NodeX n = load_node(x, jj);
   const float* a1 = n.a;
   const float* a2 = n.a + 3;
   const float* a3 = n.a + 6;
-  float res[6];
-  float J[6][9];
-#pragma unroll
-  for (int k = 0; k < 6; ++k)
-#pragma unroll
-    for (int p = 0; p < 9; ++p) J[k][p] = 0.f;
-  res[0] = a1[0] * a2[0] + a1[1] * a2[1] + a1[2] * a2[2];
-  res[1] = a1[0] * a3[0] + a1[1] * a3[1] + a1[2] * a3[2];
-  res[2] = a2[0] * a3[0] + a2[1] * a3[1] + a2[2] * a3[2];
-  res[3] = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2] - 1.0f;
-  res[4] = a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2] - 1.0f;
-  res[5] = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2] - 1.0f;
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    J[0][r] = a2[r]; J[0][3 + r] = a1[r];
-    J[1][r] = a3[r]; J[1][6 + r] = a1[r];
-    J[2][3 + r] = a3[r]; J[2][6 + r] = a2[r];
-    J[3][r] = 2.f * a1[r];
-    J[4][3 + r] = 2.f * a2[r];
-    J[5][6 + r] = 2.f * a3[r];
-  }
   float gl[12];
 #pragma unroll
   for (int p = 0; p < 12; ++p) gl[p] = 0.f;
-  float* R = Rot + (size_t)j * 81;
-#pragma unroll
-  for (int p = 0; p < 9; ++p) {
+  if (on && k < 9) {
+    float res[6];
+    res[0] = a1[0] * a2[0] + a1[1] * a2[1] + a1[2] * a2[2];
+    res[1] = a1[0] * a3[0] + a1[1] * a3[1] + a1[2] * a3[2];
+    res[2] = a2[0] * a3[0] + a2[1] * a3[1] + a2[2] * a3[2];
+    res[3] = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2] - 1.0f;
+    res[4] = a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2] - 1.0f;
+    res[5] = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2] - 1.0f;
+    // column p of the 6x9 Jacobian, for p = k and for every q
+    auto Jcol = [&](int p, float out[6]) {
+      int c = p / 3, r = p - 3 * c;  // unknown a_{c+1}[r]
+      out[0] = c == 0 ? a2[r] : (c == 1 ? a1[r] : 0.f);
+      out[1] = c == 0 ? a3[r] : (c == 2 ? a1[r] : 0.f);
+      out[2] = c == 1 ? a3[r] : (c == 2 ? a2[r] : 0.f);
+      out[3] = c == 0 ? 2.f * a1[r] : 0.f;
+      out[4] = c == 1 ? 2.f * a2[r] : 0.f;
+      out[5] = c == 2 ? 2.f * a3[r] : 0.f;
+    };
+    float Jp[6];
+    Jcol(k, Jp);
     float gp = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) gp += J[k][p] * res[k];
-    gl[p] = w_rot * gp;
+    for (int e = 0; e < 6; ++e) gp += Jp[e] * res[e];
+    float* R = Rot + (size_t)j * 81 + 9 * k;
 #pragma unroll
     for (int q = 0; q < 9; ++q) {
-      float s = 0.f;
+      float Jq[6];
+      Jcol(q, Jq);
+      float sacc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s += J[k][p] * J[k][q];
-      R[9 * p + q] = w_rot * s;
+      for (int e = 0; e < 6; ++e) sacc += Jp[e] * Jq[e];
+      R[q] = w_rot * sacc;
     }
+    // gradient entry k goes to lane-local gl[k] (static index via unrolled select)
+#pragma unroll
+    for (int p = 0; p < 9; ++p)
+      if (p == k) gl[p] = w_rot * gp;
   }
-  // smoothness edges j -> l
   float Bjj[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) Bjj[k] = 0.f;
-  float4 gj = __ldg(g + j);
-  for (int e = 0; e < gk1; ++e) {
-    int l = __ldg(graph + (size_t)j * gk1 + e);
-    if (l < 0 || l == j) continue;
-    float4 gv = __ldg(g + l);
-    NodeX nl = load_node(x, l);
-    float ev[3] = {gv.x - gj.x, gv.y - gj.y, gv.z - gj.z};
-    float r[3];
+  for (int q = 0; q < 16; ++q) Bjj[q] = 0.f;
+  if (on) {
+    float4 gj = __ldg(g + j);
+    for (int e = k; e < gk1; e += kNodeLanes) {
+      int l = __ldg(graph + (size_t)j * gk1 + e);
+      if (l < 0 || l == j) continue;
+      float4 gv = __ldg(g + l);
+      NodeX nl = load_node(x, l);
+      float ev[3] = {gv.x - gj.x, gv.y - gj.y, gv.z - gj.z};
+      float r[3];
 #pragma unroll
-    for (int rr = 0; rr < 3; ++rr)
-      r[rr] = (n.a[rr] * ev[0] + n.a[3 + rr] * ev[1] + n.a[6 + rr] * ev[2] - ev[rr]) +
-              (n.a[9 + rr] - nl.a[9 + rr]);
-    float a[4] = {ev[0], ev[1], ev[2], 1.0f};
+      for (int rr = 0; rr < 3; ++rr)
+        r[rr] = (n.a[rr] * ev[0] + n.a[3 + rr] * ev[1] + n.a[6 + rr] * ev[2] - ev[rr]) +
+                (n.a[9 + rr] - nl.a[9 + rr]);
+      float a[4] = {ev[0], ev[1], ev[2], 1.0f};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll
-      for (int d = 0; d < 4; ++d) Bjj[4 * c + d] += w_reg * a[c] * a[d];
+        for (int d = 0; d < 4; ++d) Bjj[4 * c + d] += w_reg * a[c] * a[d];
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) gl[3 * c + rr] += w_reg * a[c] * r[rr];
+        for (int rr = 0; rr < 3; ++rr) gl[3 * c + rr] += w_reg * a[c] * r[rr];
+      }
+      float* Bjl = B + (size_t)find_slot(row_ptr, col, (int)j, l) * 16;
+      float* Blj = B + (size_t)find_slot(row_ptr, col, l, (int)j) * 16;
+      float* Bll = B + (size_t)find_slot(row_ptr, col, l, l) * 16;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) atomicAdd(Bjl + 4 * c + 3, -w_reg * a[c]);
+      red_add_f4(Blj + 12, -w_reg * a[0], -w_reg * a[1], -w_reg * a[2], -w_reg * a[3]);
+      atomicAdd(Bll + 15, w_reg);
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) atomicAdd(rhs + (size_t)l * 12 + 9 + rr, -w_reg * r[rr]);
     }
-    float* Bjl = B + (size_t)find_slot(row_ptr, col, j, l) * 16;
-    float* Blj = B + (size_t)find_slot(row_ptr, col, l, j) * 16;
-    float* Bll = B + (size_t)find_slot(row_ptr, col, l, l) * 16;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      atomicAdd(Bjl + 4 * c + 3, -w_reg * a[c]);
-      atomicAdd(Blj + 12 + c, -w_reg * a[c]);
-    }
-    atomicAdd(Bll + 15, w_reg);
-#pragma unroll
-    for (int rr = 0; rr < 3; ++rr) atomicAdd(rhs + (size_t)l * 12 + 9 + rr, -w_reg * r[rr]);
   }
-  float* Bd = B + (size_t)find_slot(row_ptr, col, j, j) * 16;
+  // reduce the node's own contributions over its 16 lanes
 #pragma unroll
-  for (int k = 0; k < 16; ++k) atomicAdd(Bd + k, Bjj[k]);
+  for (int o = kNodeLanes / 2; o > 0; o >>= 1) {
 #pragma unroll
-  for (int p = 0; p < 12; ++p) atomicAdd(rhs + (size_t)j * 12 + p, gl[p]);
+    for (int q = 0; q < 16; ++q) Bjj[q] += __shfl_xor_sync(full, Bjj[q], o);
+#pragma unroll
+    for (int p = 0; p < 12; ++p) gl[p] += __shfl_xor_sync(full, gl[p], o);
+  }
+  if (on && k < 4) {
+    float* Bd = B + (size_t)find_slot(row_ptr, col, (int)j, (int)j) * 16;
+    // lane k flushes row k of the 4x4 factor and 3 gradient entries
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c == k) {
+        b0 = Bjj[4 * c]; b1 = Bjj[4 * c + 1]; b2 = Bjj[4 * c + 2]; b3 = Bjj[4 * c + 3];
+        g0 = gl[3 * c]; g1 = gl[3 * c + 1]; g2 = gl[3 * c + 2];
+      }
+    red_add_f4(Bd + 4 * k, b0, b1, b2, b3);
+    atomicAdd(rhs + (size_t)j * 12 + 3 * k, g0);
+    atomicAdd(rhs + (size_t)j * 12 + 3 * k + 1, g1);
+    atomicAdd(rhs + (size_t)j * 12 + 3 * k + 2, g2);
+  }
 }
 
 // ------------------------------------------------------------------ preconditioner
-__global__ void __launch_bounds__(64)
+// 12x12 block-Jacobi preconditioner: 16 lanes per node, lane k holds row k of the diagonal block
+// D_j = kron(B_jj, I3) + Rot_j + lambda I in float64 registers and the group inverts it in place by
+// Gauss-Jordan elimination (D is symmetric positive definite: no pivoting), exchanging the pivot
+// row with shuffles.
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+
+__global__ void __launch_bounds__(128)
     k_precond(const int* __restrict__ row_ptr, const int* __restrict__ col,
               const float* __restrict__ B, const float* __restrict__ Rot, int64_t m, double lambda,
               float* __restrict__ Minv) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
-  double D[144];
-  for (int k = 0; k < 144; ++k) D[k] = 0.0;
-  const float* Bd = B + (size_t)find_slot(row_ptr, col, j, j) * 16;
-  for (int a = 0; a < 4; ++a)
-    for (int b = 0; b < 4; ++b)
-      for (int r = 0; r < 3; ++r) D[(3 * a + r) * 12 + 3 * b + r] += (double)Bd[4 * a + b];
-  const float* R = Rot + (size_t)j * 81;
-  for (int p = 0; p < 9; ++p)
-    for (int q = 0; q < 9; ++q) D[p * 12 + q] += (double)R[9 * p + q];
-  for (int k = 0; k < 12; ++k) D[k * 12 + k] += lambda;
-  // Cholesky D = L L^T (in place, lower), then inverse via L^-1
-  double L[144];
-  bool ok = true;
-  for (int i = 0; i < 12 && ok; ++i)
-    for (int c = 0; c <= i; ++c) {
-      double s = D[i * 12 + c];
-      for (int k = 0; k < c; ++k) s -= L[i * 12 + k] * L[c * 12 + k];
-      if (i == c) {
-        if (!(s > 0.0)) {
-          ok = false;
-          break;
-        }
-        L[i * 12 + i] = sqrt(s);
-      } else {
-        L[i * 12 + c] = s / L[c * 12 + c];
-      }
+  int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kNodeLanes;
+  int lane = threadIdx.x & 31;
+  int k = lane & (kNodeLanes - 1);
+  int gbase = lane & ~(kNodeLanes - 1);
+  bool on = j < m;
+  bool act = on && k < 12;
+  double a[12];
+  double diag0 = 1.0;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) a[q] = (q == k) ? 1.0 : 0.0;  // identity rows for idle lanes
+  if (act) {
+    const float* Bd = B + (size_t)find_slot(row_ptr, col, (int)j, (int)j) * 16;
+    int ka = k / 3, kr = k - 3 * ka;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+      int qa = q / 3, qr = q - 3 * qa;
+      double v = (qr == kr) ? (double)__ldg(Bd + 4 * ka + qa) : 0.0;
+      if (k < 9 && q < 9) v += (double)__ldg(Rot + (size_t)j * 81 + 9 * k + q);
+      if (q == k) v += lambda;
+      a[q] = v;
     }
-  float* out = Minv + (size_t)j * 144;
-  if (!ok) {
-    for (int k = 0; k < 144; ++k) out[k] = 0.f;
-    for (int k = 0; k < 12; ++k) out[13 * k] = (float)(1.0 / D[13 * k]);
-    return;
+#pragma unroll
+    for (int q = 0; q < 12; ++q)
+      if (q == k) diag0 = a[q];
   }
-  double Li[144];
-  for (int k = 0; k < 144; ++k) Li[k] = 0.0;
+  bool bad = false;
+#pragma unroll
   for (int c = 0; c < 12; ++c) {
-    Li[c * 12 + c] = 1.0 / L[c * 12 + c];
-    for (int i = c + 1; i < 12; ++i) {
-      double s = 0.0;
-      for (int k = c; k < i; ++k) s -= L[i * 12 + k] * Li[k * 12 + c];
-      Li[i * 12 + c] = s / L[i * 12 + i];
+    double piv = shfl_d(a[c], gbase + c);
+    if (!(piv > 0.0)) bad = true;
+    double d = 1.0 / piv;
+    double f = a[c];  // this row's entry in the pivot column
+    double prow[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) prow[q] = shfl_d(a[q], gbase + c) * d;  // scaled pivot row
+    if (k == c) {
+#pragma unroll
+      for (int q = 0; q < 12; ++q) a[q] = (q == c) ? d : prow[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 12; ++q) a[q] = (q == c) ? -f * d : a[q] - f * prow[q];
     }
   }
-  for (int i = 0; i < 12; ++i)
-    for (int c = 0; c < 12; ++c) {
-      double s = 0.0;
-      for (int k = (i > c ? i : c); k < 12; ++k) s += Li[k * 12 + i] * Li[k * 12 + c];
-      out[i * 12 + c] = (float)s;
-    }
+  // every lane of a node saw the same pivots, so `bad` is uniform over the node's 16 lanes:
+  // fall back to the inverse of the diagonal (Jacobi) for that node
+  if (act) {
+    float* out = Minv + (size_t)j * 144 + 12 * k;
+#pragma unroll
+    for (int q = 0; q < 12; ++q)
+      out[q] = bad ? ((q == k && diag0 > 0.0) ? (float)(1.0 / diag0) : 0.f) : (float)a[q];
+  }
 }
 
 int gn_assemble(mvs_deform* h) {
@@ -486,14 +532,14 @@ int gn_assemble(mvs_deform* h) {
   }
   {
     ProfScope ps(ctx, "gn_node_terms");
-    k_node_terms<<<div_up(h->m, 64), 64, 0, st>>>(h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m,
+    k_node_terms<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m,
                                                   h->row_ptr.p, h->col.p, h->B(), h->Rot(),
                                                   h->rhs(), (float)h->prm.w_rot,
                                                   (float)h->prm.w_reg);
   }
   {
     ProfScope ps(ctx, "gn_precond");
-    k_precond<<<div_up(h->m, 64), 64, 0, st>>>(h->row_ptr.p, h->col.p, h->B(), h->Rot(), h->m,
+    k_precond<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(h->row_ptr.p, h->col.p, h->B(), h->Rot(), h->m,
                                                h->prm.lambda, h->Minv.p);
   }
   MVS_CUDA(cudaGetLastError());

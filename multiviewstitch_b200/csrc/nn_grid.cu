@@ -385,6 +385,7 @@ int nn_build(mvs_nn_index* idx, const float4* pts, int64_t n, float target_ppc) 
   MVS_CUDA(cudaGetLastError());
   idx->g = g;
   idx->built = true;
+  idx->pyr_built = false;
   return MVS_OK;
 }
 
@@ -504,11 +505,15 @@ int nn_knn(mvs_nn_index* idx, const float4* q, int64_t nq, int k, int* out_idx, 
     MVS_CUDA(cudaGetLastError());
     perm = idx->q_perm.p;
   }
+  if (k == 1) {
+    // 1-NN: sparse occupancy pyramid (built lazily from the cell-sorted copy, .w = original index)
+    if (!idx->pyr_built)
+      MVS_TRY(nn_build_pyramid(idx, idx->pts_sorted.p, idx->g.n, 3.0f, true));
+    return nn_nn1_pyramid(idx, q, perm, nq, out_idx, out_d2);
+  }
   {
     ProfScope ps(ctx, "knn");
-    if (k <= 1)
-      launch_knn<1>(idx, q, perm, nq, k, out_idx, out_d2);
-    else if (k <= 4)
+    if (k <= 4)
       launch_knn<4>(idx, q, perm, nq, k, out_idx, out_d2);
     else if (k <= 5)
       launch_knn<5>(idx, q, perm, nq, k, out_idx, out_d2);
@@ -537,6 +542,7 @@ int mvs_nn_index_create(mvs_ctx* ctx, mvs_nn_index** out) {
   if (!ctx) return MVS_ERR_NO_DEVICE;
   mvs_nn_index* i = new mvs_nn_index();
   i->ctx = ctx;
+  ctx_retain(ctx);
   *out = i;
   return MVS_OK;
 }
@@ -545,7 +551,9 @@ int mvs_nn_index_destroy(mvs_nn_index* idx) {
   if (!idx) return MVS_OK;
   cudaSetDevice(idx->ctx->device);
   cudaStreamSynchronize(idx->ctx->stream);
+  mvs_ctx* ctx = idx->ctx;
   delete idx;
+  ctx_release(ctx);
   return MVS_OK;
 }
 

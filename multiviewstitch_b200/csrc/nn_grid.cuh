@@ -163,6 +163,22 @@ struct KnnList {
   }
 };
 
+// sparse occupancy pyramid (nn_pyramid.cuh)
+struct PyrParams {
+  float bmin[3];
+  float h, inv_h;
+  int dims[3];    // fine cells
+  int d1[3];      // bricks
+  int d2[3], d3[3], d4[3];
+  const ulonglong2* b1;  // per brick: .x occupancy mask of its cells, .y first occupied-cell index
+  const unsigned long long* m2;
+  const unsigned long long* m3;
+  const unsigned long long* m4;
+  const int* occ_start;
+  const float4* pts;
+  int64_t n;
+};
+
 }  // namespace mvs
 
 // Device-resident search structure.
@@ -183,11 +199,28 @@ struct mvs_nn_index {
   mvs::DevBuf<int> o_idx;
   mvs::DevBuf<float> o_d2;
   bool built = false;
+  // sparse occupancy pyramid (exact 1-NN / fixed-radius queries; nn_pyramid.cu)
+  mvs::PyrParams pyr{};
+  bool pyr_built = false;
+  int pyr_n_occ = 0;
+  float pyr_last_h = 0.f;
+  int64_t pyr_last_n = 0;
+  double pyr_last_ext = 0.0;
+  mvs::DevBuf<unsigned long long> pyr_keys, pyr_keys2, pyr_m2, pyr_m3, pyr_m4;
+  mvs::DevBuf<ulonglong2> pyr_b1;
+  mvs::DevBuf<int> pyr_vals, pyr_order, pyr_flag, pyr_occ;
+  mvs::DevBuf<float4> pyr_pts;
+  mvs::DevBuf<char> pyr_tmp;
 };
 
 namespace mvs {
 // Build from device float4 points (w ignored).  target_ppc: wanted points per occupied cell.
 int nn_build(mvs_nn_index* idx, const float4* pts_dev, int64_t n, float target_ppc = 3.0f);
+// Sparse pyramid over device float4 points (w ignored unless w_is_index).
+int nn_build_pyramid(mvs_nn_index* idx, const float4* pts_dev, int64_t n, float target_ppc = 3.0f,
+                     bool w_is_index = false);
+int nn_nn1_pyramid(mvs_nn_index* idx, const float4* q_dev, const int* perm_dev, int64_t nq,
+                   int* out_idx_dev, float* out_d2_dev);
 // Exact kNN, device pointers. out_idx: nq*k, out_d2: nq*k (either may be null).
 int nn_knn(mvs_nn_index* idx, const float4* q_dev, int64_t nq, int k, int* out_idx_dev,
            float* out_d2_dev);

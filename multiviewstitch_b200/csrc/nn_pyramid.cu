@@ -1,0 +1,327 @@
+// nn_pyramid.cu — build of the sparse occupancy pyramid (nn_pyramid.cuh) and the exact 1-NN kernel
+// that uses it.  Build = one radix sort of (cell key, point id) + three small passes; no dense cell
+// table is ever allocated.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <stdlib.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "nn_pyramid.cuh"
+
+namespace mvs {
+
+struct PyrGeom {
+  float bmin[3];
+  float h, inv_h;
+  int dims[3], d1[3], d2[3], d3[3], d4[3];
+};
+
+__device__ __forceinline__ unsigned long long cell_key(const PyrGeom& g, float4 p) {
+  int cx = grid_coord(p.x, g.bmin[0], g.inv_h, g.dims[0]);
+  int cy = grid_coord(p.y, g.bmin[1], g.inv_h, g.dims[1]);
+  int cz = grid_coord(p.z, g.bmin[2], g.inv_h, g.dims[2]);
+  unsigned long long brick =
+      ((unsigned long long)(cz >> 2) * g.d1[1] + (cy >> 2)) * g.d1[0] + (cx >> 2);
+  unsigned bit = ((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3);
+  return (brick << 6) | bit;
+}
+
+__global__ void k_pyr_keys(PyrGeom g, const float4* __restrict__ pts, int64_t n,
+                           unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    keys[i] = cell_key(g, __ldg(pts + i));
+    vals[i] = (int)i;
+  }
+}
+
+__global__ void k_pyr_heads(const unsigned long long* __restrict__ keys, int64_t n,
+                            int* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// scan[i] = number of heads before i; a head at i opens occupied cell scan[i]
+__global__ void k_pyr_fill(const unsigned long long* __restrict__ keys,
+                           const int* __restrict__ order, const int* __restrict__ scan, int64_t n,
+                           const float4* __restrict__ pts_in, const float* __restrict__ w_from,
+                           float4* __restrict__ pts_out, int* __restrict__ occ_start,
+                           ulonglong2* __restrict__ b1) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int src = order[i];
+    float4 p = __ldg(pts_in + src);
+    // .w = original point index (taken from the input's .w when the input is itself a sorted copy)
+    p.w = w_from ? __ldg(w_from + 4 * (size_t)src + 3) : __int_as_float(src);
+    pts_out[i] = p;
+    unsigned long long k = keys[i];
+    bool head = (i == 0) || (k != keys[i - 1]);
+    if (head) {
+      int oi = scan[i];
+      occ_start[oi] = (int)i;
+      unsigned long long brick = k >> 6;
+      unsigned long long* rec = reinterpret_cast<unsigned long long*>(b1 + brick);
+      atomicOr(rec, 1ull << (k & 63));
+      atomicMin(rec + 1, (unsigned long long)oi);
+    }
+  }
+}
+
+__global__ void k_pyr_clear(ulonglong2* __restrict__ b1, int64_t n) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) b1[t] = make_ulonglong2(0ull, ~0ull);
+}
+
+__global__ void k_pyr_up(const unsigned long long* __restrict__ child, int child_stride, int cx,
+                         int cy, int cz, unsigned long long* __restrict__ parent, int px, int py) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t nchild = (int64_t)cx * cy * cz;
+  if (t >= nchild) return;
+  if (child[t * child_stride] == 0ull) return;
+  int x = (int)(t % cx), y = (int)((t / cx) % cy), z = (int)(t / ((int64_t)cx * cy));
+  unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
+  atomicOr(parent + ((size_t)(z >> 2) * py + (y >> 2)) * px + (x >> 2), 1ull << bit);
+}
+
+static void set_geom(const float mn[3], const float mx[3], float h, PyrGeom& g) {
+  g.h = h;
+  g.inv_h = 1.0f / h;
+  for (int a = 0; a < 3; ++a) {
+    g.bmin[a] = mn[a];
+    double e = (double)mx[a] - (double)mn[a];
+    g.dims[a] = std::max(1, (int)std::floor(e / h) + 1);
+    g.d1[a] = (g.dims[a] + 3) / 4;
+    g.d2[a] = (g.d1[a] + 3) / 4;
+    g.d3[a] = (g.d2[a] + 3) / 4;
+    g.d4[a] = (g.d3[a] + 3) / 4;
+  }
+}
+
+constexpr int kPyrMaxDim = 2048;
+constexpr int64_t kPyrMaxBricks = (int64_t)1 << 25;
+
+static float pyr_clamp_h(const float mn[3], const float mx[3], float h) {
+  for (int it = 0; it < 64; ++it) {
+    PyrGeom g;
+    set_geom(mn, mx, h, g);
+    bool ok = (int64_t)g.d1[0] * g.d1[1] * g.d1[2] <= kPyrMaxBricks;
+    for (int a = 0; a < 3; ++a) ok = ok && g.dims[a] <= kPyrMaxDim;
+    if (ok) return h;
+    h *= 1.26f;
+  }
+  return h;
+}
+
+int bbox_host(mvs_ctx* ctx, const float4* pts, int64_t n, DevBuf<float>& red, float mn[3],
+              float mx[3]);
+
+// Build from device float4 points.  w_is_index: the input's .w already carries the original index
+// (input is a sorted copy made by nn_build).
+int nn_build_pyramid(mvs_nn_index* idx, const float4* pts, int64_t n, float target_ppc,
+                     bool w_is_index) {
+  mvs_ctx* ctx = idx->ctx;
+  MVS_TRY(ctx_ensure_device(ctx));
+  cudaStream_t st = ctx->stream;
+  idx->pyr_built = false;
+  if (n <= 0) {
+    set_error("nn_build_pyramid: empty point set");
+    return MVS_ERR_DEGENERATE;
+  }
+  if (n >= (int64_t)INT32_MAX) {
+    set_error("nn_build_pyramid: more than 2^31-1 points");
+    return MVS_ERR_INVALID_ARG;
+  }
+  float mn[3], mx[3];
+  MVS_TRY(bbox_host(ctx, pts, n, idx->red, mn, mx));
+  double ext[3], emax = 0;
+  for (int a = 0; a < 3; ++a) {
+    ext[a] = (double)mx[a] - (double)mn[a];
+    emax = std::max(emax, ext[a]);
+  }
+  PyrGeom g;
+  bool degenerate = !(emax > 0) || !std::isfinite(emax);
+  float h;
+  if (degenerate) {
+    h = 1.0f;
+  } else if (idx->pyr_last_h > 0.f && idx->pyr_last_n == n &&
+             std::fabs(emax - idx->pyr_last_ext) <= 0.25 * emax) {
+    h = idx->pyr_last_h;  // same-sized rebuild (next frame of the same scan): reuse the cell size
+  } else {
+    double vol = 1.0;
+    for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 1e-3 * emax);
+    h = (float)std::cbrt(vol * target_ppc / (double)n);
+  }
+  h = pyr_clamp_h(mn, mx, h);
+  set_geom(mn, mx, h, g);
+  if (degenerate)
+    for (int a = 0; a < 3; ++a) g.dims[a] = g.d1[a] = g.d2[a] = g.d3[a] = g.d4[a] = 1;
+
+  MVS_TRY(idx->pyr_keys.reserve((size_t)n));
+  MVS_TRY(idx->pyr_keys2.reserve((size_t)n));
+  MVS_TRY(idx->pyr_vals.reserve((size_t)n));
+  MVS_TRY(idx->pyr_order.reserve((size_t)n));
+  MVS_TRY(idx->pyr_flag.reserve((size_t)n + 2));
+  MVS_TRY(idx->pyr_pts.reserve((size_t)n));
+  MVS_TRY(idx->pyr_occ.reserve((size_t)n + 2));
+  int gridn = grid_for(ctx, n, 256, 8);
+  int n_occ = 0;
+  int64_t nb1 = 0;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    nb1 = (int64_t)g.d1[0] * g.d1[1] * g.d1[2];
+    int key_bits = 6;
+    while (((int64_t)1 << (key_bits - 6)) < nb1) ++key_bits;
+    {
+      ProfScope ps(ctx, "pyr_keys");
+      k_pyr_keys<<<gridn, 256, 0, st>>>(g, pts, n, idx->pyr_keys.p, idx->pyr_vals.p);
+    }
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, idx->pyr_keys.p, idx->pyr_keys2.p,
+                                    idx->pyr_vals.p, idx->pyr_order.p, (int)n, 0, key_bits, st);
+    MVS_TRY(idx->pyr_tmp.reserve(tmp_bytes));
+    {
+      ProfScope ps(ctx, "pyr_sort", 4);
+      MVS_CUDA(cub::DeviceRadixSort::SortPairs(idx->pyr_tmp.p, tmp_bytes, idx->pyr_keys.p,
+                                               idx->pyr_keys2.p, idx->pyr_vals.p, idx->pyr_order.p,
+                                               (int)n, 0, key_bits, st));
+    }
+    {
+      ProfScope ps(ctx, "pyr_heads");
+      k_pyr_heads<<<gridn, 256, 0, st>>>(idx->pyr_keys2.p, n, idx->pyr_flag.p);
+    }
+    MVS_CUDA(cudaMemsetAsync(idx->pyr_flag.p + n, 0, sizeof(int) * 2, st));
+    MVS_TRY(exclusive_scan_inplace(ctx, idx->pyr_flag.p, n, idx->scan_tmp));
+    MVS_TRY(d2h_sync(ctx, &n_occ, idx->pyr_flag.p + n, sizeof(int)));
+    if (attempt == 2 || degenerate) break;
+    double ppc = (double)n / (double)std::max(n_occ, 1);
+    if (ppc <= 2.0 * target_ppc) break;
+    // surfaces occupy O(1/h^2) cells: shrink h using the measured occupancy
+    float h_new = pyr_clamp_h(mn, mx, g.h * (float)std::sqrt(target_ppc / ppc));
+    if (h_new >= g.h * 0.95f) break;
+    set_geom(mn, mx, h_new, g);
+  }
+  idx->pyr_last_h = g.h;
+  idx->pyr_last_n = n;
+  idx->pyr_last_ext = emax;
+  int64_t nb2 = (int64_t)g.d2[0] * g.d2[1] * g.d2[2], nb3 = (int64_t)g.d3[0] * g.d3[1] * g.d3[2],
+          nb4 = (int64_t)g.d4[0] * g.d4[1] * g.d4[2];
+  MVS_TRY(idx->pyr_b1.reserve((size_t)nb1));
+  MVS_TRY(idx->pyr_m2.reserve((size_t)nb2));
+  MVS_TRY(idx->pyr_m3.reserve((size_t)nb3));
+  MVS_TRY(idx->pyr_m4.reserve((size_t)nb4));
+  {
+    ProfScope ps(ctx, "pyr_clear");
+    k_pyr_clear<<<div_up(nb1, 256), 256, 0, st>>>(idx->pyr_b1.p, nb1);
+  }
+  MVS_CUDA(cudaMemsetAsync(idx->pyr_m2.p, 0, sizeof(unsigned long long) * nb2, st));
+  MVS_CUDA(cudaMemsetAsync(idx->pyr_m3.p, 0, sizeof(unsigned long long) * nb3, st));
+  MVS_CUDA(cudaMemsetAsync(idx->pyr_m4.p, 0, sizeof(unsigned long long) * nb4, st));
+  {
+    ProfScope ps(ctx, "pyr_fill");
+    k_pyr_fill<<<gridn, 256, 0, st>>>(idx->pyr_keys2.p, idx->pyr_order.p, idx->pyr_flag.p, n, pts,
+                                      w_is_index ? reinterpret_cast<const float*>(pts) : nullptr,
+                                      idx->pyr_pts.p, idx->pyr_occ.p, idx->pyr_b1.p);
+  }
+  int n32 = (int)n;
+  MVS_CUDA(cudaMemcpyAsync(idx->pyr_occ.p + n_occ, &n32, sizeof(int), cudaMemcpyHostToDevice, st));
+  {
+    ProfScope ps(ctx, "pyr_levels", 3);
+    k_pyr_up<<<div_up(nb1, 256), 256, 0, st>>>(
+        reinterpret_cast<const unsigned long long*>(idx->pyr_b1.p), 2, g.d1[0], g.d1[1], g.d1[2],
+        idx->pyr_m2.p, g.d2[0], g.d2[1]);
+    k_pyr_up<<<div_up(nb2, 256), 256, 0, st>>>(idx->pyr_m2.p, 1, g.d2[0], g.d2[1], g.d2[2],
+                                               idx->pyr_m3.p, g.d3[0], g.d3[1]);
+    k_pyr_up<<<div_up(nb3, 256), 256, 0, st>>>(idx->pyr_m3.p, 1, g.d3[0], g.d3[1], g.d3[2],
+                                               idx->pyr_m4.p, g.d4[0], g.d4[1]);
+  }
+  MVS_CUDA(cudaGetLastError());
+  MVS_CUDA(cudaStreamSynchronize(st));  // n32 is on the stack
+  PyrParams& P = idx->pyr;
+  for (int a = 0; a < 3; ++a) {
+    P.bmin[a] = g.bmin[a];
+    P.dims[a] = g.dims[a];
+    P.d1[a] = g.d1[a];
+    P.d2[a] = g.d2[a];
+    P.d3[a] = g.d3[a];
+    P.d4[a] = g.d4[a];
+  }
+  P.h = g.h;
+  P.inv_h = g.inv_h;
+  P.b1 = idx->pyr_b1.p;
+  P.m2 = idx->pyr_m2.p;
+  P.m3 = idx->pyr_m3.p;
+  P.m4 = idx->pyr_m4.p;
+  P.occ_start = idx->pyr_occ.p;
+  P.pts = idx->pyr_pts.p;
+  P.n = n;
+  idx->pyr_n_occ = n_occ;
+  idx->pyr_built = true;
+  return MVS_OK;
+}
+
+// ------------------------------------------------------------------ exact 1-NN over the pyramid
+__global__ void __launch_bounds__(128)
+    k_nn1_pyr(PyrParams P, const float4* __restrict__ q, const int* __restrict__ perm, int64_t nq,
+              int* __restrict__ out_idx, float* __restrict__ out_d2) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  int64_t i = perm ? perm[t] : t;
+  float4 qq = __ldg(q + i);
+  KnnList<1> list;
+  list.init(qq.x, qq.y, qq.z);
+  pyr_search(P, qq.x, qq.y, qq.z, list);
+  if (out_idx) out_idx[i] = list.idx[0] == 0x7fffffff ? -1 : list.idx[0];
+  if (out_d2) out_d2[i] = list.d2[0];
+}
+
+// debug: number of candidate points each query evaluated (MVS_PYR_DEBUG=1 routes 1-NN calls here
+// and returns the count in out_d2)
+struct CountingNN {
+  KnnList<1> l;
+  int npts;
+  __device__ __forceinline__ float worst2() const { return l.worst2(); }
+  __device__ __forceinline__ void point(float4 p) {
+    ++npts;
+    l.point(p);
+  }
+};
+__global__ void __launch_bounds__(128)
+    k_nn1_pyr_count(PyrParams P, const float4* __restrict__ q, int64_t nq, int* __restrict__ out_idx,
+                    float* __restrict__ out_d2) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  float4 qq = __ldg(q + i);
+  CountingNN c;
+  c.l.init(qq.x, qq.y, qq.z);
+  c.npts = 0;
+  long long t0 = clock64();
+  pyr_search(P, qq.x, qq.y, qq.z, c);
+  long long t1 = clock64();
+  if (out_idx) out_idx[i] = c.npts;
+  if (out_d2) out_d2[i] = (float)(t1 - t0);
+}
+
+int nn_nn1_pyramid(mvs_nn_index* idx, const float4* q, const int* perm, int64_t nq, int* out_idx,
+                   float* out_d2) {
+  mvs_ctx* ctx = idx->ctx;
+  if (!idx->pyr_built) {
+    set_error("nn_nn1_pyramid: pyramid not built");
+    return MVS_ERR_STATE;
+  }
+  if (nq <= 0) return MVS_OK;
+  if (getenv("MVS_PYR_DEBUG")) {
+    k_nn1_pyr_count<<<div_up(nq, 128), 128, 0, ctx->stream>>>(idx->pyr, q, nq, out_idx, out_d2);
+    MVS_CUDA(cudaGetLastError());
+    return MVS_OK;
+  }
+  ProfScope ps(ctx, "nn1_pyramid");
+  k_nn1_pyr<<<div_up(nq, 128), 128, 0, ctx->stream>>>(idx->pyr, q, perm, nq, out_idx, out_d2);
+  MVS_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+}  // namespace mvs

@@ -2,188 +2,433 @@
 // in the Kronecker-compressed block-CSR form (deform.cuh): per pattern entry (j,l) a 4x4 factor
 // B_jl with H_jl = kron(B_jl, I3), plus a dense 9x9 rotation block and lambda on the diagonal.
 //
-// Two kernels per iteration, all scalars stay on the device (no host round trip):
-//   k_pcg_spmv    p = z + beta p_prev (recomputed on the fly for gathered rows, written for the own
-//                 row), q = H p, pq = p.q (grid reduction)
-//   k_pcg_update  alpha = rz/pq; delta += alpha p; r -= alpha q; z = M^-1 r; rz' = r.z, |r|^2
-// 16 lanes per node row (12 active: one per unknown), 2 rows per warp; the 12 entries of a
-// neighbour's vector are exchanged with warp shuffles inside the 16-lane group.
-// Vectors are float32, every dot product is float64 with a fixed reduction tree.
+// ONE persistent cooperative kernel runs the whole solve (all PCG iterations + x += delta):
+//   * a CTA owns a contiguous range of node rows; its slice of the matrix (the 4x4 factors and
+//     their column indices) is staged into shared memory once and reused by every iteration, so per
+//     iteration only vectors move (L2-resident);
+//   * 16 lanes per node row (12 active: one per unknown); r, z, p, delta of a row live in
+//     registers for the whole solve (RS row slots per lane group);
+//   * two grid-wide barriers per iteration (after p.q and after r.z); dot products are float64 with
+//     a fixed reduction order (lane -> warp -> CTA partial in global memory -> every CTA adds the
+//     partials in CTA order), so the solve is bit-reproducible run to run;
+//   * the search direction of a neighbour row is rebuilt on the fly as z_l + beta p_prev_l, which
+//     saves the third barrier a separate "p = z + beta p" phase would need.
+// Standard PCG recurrences, identical to oracle/deform.cpp pcg(); vectors float32, scalars float64.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "deform.cuh"
-#include "reduce.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mvs {
 
 constexpr int kRowLanes = 16;
 constexpr int kPcgThreads = 256;
-constexpr int kRowsPerBlock = kPcgThreads / kRowLanes;
+constexpr int kGroups = kPcgThreads / kRowLanes;  // row groups per CTA
 
-enum { S_RZ0 = 0, S_RZ1 = 1, S_PQV = 2, S_BN2 = 3, S_RN2 = 4, S_DONE = 5 };
+struct PcgArgs {
+  const int* row_ptr;
+  const int* col;
+  const float* B;
+  const float* Rot;
+  const float* Minv;
+  const float* rhs;
+  float* x;       // node state, updated in place at the end
+  float* zbuf;    // m x 12
+  float* pbuf;    // 2 x m x 12
+  float* delta;   // m x 12 (exported for inspection)
+  double* part;   // 3 x grid partial sums
+  double* scal;   // S_* slots
+  int64_t m;
+  int iters;
+  float lambda;
+  double tol;
+  int rows_per_cta;
+  int stage_smem;  // 1: matrix slice staged in shared memory
+};
 
-// r = -g, delta = 0, z = M^-1 r, p = z, rz = r.z, |b|^2
-__global__ void __launch_bounds__(kPcgThreads)
-    k_pcg_init(const float* __restrict__ rhs, const float* __restrict__ Minv, int64_t m,
-               float* __restrict__ r, float* __restrict__ z, float* __restrict__ p,
-               float* __restrict__ delta, double* partials, unsigned* ticket, double* scal) {
-  __shared__ double smem[32 * 2];
-  const unsigned full = 0xffffffffu;
-  int lane = threadIdx.x & 31;
-  int k = lane & (kRowLanes - 1);
-  int gbase = lane & ~(kRowLanes - 1);
-  int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x / kRowLanes);
-  bool act = row < m && k < 12;
-  float rv = act ? -rhs[row * 12 + k] : 0.f;
-  float zv = 0.f;
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-  for (int q = 0; q < 12; ++q) {
-    float rq = __shfl_sync(full, rv, gbase + q);
-    if (act) zv += __ldg(Minv + row * 144 + k * 12 + q) * rq;
-  }
-  if (act) {
-    r[row * 12 + k] = rv;
-    z[row * 12 + k] = zv;
-    p[row * 12 + k] = zv;
-    delta[row * 12 + k] = 0.f;
-  }
-  double v[2] = {(double)rv * (double)zv, (double)rv * (double)rv};
-  if (grid_reduce_sum<2>(v, smem, partials, ticket, scal + 6)) {
-    if (threadIdx.x == 0) {
-      scal[S_RZ0] = scal[6];
-      scal[S_BN2] = scal[7];
-      scal[S_RN2] = scal[7];
-      scal[S_DONE] = 0.0;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// CTA-wide sum of N doubles -> thread 0 writes them to out[0..N)
+template <int N>
+__device__ __forceinline__ void cta_partial(double (&v)[N], double* smem, double* out) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = warp_sum(v[j]);
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < N; ++j) smem[warp * N + j] = v[j];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+      for (int w = 0; w < kPcgThreads / 32; ++w) s += smem[w * N + j];
+      out[j] = s;
     }
+  }
+  __syncthreads();
+}
+
+// Totals of N per-CTA partials (stride 3 doubles per CTA) after a grid barrier: every thread
+// loads at most two partials (independent loads: one L2 latency instead of a serial chain), then a
+// fixed-order warp / CTA reduction; all threads return the same totals.
+template <int N>
+__device__ __forceinline__ void grid_totals(const double* part, int ncta, double* smem,
+                                            double (&out)[N]) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = 0.0;
+  int c0 = threadIdx.x, c1 = threadIdx.x + kPcgThreads;
+  double a0[N], a1[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    a0[j] = c0 < ncta ? __ldcg(part + (size_t)c0 * 3 + j) : 0.0;
+    a1[j] = c1 < ncta ? __ldcg(part + (size_t)c1 * 3 + j) : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = a0[j] + a1[j];
+  for (int c = threadIdx.x + 2 * kPcgThreads; c < ncta; c += kPcgThreads)
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] += __ldcg(part + (size_t)c * 3 + j);
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = warp_sum(v[j]);
+  __syncthreads();  // smem may still be read by the previous use
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < N; ++j) smem[warp * N + j] = v[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kPcgThreads / 32; ++w) t += smem[w * N + j];
+    out[j] = t;
   }
 }
 
-__global__ void __launch_bounds__(kPcgThreads)
-    k_pcg_spmv(const int* __restrict__ row_ptr, const int* __restrict__ col,
-               const float* __restrict__ B, const float* __restrict__ Rot, float lambda, int64_t m,
-               int it, const float* __restrict__ z, const float* __restrict__ p_prev,
-               float* __restrict__ p_cur, float* __restrict__ qv, double* partials,
-               unsigned* ticket, double* scal) {
-  __shared__ double smem[32];
+// zp[buf][row][k] = (z, p): z of the row after the update of an iteration, p its search direction;
+// iteration `it` reads buffer (it+1)&1 (written during iteration it-1) and writes buffer it&1.
+template <int RS>
+__global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ float4 smem_dyn[];
+  __shared__ double red[(kPcgThreads / 32) * 2];
   const unsigned full = 0xffffffffu;
-  int lane = threadIdx.x & 31;
-  int k = lane & (kRowLanes - 1);
-  int gbase = lane & ~(kRowLanes - 1);
-  int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x / kRowLanes);
-  bool rowok = row < m;
-  bool act = rowok && k < 12;
-  float beta = 0.f;
-  if (it > 0) {
-    double rz_old = scal[(it - 1) & 1], rz_new = scal[it & 1];
-    beta = rz_old > 0.0 ? (float)(rz_new / rz_old) : 0.f;
+  const int lane = threadIdx.x & 31;
+  const int k = lane & (kRowLanes - 1);
+  const int gbase = lane & ~(kRowLanes - 1);
+  const int gi = threadIdx.x / kRowLanes;
+  const int ncta = gridDim.x;
+  const int64_t m = a.m;
+  const int64_t row0 = (int64_t)blockIdx.x * a.rows_per_cta;
+  const int64_t row1 = min(m, row0 + a.rows_per_cta);
+  const bool lane_on = k < 12;
+  const int ba = k / 3, rr = k - 3 * ba;
+  float2* zp = reinterpret_cast<float2*>(a.zbuf);  // 2 x m x 12 float2
+
+  // ---- stage this CTA's matrix slice
+  const int nz0 = row0 < m ? __ldg(a.row_ptr + row0) : 0;
+  const int nz1 = row0 < m ? __ldg(a.row_ptr + row1) : 0;
+  const float4* Bsrc = reinterpret_cast<const float4*>(a.B) + (size_t)nz0 * 4;
+  const int* csrc = a.col + nz0;
+  const float4* Bs = Bsrc;
+  const int* cs = csrc;
+  if (a.stage_smem) {
+    int nb = (nz1 - nz0) * 4;
+    int* scol = reinterpret_cast<int*>(smem_dyn + nb);
+    for (int i = threadIdx.x; i < nb; i += kPcgThreads) smem_dyn[i] = __ldg(Bsrc + i);
+    for (int i = threadIdx.x; i < nz1 - nz0; i += kPcgThreads) scol[i] = __ldg(csrc + i);
+    Bs = smem_dyn;
+    cs = scol;
+    __syncthreads();
   }
-  // own row's search direction
-  float pj = 0.f;
-  if (act) {
-    pj = (it == 0) ? p_prev[row * 12 + k] : z[row * 12 + k] + beta * p_prev[row * 12 + k];
-    p_cur[row * 12 + k] = pj;
-  }
-  float y = lambda * pj;
-  // dense rotation block on the first 9 unknowns
+
+  float r[RS], z[RS], p[RS], d[RS];
+  int t0s[RS], t1s[RS];
+  // with one row slot the rows of M^-1 and of the rotation block stay in registers for the solve
+  float minv[RS == 1 ? 12 : 1], rot[RS == 1 ? 9 : 1];
+  // ---- init: r = -g, z = M^-1 r, delta = 0, p_prev = 0
+  double acc[2] = {0.0, 0.0};
 #pragma unroll
-  for (int q = 0; q < 9; ++q) {
-    float pq = __shfl_sync(full, pj, gbase + q);
-    if (act && k < 9) y += __ldg(Rot + row * 81 + k * 9 + q) * pq;
-  }
-  int s = rowok ? __ldg(row_ptr + row) : 0;
-  int e = rowok ? __ldg(row_ptr + row + 1) : 0;
-  int len = e - s;
-  int maxlen = max(len, __shfl_xor_sync(full, len, kRowLanes));
-  int a = k / 3, rr = k - 3 * a;
-  for (int t = 0; t < maxlen; ++t) {
-    bool have = t < len;
-    int l = have ? __ldg(col + s + t) : 0;
-    float pl = 0.f;
-    if (have && k < 12) {
-      int64_t o = (int64_t)l * 12 + k;
-      pl = (it == 0) ? __ldg(p_prev + o) : __ldg(z + o) + beta * __ldg(p_prev + o);
+  for (int s = 0; s < RS; ++s) {
+    int64_t j = row0 + s * kGroups + gi;
+    bool on = j < row1;
+    bool act = on && lane_on;
+    t0s[s] = act ? __ldg(a.row_ptr + j) - nz0 : 0;
+    t1s[s] = act ? __ldg(a.row_ptr + j + 1) - nz0 : 0;
+    if (RS == 1) {
+#pragma unroll
+      for (int q = 0; q < 12; ++q) minv[q] = act ? __ldg(a.Minv + j * 144 + k * 12 + q) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) rot[q] = (act && k < 9) ? __ldg(a.Rot + j * 81 + k * 9 + q) : 0.f;
     }
-    float v0 = __shfl_sync(full, pl, gbase + rr);
-    float v1 = __shfl_sync(full, pl, gbase + 3 + rr);
-    float v2 = __shfl_sync(full, pl, gbase + 6 + rr);
-    float v3 = __shfl_sync(full, pl, gbase + 9 + rr);
-    if (have && act) {
-      float4 Ba = __ldg(reinterpret_cast<const float4*>(B + (size_t)(s + t) * 16 + 4 * a));
-      y += Ba.x * v0 + Ba.y * v1 + Ba.z * v2 + Ba.w * v3;
+    r[s] = act ? -__ldg(a.rhs + j * 12 + k) : 0.f;
+    float zv = 0.f;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+      float rq = __shfl_sync(full, r[s], gbase + q);
+      if (RS == 1)
+        zv += minv[q] * rq;
+      else if (act)
+        zv += __ldg(a.Minv + j * 144 + k * 12 + q) * rq;
+    }
+    z[s] = zv;
+    p[s] = 0.f;
+    d[s] = 0.f;
+    if (act) zp[(size_t)m * 12 + j * 12 + k] = make_float2(zv, 0.f);  // buffer 1: read by iteration 0
+    acc[0] += (double)r[s] * (double)zv;
+    acc[1] += (double)r[s] * (double)r[s];
+  }
+  cta_partial<2>(acc, red, a.part + (size_t)blockIdx.x * 3 + 1);
+  grid.sync();
+  double rz, bn2;
+  {
+    double tot[2];
+    grid_totals<2>(a.part + 1, ncta, red, tot);
+    rz = tot[0];
+    bn2 = tot[1];
+  }
+  double rn2 = bn2;
+  double rz_old = 0.0;
+  int it = 0;
+  for (; it < a.iters; ++it) {
+    if (a.tol > 0.0 && rn2 <= a.tol * a.tol * bn2) break;  // uniform over the grid
+    // ---- phase A: p = z + beta p ; q = (H + lambda) p ; p.q
+    float beta = (it > 0 && rz_old > 0.0) ? (float)(rz / rz_old) : 0.f;
+    const float2* zprev = zp + (size_t)((it + 1) & 1) * m * 12;
+    float2* zcur = zp + (size_t)(it & 1) * m * 12;
+    float qv[RS];
+    double pq[1] = {0.0};
+#pragma unroll
+    for (int s = 0; s < RS; ++s) {
+      int64_t j = row0 + s * kGroups + gi;
+      bool on = j < row1;
+      bool act = on && lane_on;
+      p[s] = z[s] + beta * p[s];
+      if (act) zcur[j * 12 + k].y = p[s];
+      float y = a.lambda * p[s];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        float pqv = __shfl_sync(full, p[s], gbase + q);
+        if (RS == 1)
+          y += rot[q] * pqv;
+        else if (act && k < 9)
+          y += __ldg(a.Rot + j * 81 + k * 9 + q) * pqv;
+      }
+      if (act) {
+        int t = t0s[s];
+        const int t1 = t1s[s];
+        for (; t + 8 <= t1; t += 8) {  // 8 neighbours (32 loads) in flight
+          float2 v[8][4];
+          float4 Bv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            int l = cs[t + u];
+            Bv[u] = Bs[(size_t)(t + u) * 4 + ba];
+            const float2* src = zprev + (size_t)l * 12 + rr;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[u][b] = __ldcg(src + 3 * b);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            y += Bv[u].x * (v[u][0].x + beta * v[u][0].y) + Bv[u].y * (v[u][1].x + beta * v[u][1].y) +
+                 Bv[u].z * (v[u][2].x + beta * v[u][2].y) + Bv[u].w * (v[u][3].x + beta * v[u][3].y);
+        }
+        for (; t + 2 <= t1; t += 2) {
+          float2 v[2][4];
+          float4 Bv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            int l = cs[t + u];
+            Bv[u] = Bs[(size_t)(t + u) * 4 + ba];
+            const float2* src = zprev + (size_t)l * 12 + rr;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[u][b] = __ldcg(src + 3 * b);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            y += Bv[u].x * (v[u][0].x + beta * v[u][0].y) + Bv[u].y * (v[u][1].x + beta * v[u][1].y) +
+                 Bv[u].z * (v[u][2].x + beta * v[u][2].y) + Bv[u].w * (v[u][3].x + beta * v[u][3].y);
+        }
+        if (t < t1) {
+          int l = cs[t];
+          float4 Bv = Bs[(size_t)t * 4 + ba];
+          const float2* src = zprev + (size_t)l * 12 + rr;
+          float2 v0 = __ldcg(src), v1 = __ldcg(src + 3), v2 = __ldcg(src + 6), v3 = __ldcg(src + 9);
+          y += Bv.x * (v0.x + beta * v0.y) + Bv.y * (v1.x + beta * v1.y) +
+               Bv.z * (v2.x + beta * v2.y) + Bv.w * (v3.x + beta * v3.y);
+        }
+      } else {
+        y = 0.f;
+      }
+      qv[s] = y;
+      pq[0] += (double)p[s] * (double)y;
+    }
+    cta_partial<1>(pq, red, a.part + (size_t)blockIdx.x * 3);
+    grid.sync();
+    // ---- phase B: alpha ; delta += alpha p ; r -= alpha q ; z = M^-1 r ; r.z, |r|^2
+    double pqa[1];
+    grid_totals<1>(a.part, ncta, red, pqa);
+    double pqt = pqa[0];
+    float alpha = (pqt > 0.0 && rz > 0.0) ? (float)(rz / pqt) : 0.f;
+    acc[0] = acc[1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < RS; ++s) {
+      int64_t j = row0 + s * kGroups + gi;
+      bool act = (j < row1) && lane_on;
+      d[s] += alpha * p[s];
+      r[s] -= alpha * qv[s];
+      float zv = 0.f;
+#pragma unroll
+      for (int q = 0; q < 12; ++q) {
+        float rq = __shfl_sync(full, r[s], gbase + q);
+        if (RS == 1)
+          zv += minv[q] * rq;
+        else if (act)
+          zv += __ldg(a.Minv + j * 144 + k * 12 + q) * rq;
+      }
+      z[s] = zv;
+      if (act) zcur[j * 12 + k].x = zv;
+      acc[0] += (double)r[s] * (double)zv;
+      acc[1] += (double)r[s] * (double)r[s];
+    }
+    cta_partial<2>(acc, red, a.part + (size_t)blockIdx.x * 3 + 1);
+    grid.sync();
+    rz_old = rz;
+    {
+      double tot[2];
+      grid_totals<2>(a.part + 1, ncta, red, tot);
+      rz = tot[0];
+      rn2 = tot[1];
     }
   }
-  if (act) qv[row * 12 + k] = y;
-  double v[1] = {(double)pj * (double)y};
-  grid_reduce_sum<1>(v, smem, partials, ticket, scal + S_PQV);
+  // ---- x += delta
+#pragma unroll
+  for (int s = 0; s < RS; ++s) {
+    int64_t j = row0 + s * kGroups + gi;
+    if (j < row1 && lane_on) {
+      a.x[j * 12 + k] += d[s];
+      a.delta[j * 12 + k] = d[s];
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.scal[S_RZ] = rz;
+    a.scal[S_BNORM2] = bn2;
+    a.scal[S_RNORM2] = rn2;
+    a.scal[S_PQ] = (double)it;  // iterations actually run
+  }
 }
 
-__global__ void __launch_bounds__(kPcgThreads)
-    k_pcg_update(const float* __restrict__ Minv, int64_t m, int it, double tol,
-                 const float* __restrict__ p, const float* __restrict__ qv, float* __restrict__ r,
-                 float* __restrict__ z, float* __restrict__ delta, double* partials,
-                 unsigned* ticket, double* scal) {
-  __shared__ double smem[32 * 2];
-  const unsigned full = 0xffffffffu;
-  int lane = threadIdx.x & 31;
-  int k = lane & (kRowLanes - 1);
-  int gbase = lane & ~(kRowLanes - 1);
-  int64_t row = (int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x / kRowLanes);
-  bool act = row < m && k < 12;
-  double rz = scal[it & 1], pq = scal[S_PQV];
-  float alpha = (pq > 0.0 && rz > 0.0 && scal[S_DONE] == 0.0) ? (float)(rz / pq) : 0.f;
-  float rv = 0.f;
-  if (act) {
-    int64_t o = row * 12 + k;
-    delta[o] += alpha * p[o];
-    rv = r[o] - alpha * qv[o];
-    r[o] = rv;
-  }
-  float zv = 0.f;
-#pragma unroll
-  for (int q = 0; q < 12; ++q) {
-    float rq = __shfl_sync(full, rv, gbase + q);
-    if (act) zv += __ldg(Minv + row * 144 + k * 12 + q) * rq;
-  }
-  if (act) z[row * 12 + k] = zv;
-  double v[2] = {(double)rv * (double)zv, (double)rv * (double)rv};
-  if (grid_reduce_sum<2>(v, smem, partials, ticket, scal + 6)) {
-    if (threadIdx.x == 0) {
-      scal[(it + 1) & 1] = scal[6];
-      scal[S_RN2] = scal[7];
-      if (tol > 0.0 && scal[7] <= tol * tol * scal[S_BN2]) scal[S_DONE] = 1.0;
+template <int RS>
+static int launch_pcg(mvs_deform* h, PcgArgs& a, int grid, size_t smem) {
+  auto kern = k_pcg_persistent<RS>;
+  if (smem > 48 * 1024)
+    MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {&a};
+  MVS_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kPcgThreads), args, smem,
+                                       h->ctx->stream));
+  return MVS_OK;
+}
+
+template <int RS>
+static int max_coresident(size_t smem, int num_sms, int* out) {
+  auto kern = k_pcg_persistent<RS>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      *out = 0;
+      return MVS_OK;
     }
   }
+  int per_sm = 0;
+  MVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPcgThreads, smem));
+  *out = per_sm * num_sms;
+  return MVS_OK;
+}
+
+// Picks the row-slot count RS, the grid and whether the matrix slice fits in shared memory.
+static int plan_pcg(mvs_deform* h) {
+  if (h->pcg_plan_valid) return MVS_OK;
+  mvs_ctx* ctx = h->ctx;
+  int64_t m = h->m;
+  const int rs_opts[4] = {1, 2, 4, 8};
+  for (int stage = 1; stage >= 0; --stage) {
+    for (int oi = 0; oi < 4; ++oi) {
+      int RS = rs_opts[oi];
+      int rpc = RS * kGroups;
+      int grid = (int)((m + rpc - 1) / rpc);
+      size_t smem = 0;
+      if (stage) {
+        int worst = 0;
+        for (int64_t r0 = 0; r0 < m; r0 += rpc) {
+          int64_t r1 = std::min<int64_t>(m, r0 + rpc);
+          worst = std::max(worst, h->h_row_ptr[r1] - h->h_row_ptr[r0]);
+        }
+        smem = (size_t)worst * (64 + 4) + 16;
+        if (smem > 200 * 1024) continue;
+      }
+      int cap = 0;
+      switch (RS) {
+        case 1: MVS_TRY(max_coresident<1>(smem, ctx->num_sms, &cap)); break;
+        case 2: MVS_TRY(max_coresident<2>(smem, ctx->num_sms, &cap)); break;
+        case 4: MVS_TRY(max_coresident<4>(smem, ctx->num_sms, &cap)); break;
+        default: MVS_TRY(max_coresident<8>(smem, ctx->num_sms, &cap)); break;
+      }
+      if (grid <= cap) {
+        h->pcg_rs = RS;
+        h->pcg_grid = grid;
+        h->pcg_smem = smem;
+        h->pcg_stage = stage;
+        h->pcg_plan_valid = true;
+        return MVS_OK;
+      }
+    }
+  }
+  set_error("pcg: %lld nodes exceed the co-resident capacity of the persistent solver (max %d rows)",
+            (long long)m, 8 * kGroups * ctx->num_sms * 2);
+  return MVS_ERR_CAPACITY;
 }
 
 int pcg_solve(mvs_deform* h) {
   mvs_ctx* ctx = h->ctx;
-  cudaStream_t st = ctx->stream;
+  MVS_TRY(plan_pcg(h));
   int64_t m = h->m;
   size_t N = (size_t)m * 12;
-  float* r = h->pcg.p;
-  float* z = r + N;
-  float* p0 = z + N;
-  float* p1 = p0 + N;
-  float* q = p1 + N;
-  float* delta = q + N;
-  int grid = div_up(m, kRowsPerBlock);
-  MVS_TRY(h->partials.reserve((size_t)grid * 2 + 16));
-  {
-    ProfScope ps(ctx, "pcg_init");
-    k_pcg_init<<<grid, kPcgThreads, 0, st>>>(h->rhs(), h->Minv.p, m, r, z, p0, delta,
-                                             h->partials.p, h->ticket.p, h->scal.p);
-  }
-  int iters = h->prm.pcg_iters;
-  {
-    ProfScope ps(ctx, "pcg_iterations", 2 * (int64_t)iters);
-    for (int it = 0; it < iters; ++it) {
-      float* pprev = (it & 1) ? p1 : p0;
-      float* pcur = (it & 1) ? p0 : p1;
-      if (it == 0) pprev = p0, pcur = p1;
-      k_pcg_spmv<<<grid, kPcgThreads, 0, st>>>(h->row_ptr.p, h->col.p, h->B(), h->Rot(),
-                                               (float)h->prm.lambda, m, it, z, pprev, pcur, q,
-                                               h->partials.p, h->ticket.p, h->scal.p);
-      k_pcg_update<<<grid, kPcgThreads, 0, st>>>(h->Minv.p, m, it, h->prm.pcg_tol, pcur, q, r, z,
-                                                 delta, h->partials.p, h->ticket.p, h->scal.p);
-    }
+  PcgArgs a;
+  a.row_ptr = h->row_ptr.p;
+  a.col = h->col.p;
+  a.B = h->B();
+  a.Rot = h->Rot();
+  a.Minv = h->Minv.p;
+  a.rhs = h->rhs();
+  a.x = h->x.p;
+  a.zbuf = h->pcg.p;          // 2 x N float2 = 4N floats
+  a.pbuf = nullptr;
+  a.delta = h->pcg.p + 4 * N;
+  MVS_TRY(h->partials.reserve((size_t)h->pcg_grid * 3 + 16));
+  a.part = h->partials.p;
+  a.scal = h->scal.p;
+  a.m = m;
+  a.iters = h->prm.pcg_iters;
+  a.lambda = (float)h->prm.lambda;
+  a.tol = h->prm.pcg_tol;
+  a.rows_per_cta = h->pcg_rs * kGroups;
+  a.stage_smem = h->pcg_stage;
+  ProfScope ps(ctx, "pcg_solve");
+  switch (h->pcg_rs) {
+    case 1: MVS_TRY(launch_pcg<1>(h, a, h->pcg_grid, h->pcg_smem)); break;
+    case 2: MVS_TRY(launch_pcg<2>(h, a, h->pcg_grid, h->pcg_smem)); break;
+    case 4: MVS_TRY(launch_pcg<4>(h, a, h->pcg_grid, h->pcg_smem)); break;
+    default: MVS_TRY(launch_pcg<8>(h, a, h->pcg_grid, h->pcg_smem)); break;
   }
   MVS_CUDA(cudaGetLastError());
   return MVS_OK;

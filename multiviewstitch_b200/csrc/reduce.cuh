@@ -55,12 +55,21 @@ __device__ __forceinline__ bool grid_reduce_sum(double (&v)[N], double* smem, do
   __syncthreads();
   if (!is_last) return false;
   __threadfence();
-  if (threadIdx.x < N) {
-    double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partials + (size_t)b * N + threadIdx.x);
-    out[threadIdx.x] = s;
+  // every thread takes the partial rows b = t, t + blockDim, ... (independent loads, one memory
+  // latency) and the CTA adds them with the same fixed tree as above
+  double w[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) w[j] = 0.0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) w[j] += __ldcg(partials + (size_t)b * N + j);
   }
-  if (threadIdx.x == 0) *ticket = 0u;
+  block_reduce_sum<N>(w, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) out[j] = w[j];
+    *ticket = 0u;
+  }
   __threadfence();
   __syncthreads();
   return true;

@@ -425,6 +425,7 @@ int mvs_srt_create(mvs_ctx* ctx, mvs_srt** out) {
   if (!ctx) return MVS_ERR_NO_DEVICE;
   mvs_srt* h = new mvs_srt();
   h->ctx = ctx;
+  ctx_retain(ctx);
   *out = h;
   return MVS_OK;
 }
@@ -433,7 +434,9 @@ int mvs_srt_destroy(mvs_srt* h) {
   if (!h) return MVS_OK;
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
+  mvs_ctx* ctx = h->ctx;
   delete h;
+  ctx_release(ctx);
   return MVS_OK;
 }
 

@@ -187,3 +187,42 @@ def humanoid(n_per_part=400, seed=0, arm_angle=0.5, leg_angle=0.12, scale=1.0):
         add(hp + 0.90 * d + np.array([0, 0, 0.05]), [0.05, 0.04, 0.10], ft)
     pts = np.concatenate(P, 0) * scale
     return pts, np.concatenate(L, 0)
+
+
+def cube_sphere(n, radius=1.0, bumps=0.05, rot=None):
+    """Closed genus-0 triangle mesh with near-uniform vertex density: the 6 faces of a cube, each an
+    n x n quad grid (tangent-warped), projected onto the sphere, with the same low-frequency bumps as
+    uv_sphere.  6 n^2 + 2 vertices, 12 n^2 faces.  (A UV sphere packs ~1000x the mean density into
+    its poles, which no scanner or Poisson mesh does.)"""
+    t = np.tan(np.linspace(-np.pi / 4, np.pi / 4, n + 1))
+    U, V = np.meshgrid(t, t, indexing="ij")
+    one = np.ones_like(U)
+    faces_xyz = [(one, U, V), (-one, V, U), (V, one, U), (U, -one, V), (U, V, one), (V, U, -one)]
+    pts, quads = [], []
+    for k, (X, Y, Z) in enumerate(faces_xyz):
+        P = np.stack([X, Y, Z], -1).reshape(-1, 3)
+        pts.append(P / np.linalg.norm(P, axis=1, keepdims=True))
+        idx = (np.arange((n + 1) ** 2).reshape(n + 1, n + 1) + k * (n + 1) ** 2)
+        a, b, c, d = idx[:-1, :-1], idx[1:, :-1], idx[:-1, 1:], idx[1:, 1:]
+        quads.append(np.stack([np.stack([a, b, c], -1), np.stack([b, d, c], -1)], 2).reshape(-1, 3))
+    P = np.concatenate(pts, 0)
+    F = np.concatenate(quads, 0)
+    # weld the duplicated edge / corner vertices (exact grid positions: round to a fine lattice)
+    key = np.round(P * (1 << 20)).astype(np.int64)
+    _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    order = np.argsort(first)               # keep the original vertex order (face-major)
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    V3 = P[first[order]]
+    F = rank[inv.reshape(-1)][F]
+    # consistent outward orientation
+    c = V3[F].mean(1)
+    nrm = np.cross(V3[F[:, 1]] - V3[F[:, 0]], V3[F[:, 2]] - V3[F[:, 0]])
+    flip = np.sum(nrm * c, 1) < 0
+    F[flip] = F[flip][:, [0, 2, 1]]
+    if rot is not None:  # turn the tessellation, not the shape: the bumps are a function of position
+        V3 = V3 @ np.asarray(rot, np.float64).T
+    th = np.arccos(np.clip(V3[:, 2], -1, 1))
+    ph = np.arctan2(V3[:, 1], V3[:, 0])
+    r = radius * (1 + bumps * (np.sin(3 * th) * np.cos(2 * ph) + 0.5 * np.cos(5 * th + 1.0) * np.sin(3 * ph)))
+    return (V3 * r[:, None]).astype(np.float64), F.astype(np.int32)
