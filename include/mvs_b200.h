@@ -266,6 +266,9 @@ int mvs_deform_export_obj(mvs_deform* h, const char* filename);
  * (J^T r).  Any pointer may be NULL; *nnz receives the block count. */
 int mvs_deform_get_system(mvs_deform* h, int32_t* row_ptr, int32_t* col, float* blocks, float* rot,
                           float* rhs, int64_t* nnz);
+/* Sizes of the solver structures: stats[0..5] = vertices, nodes, pattern blocks (nnz), runs of
+ * equal node 4-tuples in the sorted vertex order, facets, target points. */
+int mvs_deform_get_stats(mvs_deform* h, int64_t stats[6]);
 
 /* ---------------------------------------------------------------- Model2Depth -------------- */
 /* [ref: Model2Depth/Model2Depth.h:17-54 SetInput/Run, Model2Depth.cpp:93-156] z-buffer render of a

@@ -475,6 +475,12 @@ class Deformation:
                                           _ptr(rhs, C.c_float), C.byref(nnz)))
         return rp, col, B, rot, rhs
 
+    def Stats(self) -> dict:
+        out = (C.c_int64 * 6)()
+        check(lib().mvs_deform_get_stats(self._h, out))
+        return dict(zip(("vertices", "nodes", "pattern_blocks", "tuple_runs", "facets",
+                         "target_points"), [int(v) for v in out]))
+
     def SetShard(self, v_begin: int, v_end: int):
         check(lib().mvs_deform_set_shard(self._h, C.c_int64(v_begin), C.c_int64(v_end)))
 

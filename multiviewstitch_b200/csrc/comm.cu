@@ -80,6 +80,14 @@ int comm_allreduce_sum_f64(mvs_ctx* ctx, double* buf_dev, size_t count) {
   return MVS_OK;
 }
 
+int comm_allreduce_sum_i64(mvs_ctx* ctx, long long* buf_dev, size_t count) {
+  if (!ctx->comm || ctx->nranks <= 1 || count == 0) return MVS_OK;
+  ctx->launch_count += 1;
+  MVS_NCCL(g_nccl.AllReduce(buf_dev, buf_dev, count, ncclInt64, ncclSum, (ncclComm_t)ctx->comm,
+                            ctx->stream));
+  return MVS_OK;
+}
+
 }  // namespace mvs
 
 using namespace mvs;

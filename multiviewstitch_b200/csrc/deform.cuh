@@ -4,7 +4,7 @@
 // deform_api.cu (C ABI).
 //
 // Data layout in HBM (all float32, 16-byte records, SoA across arrays):
-//   v[n], nrm[n]          float4  rest vertices / normals in SORTED order: vertices are permuted
+//   v[n], nrm[n]          float4  rest vertices (.w = tuple-run id) / normals in SORTED order: vertices are permuted
 //                                 once at graph-build time so that vertices sharing the same
 //                                 4-node set are adjacent (key = primary node | tuple hash);
 //                                 perm[i] = original vertex id of sorted position i
@@ -51,6 +51,17 @@ struct mvs_deform {
   int pcg_rs = 1, pcg_grid = 0, pcg_stage = 0;
   size_t pcg_smem = 0;
   mvs::DevBuf<float> sys;
+  // order-independent accumulation: J^T J / J^T r are summed as 64-bit fixed point (integer atomics
+  // commute exactly), then converted to the float32 system above; layout [B: nnz x 16 | rhs: m x 12]
+  mvs::DevBuf<long long> sys64;
+  double fx_scale = 1.0;   // power of two, set per solve from the magnitude bound
+  double diag2 = 1.0;      // squared bbox diagonal of the rest mesh
+  float omega_max = 1.0f;  // largest per-vertex constraint weight
+  // runs of equal node 4-tuples in the sorted vertex order: v[i].w = run id; per run the 16 pattern
+  // slots (j_a, j_b) and the 4 node ids, so the assembly never searches the block pattern
+  mvs::DevBuf<int> run_slots;  // nruns x 20
+  mvs::DevBuf<int> run_start;  // nruns + 1: first sorted vertex of each run
+  int64_t nruns = 0;
   mvs::DevBuf<float> Minv;  // m x 144
   mvs::DevBuf<float> x;     // m x 12
   mvs::DevBuf<float> pcg;   // r, z, p0, p1, q, delta : 6 x m x 12
@@ -83,6 +94,9 @@ struct mvs_deform {
   float* rhs() { return sys.p + (size_t)nnz * 16; }
   float* Rot() { return sys.p + (size_t)nnz * 16 + (size_t)m * 12; }
   size_t sys_floats() const { return (size_t)nnz * 16 + (size_t)m * 81 + (size_t)m * 12; }
+  size_t sys64_count() const { return (size_t)nnz * 16 + (size_t)m * 12; }
+  long long* B64() { return sys64.p; }
+  long long* rhs64() { return sys64.p + (size_t)nnz * 16; }
   int64_t shard_begin() const { return v_begin; }
   int64_t shard_end() const { return v_end < 0 ? n : v_end; }
 };

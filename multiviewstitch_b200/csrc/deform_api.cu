@@ -3,6 +3,7 @@
 // gn_assemble.cu and pcg.cu.
 #include <stdio.h>
 
+#include <algorithm>
 #include <cmath>
 
 #include "deform.cuh"
@@ -169,6 +170,7 @@ static int set_node_targets(mvs_deform* h, DevBuf<double>& controls, DevBuf<int>
   }
   MVS_CUDA(cudaGetLastError());
   h->have_targets = true;
+  h->omega_max = 1.0f;
   return MVS_OK;
 }
 
@@ -363,6 +365,16 @@ int mvs_deform_set_targets(mvs_deform* h, const double* targets, const float* we
   mvs_ctx* ctx = h->ctx;
   MVS_TRY(ctx_ensure_device(ctx));
   MVS_TRY(ensure_graph(h));
+  float wmax = 1.0f;
+  if (weights)
+    for (int64_t i = 0; i < n; ++i) {
+      if (!(weights[i] >= 0.f) || !std::isfinite(weights[i])) {
+        set_error("set_targets: weight %lld is negative or not finite", (long long)i);
+        return MVS_ERR_INVALID_ARG;
+      }
+      wmax = std::max(wmax, weights[i]);
+    }
+  h->omega_max = wmax;  // bounds the fixed-point accumulation of the assembly
   double* dt = nullptr;
   float* dw = nullptr;
   MVS_CUDA(cudaMallocAsync((void**)&dt, sizeof(double) * 3 * n, ctx->stream));
@@ -623,6 +635,17 @@ int mvs_deform_get_system(mvs_deform* h, int32_t* row_ptr, int32_t* col, float* 
   if (rhs)
     MVS_CUDA(cudaMemcpyAsync(rhs, h->rhs(), sizeof(float) * 12 * h->m, cudaMemcpyDeviceToHost, st));
   MVS_CUDA(cudaStreamSynchronize(st));
+  return MVS_OK;
+}
+
+int mvs_deform_get_stats(mvs_deform* h, int64_t stats[6]) {
+  MVS_REQUIRE(h && stats, "null argument");
+  stats[0] = h->n;
+  stats[1] = h->m;
+  stats[2] = h->graph_built ? h->nnz : 0;
+  stats[3] = h->graph_built ? h->nruns : 0;
+  stats[4] = h->nf;
+  stats[5] = h->nt;
   return MVS_OK;
 }
 

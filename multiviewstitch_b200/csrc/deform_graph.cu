@@ -13,6 +13,9 @@
 
 namespace mvs {
 
+int bbox_host(mvs_ctx* ctx, const float4* pts, int64_t n, DevBuf<float>& red, float mn[3],
+              float mx[3]);
+
 // ------------------------------------------------------------------ small gathers
 __global__ void k_gather_f4(const float4* __restrict__ src, const int* __restrict__ ids, int64_t m,
                             float4* __restrict__ dst) {
@@ -275,6 +278,56 @@ __global__ void k_pattern_gather(const int* __restrict__ tab, int cap, int64_t m
   for (int t = threadIdx.x; t < e - s; t += blockDim.x) col[s + t] = tab[(size_t)j * cap + t];
 }
 
+// ------------------------------------------------------------------ tuple runs
+__global__ void k_run_heads(const int4* __restrict__ vidx, int64_t n, int* __restrict__ flag) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int h = 1;
+  if (i > 0) {
+    int4 a = vidx[i], b = vidx[i - 1];
+    h = (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) ? 1 : 0;
+  }
+  flag[i] = h;
+}
+
+__device__ __forceinline__ int find_slot_dev(const int* __restrict__ row_ptr,
+                                             const int* __restrict__ col, int j, int l) {
+  int lo = row_ptr[j], hi = row_ptr[j + 1] - 1;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (col[mid] < l) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// scan[i] = run id of vertex i's run when i is a head; every vertex records its run id in v.w,
+// heads fill the run's slot table (16 pattern slots (a,b) row-major, then the 4 node ids)
+__global__ void k_run_table(const int4* __restrict__ vidx, const int* __restrict__ flag_scan,
+                            int64_t n, const int* __restrict__ row_ptr,
+                            const int* __restrict__ col, float4* __restrict__ v,
+                            int* __restrict__ run_slots, int* __restrict__ run_start) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 id = vidx[i];
+  bool head = true;
+  if (i > 0) {
+    int4 b = vidx[i - 1];
+    head = id.x != b.x || id.y != b.y || id.z != b.z || id.w != b.w;
+  }
+  // exclusive scan of the head flags: a head's value is its run id, a non-head's is run id + 1
+  int run = flag_scan[i] - (head ? 0 : 1);
+  v[i].w = __int_as_float(run);
+  if (!head) return;
+  run_start[run] = (int)i;
+  int js[4] = {id.x, id.y, id.z, id.w};
+  int* out = run_slots + (size_t)run * 20;
+  for (int a = 0; a < 4; ++a) {
+    for (int b = 0; b < 4; ++b)
+      out[4 * a + b] = (js[a] >= 0 && js[b] >= 0) ? find_slot_dev(row_ptr, col, js[a], js[b]) : -1;
+    out[16 + a] = js[a];
+  }
+}
+
 // ------------------------------------------------------------------ build_graph
 int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
   mvs_ctx* ctx = h->ctx;
@@ -389,8 +442,39 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
     k_pattern_gather<<<(unsigned)m, 64, 0, st>>>(tab.p, cap, m, h->row_ptr.p, h->col.p);
   }
   MVS_CUDA(cudaGetLastError());
-  // 5. solver buffers
+  // 5. runs of equal node tuples + their slot tables
+  {
+    DevBuf<int> rflag;
+    MVS_TRY(rflag.reserve((size_t)n + 2));
+    {
+      ProfScope ps(ctx, "run_heads");
+      k_run_heads<<<div_up(n, 256), 256, 0, st>>>(h->vidx.p, n, rflag.p);
+    }
+    MVS_CUDA(cudaMemsetAsync(rflag.p + n, 0, sizeof(int) * 2, st));
+    MVS_TRY(exclusive_scan_inplace(ctx, rflag.p, n, h->node_index->scan_tmp));
+    int nruns = 0;
+    MVS_TRY(d2h_sync(ctx, &nruns, rflag.p + n, sizeof(int)));
+    h->nruns = nruns;
+    MVS_TRY(h->run_slots.reserve((size_t)nruns * 20));
+    MVS_TRY(h->run_start.reserve((size_t)nruns + 1));
+    {
+      ProfScope ps(ctx, "run_table");
+      k_run_table<<<div_up(n, 256), 256, 0, st>>>(h->vidx.p, rflag.p, n, h->row_ptr.p, h->col.p,
+                                                  h->v.p, h->run_slots.p, h->run_start.p);
+    }
+    int n32 = (int)n;
+    MVS_CUDA(cudaMemcpyAsync(h->run_start.p + nruns, &n32, sizeof(int), cudaMemcpyHostToDevice, st));
+    MVS_CUDA(cudaGetLastError());
+    MVS_CUDA(cudaStreamSynchronize(st));
+    float mn[3], mx[3];
+    MVS_TRY(bbox_host(ctx, h->v0.p, n, h->node_index->red, mn, mx));
+    double d2 = 0;
+    for (int a = 0; a < 3; ++a) d2 += ((double)mx[a] - mn[a]) * ((double)mx[a] - mn[a]);
+    h->diag2 = d2 > 0 ? d2 : 1.0;
+  }
+  // 6. solver buffers
   MVS_TRY(h->sys.reserve(h->sys_floats()));
+  MVS_TRY(h->sys64.reserve(h->sys64_count()));
   MVS_TRY(h->Minv.reserve((size_t)m * 144));
   MVS_TRY(h->x.reserve((size_t)m * 12));
   MVS_TRY(h->pcg.reserve((size_t)m * 12 * 6));

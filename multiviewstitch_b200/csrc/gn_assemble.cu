@@ -13,6 +13,8 @@
 //                   flushes one vector atomic per tile row.                  64 B/vertex in
 //   k_node_terms    rotation (dense 9x9 per node) and smoothness (graph edges) terms
 //   k_precond       12x12 block-Jacobi preconditioner: Cholesky inverse of each diagonal block
+#include <stdlib.h>
+
 #include <cmath>
 
 #include "comm.cuh"
@@ -176,6 +178,7 @@ int gn_deform_and_correspond(mvs_deform* h) {
 // ------------------------------------------------------------------ fit assembly
 constexpr int kAsmWarps = 4;
 constexpr int kRecStride = 20;
+constexpr int kOutTiles = 20;  // 16 block tiles (a,b) row-major + 4 rhs tiles
 
 __device__ __forceinline__ int find_slot(const int* __restrict__ row_ptr,
                                          const int* __restrict__ col, int j, int l) {
@@ -187,24 +190,33 @@ __device__ __forceinline__ int find_slot(const int* __restrict__ row_ptr,
   return lo;
 }
 
-__device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float c, float d) {
-  // one 16-byte vector reduction (sm_90+): red.global.add.v4.f32
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
-               "f"(d)
-               : "memory");
+// order-independent accumulation: value * 2^k rounded to int64, summed with integer atomics
+__device__ __forceinline__ void fx_add(long long* addr, float v, float scale) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(addr),
+            (unsigned long long)__float2ll_rn(v * scale));
 }
 
-__global__ void __launch_bounds__(kAsmWarps * 32)
+// One warp takes one tuple run (consecutive sorted vertices that share their four nodes, avg ~22
+// at C3) at a time, 32 vertices per pass: per-vertex records (b_a = sqrt(w_fit omega) w_a (d_a, 1),
+// a = 0..3, and the scaled residual) are staged in shared memory, 14 tile lanes x 2 half-warps
+// accumulate the 10 distinct 4x4 products b_a b_b^T and the 4 gradient tiles b_a r^T in registers
+// over the whole run, then the result tiles are laid out in shared memory in the order of the
+// run's precomputed slot table and flushed once by the whole warp — 16 consecutive lanes hit 16
+// consecutive int64 — as fixed-point atomics.  No pattern search, one flush per run.
+__global__ void __launch_bounds__(kAsmWarps * 32, 8)
     k_assemble_fit(const float4* __restrict__ v, const int4* __restrict__ vidx,
                    const float4* __restrict__ vw, const float4* __restrict__ resid,
-                   const float4* __restrict__ g, const int* __restrict__ row_ptr,
-                   const int* __restrict__ col, float* __restrict__ B, float* __restrict__ rhs,
-                   int64_t begin, int64_t end, float w_fit) {
+                   const float4* __restrict__ g, const int* __restrict__ run_slots,
+                   const int* __restrict__ run_start, long long* __restrict__ B64,
+                   long long* __restrict__ rhs64, int64_t begin, int64_t end, float w_fit,
+                   float fx_scale) {
   __shared__ __align__(16) float rec[kAsmWarps][32][kRecStride];
+  __shared__ __align__(16) float outt[kAsmWarps][kOutTiles][16];
+  __shared__ int slots[kAsmWarps][kOutTiles];
   const unsigned full = 0xffffffffu;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int64_t nwarps = (int64_t)gridDim.x * kAsmWarps;
-  int64_t wg = (int64_t)blockIdx.x * kAsmWarps + warp;
+  int nwarps = gridDim.x * kAsmWarps;
+  int wg = blockIdx.x * kAsmWarps + warp;
   // tile table: 10 (a,b) block tiles (a<=b) then 4 rhs tiles
   int half = lane >> 4, t = lane & 15;
   int ta, tb;
@@ -221,104 +233,121 @@ __global__ void __launch_bounds__(kAsmWarps * 32)
     case 9: ta = 2; tb = 3; break;
     default: ta = (t - 10) & 3; tb = 4; break;  // rhs tiles read the residual slot (cols 16..19)
   }
-  for (int64_t base = begin + wg * 32; base < end; base += nwarps * 32) {
-    int64_t i = base + lane;
-    bool in = i < end;
-    int4 id = make_int4(-1, -1, -1, -1);
-    float s = 0.f;
-    float r0[kRecStride];
+  // runs that intersect this rank's vertex range
+  const int run_lo = __float_as_int(__ldg(&v[begin].w));
+  const int run_hi = __float_as_int(__ldg(&v[end - 1].w));
+  for (int run = run_lo + wg; run <= run_hi; run += nwarps) {
+    int64_t rs0 = max((int64_t)__ldg(run_start + run), begin);
+    int64_t rs1 = min((int64_t)__ldg(run_start + run + 1), end);
+    if (lane < kOutTiles) slots[warp][lane] = __ldg(run_slots + (size_t)run * 20 + lane);
+    float acc[16];
 #pragma unroll
-    for (int k = 0; k < kRecStride; ++k) r0[k] = 0.f;
-    if (in) {
-      float4 rs = __ldg(resid + i);
-      if (rs.w > 0.f) {
-        s = sqrtf(w_fit * rs.w);
-        float4 vi = __ldg(v + i);
-        float4 w = __ldg(vw + i);
-        id = __ldg(vidx + i);
-        int ids[4] = {id.x, id.y, id.z, id.w};
-        float ws[4] = {w.x, w.y, w.z, w.w};
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    for (int64_t base = rs0; base < rs1; base += 32) {
+      int64_t i = base + lane;
+      float r0[kRecStride];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          if (ids[a] >= 0) {
-            float4 gj = __ldg(g + ids[a]);
-            float sw = s * ws[a];
-            r0[4 * a + 0] = sw * (vi.x - gj.x);
-            r0[4 * a + 1] = sw * (vi.y - gj.y);
-            r0[4 * a + 2] = sw * (vi.z - gj.z);
-            r0[4 * a + 3] = sw;
+      for (int k = 0; k < kRecStride; ++k) r0[k] = 0.f;
+      if (i < rs1) {
+        float4 rs = __ldg(resid + i);
+        if (rs.w > 0.f) {
+          float s = sqrtf(w_fit * rs.w);
+          float4 vi = __ldg(v + i);
+          float4 w = __ldg(vw + i);
+          int4 id = __ldg(vidx + i);
+          int ids[4] = {id.x, id.y, id.z, id.w};
+          float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            if (ids[a] >= 0) {
+              float4 gj = __ldg(g + ids[a]);
+              float sw = s * ws[a];
+              r0[4 * a + 0] = sw * (vi.x - gj.x);
+              r0[4 * a + 1] = sw * (vi.y - gj.y);
+              r0[4 * a + 2] = sw * (vi.z - gj.z);
+              r0[4 * a + 3] = sw;
+            }
           }
+          r0[16] = s * rs.x;
+          r0[17] = s * rs.y;
+          r0[18] = s * rs.z;
         }
-        r0[16] = s * rs.x;
-        r0[17] = s * rs.y;
-        r0[18] = s * rs.z;
       }
-    }
-    unsigned long long k0 = ((unsigned long long)(unsigned)id.x << 32) | (unsigned)id.y;
-    unsigned long long k1 = ((unsigned long long)(unsigned)id.z << 32) | (unsigned)id.w;
-    unsigned act = __ballot_sync(full, s > 0.f);
-    unsigned grp = __match_any_sync(full, k0) & __match_any_sync(full, k1) & act;
-    unsigned remaining = act;
-    while (remaining) {
-      int leader = __ffs(remaining) - 1;
-      unsigned gmask = __shfl_sync(full, grp, leader);
-      int cnt = __popc(gmask);
-      if ((gmask >> lane) & 1u) {
-        int rank = __popc(gmask & ((1u << lane) - 1u));
-        float4* dst = reinterpret_cast<float4*>(&rec[warp][rank][0]);
+      __syncwarp();  // the previous pass has been consumed
+      {
+        float4* dst = reinterpret_cast<float4*>(&rec[warp][lane][0]);
 #pragma unroll
         for (int k = 0; k < 5; ++k)
           dst[k] = make_float4(r0[4 * k], r0[4 * k + 1], r0[4 * k + 2], r0[4 * k + 3]);
       }
       __syncwarp();
-      int j0 = __shfl_sync(full, id.x, leader), j1 = __shfl_sync(full, id.y, leader);
-      int j2 = __shfl_sync(full, id.z, leader), j3 = __shfl_sync(full, id.w, leader);
-      float acc[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+      int cnt = (int)min((int64_t)32, rs1 - base);
       if (t < 14) {
-        for (int mi = half; mi < cnt; mi += 2) {
-          const float4 ba = *reinterpret_cast<const float4*>(&rec[warp][mi][4 * ta]);
-          const float4 bb = *reinterpret_cast<const float4*>(&rec[warp][mi][4 * tb]);
-          acc[0] += ba.x * bb.x; acc[1] += ba.x * bb.y; acc[2] += ba.x * bb.z; acc[3] += ba.x * bb.w;
-          acc[4] += ba.y * bb.x; acc[5] += ba.y * bb.y; acc[6] += ba.y * bb.z; acc[7] += ba.y * bb.w;
-          acc[8] += ba.z * bb.x; acc[9] += ba.z * bb.y; acc[10] += ba.z * bb.z; acc[11] += ba.z * bb.w;
-          acc[12] += ba.w * bb.x; acc[13] += ba.w * bb.y; acc[14] += ba.w * bb.z; acc[15] += ba.w * bb.w;
+        // members mi = half, half + 2, ...; records past cnt are zero (whole pass is rewritten every
+        // time), so the loop runs in steps of two members without a tail
+        int cnt4 = (cnt + 3) & ~3;
+        for (int mi = half; mi < cnt4; mi += 4) {
+          const float4 ba0 = *reinterpret_cast<const float4*>(&rec[warp][mi][4 * ta]);
+          const float4 bb0 = *reinterpret_cast<const float4*>(&rec[warp][mi][4 * tb]);
+          const float4 ba1 = *reinterpret_cast<const float4*>(&rec[warp][mi + 2][4 * ta]);
+          const float4 bb1 = *reinterpret_cast<const float4*>(&rec[warp][mi + 2][4 * tb]);
+          acc[0] += ba0.x * bb0.x; acc[1] += ba0.x * bb0.y; acc[2] += ba0.x * bb0.z; acc[3] += ba0.x * bb0.w;
+          acc[4] += ba0.y * bb0.x; acc[5] += ba0.y * bb0.y; acc[6] += ba0.y * bb0.z; acc[7] += ba0.y * bb0.w;
+          acc[8] += ba0.z * bb0.x; acc[9] += ba0.z * bb0.y; acc[10] += ba0.z * bb0.z; acc[11] += ba0.z * bb0.w;
+          acc[12] += ba0.w * bb0.x; acc[13] += ba0.w * bb0.y; acc[14] += ba0.w * bb0.z; acc[15] += ba0.w * bb0.w;
+          acc[0] += ba1.x * bb1.x; acc[1] += ba1.x * bb1.y; acc[2] += ba1.x * bb1.z; acc[3] += ba1.x * bb1.w;
+          acc[4] += ba1.y * bb1.x; acc[5] += ba1.y * bb1.y; acc[6] += ba1.y * bb1.z; acc[7] += ba1.y * bb1.w;
+          acc[8] += ba1.z * bb1.x; acc[9] += ba1.z * bb1.y; acc[10] += ba1.z * bb1.z; acc[11] += ba1.z * bb1.w;
+          acc[12] += ba1.w * bb1.x; acc[13] += ba1.w * bb1.y; acc[14] += ba1.w * bb1.z; acc[15] += ba1.w * bb1.w;
         }
       }
-#pragma unroll
-      for (int k = 0; k < 16; ++k) acc[k] += __shfl_xor_sync(full, acc[k], 16);
-      if (half == 0 && t < 14) {
-        int js[4] = {j0, j1, j2, j3};
-        int ja = js[ta];
-        if (t < 10) {
-          int jb = js[tb];
-          if (ja >= 0 && jb >= 0) {
-            float* dst = B + (size_t)find_slot(row_ptr, col, ja, jb) * 16;
-            red_add_f4(dst, acc[0], acc[1], acc[2], acc[3]);
-            red_add_f4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
-            red_add_f4(dst + 8, acc[8], acc[9], acc[10], acc[11]);
-            red_add_f4(dst + 12, acc[12], acc[13], acc[14], acc[15]);
-            if (ta != tb) {
-              float* d2 = B + (size_t)find_slot(row_ptr, col, jb, ja) * 16;
-              red_add_f4(d2, acc[0], acc[4], acc[8], acc[12]);
-              red_add_f4(d2 + 4, acc[1], acc[5], acc[9], acc[13]);
-              red_add_f4(d2 + 8, acc[2], acc[6], acc[10], acc[14]);
-              red_add_f4(d2 + 12, acc[3], acc[7], acc[11], acc[15]);
-            }
-          }
-        } else if (ja >= 0) {
-          // rhs_j[3c + r] += sum b_a[c] * r[r]   (acc[4c + r], r < 3)
-          float* dst = rhs + (size_t)ja * 12;
-          red_add_f4(dst, acc[0], acc[1], acc[2], acc[4]);
-          red_add_f4(dst + 4, acc[5], acc[6], acc[8], acc[9]);
-          red_add_f4(dst + 8, acc[10], acc[12], acc[13], acc[14]);
-        }
-      }
-      remaining &= ~gmask;
-      __syncwarp();
     }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] += __shfl_xor_sync(full, acc[k], 16);
+    if (half == 0 && t < 14) {
+      if (t < 10) {
+        float4* o = reinterpret_cast<float4*>(&outt[warp][4 * ta + tb][0]);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        o[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+        o[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
+        if (ta != tb) {  // the transposed block (j_b, j_a)
+          float4* o2 = reinterpret_cast<float4*>(&outt[warp][4 * tb + ta][0]);
+          o2[0] = make_float4(acc[0], acc[4], acc[8], acc[12]);
+          o2[1] = make_float4(acc[1], acc[5], acc[9], acc[13]);
+          o2[2] = make_float4(acc[2], acc[6], acc[10], acc[14]);
+          o2[3] = make_float4(acc[3], acc[7], acc[11], acc[15]);
+        }
+      } else {
+        // rhs_j[3c + r] = sum b_a[c] * r[r]   (acc[4c + r], r < 3)
+        float* o = &outt[warp][16 + ta][0];
+        o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[4];
+        o[4] = acc[5]; o[5] = acc[6]; o[6] = acc[8]; o[7] = acc[9];
+        o[8] = acc[10]; o[9] = acc[12]; o[10] = acc[13]; o[11] = acc[14];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = lane; k < kOutTiles * 16; k += 32) {
+      int tile = k >> 4, e = k & 15;
+      int sl = slots[warp][tile];
+      if (sl < 0) continue;
+      float val = outt[warp][tile][e];
+      if (tile < 16)
+        fx_add(B64 + (size_t)sl * 16 + e, val, fx_scale);
+      else if (e < 12)
+        fx_add(rhs64 + (size_t)sl * 12 + e, val, fx_scale);
+    }
+    __syncwarp();
   }
+}
+
+// fixed point -> float32 system
+__global__ void k_sys_convert(const long long* __restrict__ in, float* __restrict__ out, int64_t n,
+                              float inv_scale) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (float)((double)in[i] * (double)inv_scale);
 }
 
 // ------------------------------------------------------------------ node terms
@@ -332,8 +361,8 @@ __global__ void __launch_bounds__(128)
     k_node_terms(const float4* __restrict__ g, const float* __restrict__ x,
                  const int* __restrict__ graph, int gk1, int64_t m,
                  const int* __restrict__ row_ptr, const int* __restrict__ col,
-                 float* __restrict__ B, float* __restrict__ Rot, float* __restrict__ rhs,
-                 float w_rot, float w_reg) {
+                 long long* __restrict__ B, float* __restrict__ Rot, long long* __restrict__ rhs,
+                 float w_rot, float w_reg, float fxs) {
   const unsigned full = 0xffffffffu;
   int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kNodeLanes;
   int k = threadIdx.x & (kNodeLanes - 1);
@@ -408,15 +437,17 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) gl[3 * c + rr] += w_reg * a[c] * r[rr];
       }
-      float* Bjl = B + (size_t)find_slot(row_ptr, col, (int)j, l) * 16;
-      float* Blj = B + (size_t)find_slot(row_ptr, col, l, (int)j) * 16;
-      float* Bll = B + (size_t)find_slot(row_ptr, col, l, l) * 16;
+      long long* Bjl = B + (size_t)find_slot(row_ptr, col, (int)j, l) * 16;
+      long long* Blj = B + (size_t)find_slot(row_ptr, col, l, (int)j) * 16;
+      long long* Bll = B + (size_t)find_slot(row_ptr, col, l, l) * 16;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) atomicAdd(Bjl + 4 * c + 3, -w_reg * a[c]);
-      red_add_f4(Blj + 12, -w_reg * a[0], -w_reg * a[1], -w_reg * a[2], -w_reg * a[3]);
-      atomicAdd(Bll + 15, w_reg);
+      for (int c = 0; c < 4; ++c) {
+        fx_add(Bjl + 4 * c + 3, -w_reg * a[c], fxs);
+        fx_add(Blj + 12 + c, -w_reg * a[c], fxs);
+      }
+      fx_add(Bll + 15, w_reg, fxs);
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) atomicAdd(rhs + (size_t)l * 12 + 9 + rr, -w_reg * r[rr]);
+      for (int rr = 0; rr < 3; ++rr) fx_add(rhs + (size_t)l * 12 + 9 + rr, -w_reg * r[rr], fxs);
     }
   }
   // reduce the node's own contributions over its 16 lanes
@@ -428,7 +459,7 @@ __global__ void __launch_bounds__(128)
     for (int p = 0; p < 12; ++p) gl[p] += __shfl_xor_sync(full, gl[p], o);
   }
   if (on && k < 4) {
-    float* Bd = B + (size_t)find_slot(row_ptr, col, (int)j, (int)j) * 16;
+    long long* Bd = B + (size_t)find_slot(row_ptr, col, (int)j, (int)j) * 16;
     // lane k flushes row k of the 4x4 factor and 3 gradient entries
     float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll
@@ -437,10 +468,13 @@ __global__ void __launch_bounds__(128)
         b0 = Bjj[4 * c]; b1 = Bjj[4 * c + 1]; b2 = Bjj[4 * c + 2]; b3 = Bjj[4 * c + 3];
         g0 = gl[3 * c]; g1 = gl[3 * c + 1]; g2 = gl[3 * c + 2];
       }
-    red_add_f4(Bd + 4 * k, b0, b1, b2, b3);
-    atomicAdd(rhs + (size_t)j * 12 + 3 * k, g0);
-    atomicAdd(rhs + (size_t)j * 12 + 3 * k + 1, g1);
-    atomicAdd(rhs + (size_t)j * 12 + 3 * k + 2, g2);
+    fx_add(Bd + 4 * k, b0, fxs);
+    fx_add(Bd + 4 * k + 1, b1, fxs);
+    fx_add(Bd + 4 * k + 2, b2, fxs);
+    fx_add(Bd + 4 * k + 3, b3, fxs);
+    fx_add(rhs + (size_t)j * 12 + 3 * k, g0, fxs);
+    fx_add(rhs + (size_t)j * 12 + 3 * k + 1, g1, fxs);
+    fx_add(rhs + (size_t)j * 12 + 3 * k + 2, g2, fxs);
   }
 }
 
@@ -513,29 +547,40 @@ __global__ void __launch_bounds__(128)
 int gn_assemble(mvs_deform* h) {
   mvs_ctx* ctx = h->ctx;
   cudaStream_t st = ctx->stream;
-  MVS_CUDA(cudaMemsetAsync(h->sys.p, 0, sizeof(float) * h->sys_floats(), st));
+  // fixed-point scale: the largest power of two that cannot overflow int64 for this problem
+  // (every entry is bounded by w_fit omega_max n max(1, D^2) plus the node terms)
+  double bound = 4.0 * (h->prm.w_fit * (double)h->omega_max * (double)h->n * std::max(1.0, h->diag2) +
+                        h->prm.w_reg * 64.0 * std::max(1.0, h->diag2) + h->prm.w_rot * 64.0 + 1.0);
+  int ex = 0;
+  frexp(bound, &ex);  // bound < 2^ex
+  h->fx_scale = ldexp(1.0, std::max(0, std::min(40, 62 - ex)));
+  float fxs = (float)h->fx_scale;
+  MVS_CUDA(cudaMemsetAsync(h->sys64.p, 0, sizeof(long long) * h->sys64_count(), st));
   int64_t b = h->shard_begin(), e = h->shard_end();
   if (e > b) {
     ProfScope ps(ctx, "gn_assemble_fit");
-    int64_t warps_needed = (e - b + 31) / 32;
+    int64_t warps_needed = std::min<int64_t>(h->nruns, (e - b + 7) / 8);
     int grid = (int)std::min<int64_t>((warps_needed + kAsmWarps - 1) / kAsmWarps,
-                                      (int64_t)ctx->num_sms * 8);
+                                      (int64_t)ctx->num_sms * 12);
     k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(h->v.p, h->vidx.p, h->vw.p, h->resid.p, h->g.p,
-                                                    h->row_ptr.p, h->col.p, h->B(), h->rhs(), b, e,
-                                                    (float)h->prm.w_fit);
+                                                    h->run_slots.p, h->run_start.p, h->B64(),
+                                                    h->rhs64(), b, e, (float)h->prm.w_fit, fxs);
   }
   MVS_CUDA(cudaGetLastError());
   if (ctx->comm && ctx->nranks > 1) {
-    // vertex-sharded solve: sum the partial J^T J blocks and J^T r over ranks (NVLink/NVSwitch)
+    // vertex-sharded solve: sum the partial J^T J blocks and J^T r over ranks (NVLink/NVSwitch);
+    // integer sums make the result independent of the reduction order NCCL picks
     ProfScope ps(ctx, "gn_allreduce", 0);
-    MVS_TRY(comm_allreduce_sum_f32(ctx, h->sys.p, h->sys_floats()));
+    MVS_TRY(comm_allreduce_sum_i64(ctx, h->sys64.p, h->sys64_count()));
   }
   {
-    ProfScope ps(ctx, "gn_node_terms");
-    k_node_terms<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m,
-                                                  h->row_ptr.p, h->col.p, h->B(), h->Rot(),
-                                                  h->rhs(), (float)h->prm.w_rot,
-                                                  (float)h->prm.w_reg);
+    ProfScope ps(ctx, "gn_node_terms", 2);
+    k_node_terms<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(
+        h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m, h->row_ptr.p, h->col.p, h->B64(),
+        h->Rot(), h->rhs64(), (float)h->prm.w_rot, (float)h->prm.w_reg, fxs);
+    // sys = [B | rhs | Rot]: B and rhs are contiguous in both buffers
+    k_sys_convert<<<grid_for(ctx, (int64_t)h->sys64_count(), 256, 4), 256, 0, st>>>(
+        h->sys64.p, h->sys.p, (int64_t)h->sys64_count(), (float)(1.0 / h->fx_scale));
   }
   {
     ProfScope ps(ctx, "gn_precond");
@@ -562,12 +607,13 @@ int gn_apply_update(mvs_deform* h) {
 // ------------------------------------------------------------------ final vertices + normals
 __global__ void k_deform_final(const float4* __restrict__ v, const int4* __restrict__ vidx,
                                const float4* __restrict__ vw, const float4* __restrict__ g,
-                               const float* __restrict__ x, int64_t n, float4* __restrict__ cur0) {
+                               const float* __restrict__ x, const int* __restrict__ perm,
+                               int64_t n, float4* __restrict__ cur0) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 vi = __ldg(v + i);
   float3 q = deform_point(vi, __ldg(vidx + i), __ldg(vw + i), g, x);
-  cur0[__float_as_int(vi.w)] = make_float4(q.x, q.y, q.z, 0.f);
+  cur0[__ldg(perm + i)] = make_float4(q.x, q.y, q.z, 0.f);
 }
 
 // Deformation/Deformation.h:111-128 FacetNormal + :86-109 VertexNormal
@@ -607,8 +653,8 @@ int gn_final_vertices(mvs_deform* h) {
   int64_t n = h->n;
   {
     ProfScope ps(ctx, "deform_final");
-    k_deform_final<<<div_up(n, 256), 256, 0, st>>>(h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, n,
-                                                   h->cur0.p);
+    k_deform_final<<<div_up(n, 256), 256, 0, st>>>(h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p,
+                                                   h->perm.p, n, h->cur0.p);
   }
   MVS_CUDA(cudaMemsetAsync(h->curn0.p, 0, sizeof(float4) * n, st));
   if (h->nf > 0) {

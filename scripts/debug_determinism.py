@@ -14,10 +14,10 @@ d = api.Deformation(pts, None, None, ctx)
 d.SampleFPS(m, 0)
 d.BuildGraph(4, 8)
 d.SetTarget(tgt)
-for mode, iters in ((1, 10),):
+for mode, iters in ((1, 10), (2, 10)):
     outs, states = [], []
     if mode == 2:
-        d.SetTargets(tgt.astype(np.float64))
+        d.SetTargets(synth.bend_twist(verts, 0.05))
     for rep in range(3):
         d.GNBegin(api.gn_params(gn_iters=iters, pcg_iters=20, corr_mode=mode))
         st = []

@@ -13,6 +13,7 @@ d = api.Deformation(pts, None, None, ctx)
 d.SampleFPS(m, 0)
 d.BuildGraph(4, 8)
 d.SetTarget(tgt)
+print(d.Stats())
 prm = api.gn_params(gn_iters=10, pcg_iters=20, corr_mode=1)
 for rep in range(3):
     d.GNBegin(prm)
