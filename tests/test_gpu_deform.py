@@ -301,3 +301,67 @@ def test_export_obj_format(ctx, tmp_path):
     assert len(fl) == len(faces)
     a = faces[0] + 1
     assert fl[0] == f"f {a[0]}//{a[0]} {a[1]}//{a[1]} {a[2]}//{a[2]}"
+
+
+@pytest.mark.parametrize("m", [6000, 12000])
+def test_many_nodes_multi_slot_pcg_parity(ctx, m):
+    """More node rows than one co-resident wave of 16-lane row groups (148 SMs x 2 CTAs x 16):
+    the persistent PCG kernel runs 2 (m = 6000) / 4 (m = 12000) row slots per lane group."""
+    verts, faces = synth.cube_sphere(64)  # 24,578 vertices
+    pts = verts.astype(np.float32)
+    d = api.Deformation(pts, None, faces, ctx)
+    ids = d.SampleFPS(m, 0)
+    nodes, widx, w, graph = oracle_graph(pts, ids)
+    targets = synth.bend_twist(verts, 0.03)
+    d.SetTargets(targets)
+    d.GNBegin(api.gn_params(gn_iters=3, pcg_iters=15, corr_mode=2))
+    for _ in range(3):
+        d.GNStep()
+    d.GNEnd()
+    xo, oo, eo = oracle.gn_solve(pts, None, ids, widx, w, graph,
+                                 oracle.gn_params(gn_iters=3, pcg_iters=15), targets=targets)
+    err = np.abs(d.Vertices() - oo).max()
+    assert err <= POS_TOL * diag(pts), err
+    assert d.Stats()["nodes"] == m
+
+
+def test_solve_is_bitwise_reproducible(ctx):
+    # fixed-point assembly + fixed-order PCG reductions: two runs give identical bits
+    verts, faces = synth.cube_sphere(48)
+    pts = verts.astype(np.float32)
+    tv = synth.bend_twist(synth.cube_sphere(53, rot=synth.axis_angle([1, 2, 3], 0.7))[0], 0.04).astype(np.float32)
+    outs = []
+    for rep in range(2):
+        d = api.Deformation(pts, None, faces, ctx)
+        d.SampleFPS(300, 0)
+        d.SetTarget(tv)
+        d.GNBegin(api.gn_params(gn_iters=5, pcg_iters=20, corr_mode=1))
+        for _ in range(5):
+            d.GNStep()
+        d.GNEnd()
+        outs.append((d.Vertices(), d.NodeState()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_weighted_targets_and_large_coordinates(ctx):
+    # per-vertex weights != 1 and millimetre-scale coordinates exercise the fixed-point scale choice
+    verts, faces = synth.uv_sphere(48, 36)
+    pts = (verts * 1000.0 + np.array([5000.0, -2000.0, 300.0])).astype(np.float32)
+    rng = np.random.default_rng(9)
+    tw = rng.uniform(0.0, 7.5, len(pts)).astype(np.float32)
+    tw[rng.random(len(pts)) < 0.2] = 0.0
+    targets = synth.bend_twist(pts.astype(np.float64) - pts.mean(0), 0.04) + pts.mean(0)
+    d = api.Deformation(pts, None, faces, ctx)
+    ids = d.SampleFPS(80, 0)
+    nodes, widx, w, graph = oracle_graph(pts, ids)
+    d.SetTargets(targets, tw)
+    d.GNBegin(api.gn_params(gn_iters=4, pcg_iters=25, corr_mode=2))
+    for _ in range(4):
+        d.GNStep()
+    d.GNEnd()
+    xo, oo, eo = oracle.gn_solve(pts, None, ids, widx, w, graph,
+                                 oracle.gn_params(gn_iters=4, pcg_iters=25), targets=targets, tweights=tw)
+    err = np.abs(d.Vertices() - oo).max()
+    assert err <= POS_TOL * diag(pts), (err, diag(pts))
+    with pytest.raises(api.MvsError):
+        d.SetTargets(targets, -tw - 1.0)
