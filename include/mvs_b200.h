@@ -134,6 +134,30 @@ int mvs_srt_estimate_array(mvs_srt* h, const int32_t* triples, uint64_t seed, do
 int mvs_srt_residual(mvs_srt* h, double scale, const double R[9], const double t[3], double* err);
 /* The triples the library would draw for (n, iter_num, seed) — lets a caller replay RANSAC. */
 int mvs_srt_draw_triples(int64_t n, int iter_num, uint64_t seed, int32_t* triples);
+/* Per-match symmetric reprojection test of the inlier loop [ref: Processor/Processor.cpp:210-239]:
+ * flags[i] = 1 iff both pixel errors are <= pixel_thr under (scale, R, t); err_sum receives the sum
+ * over ALL matches of (e1 + e2)/2 (the reference's err_all_).  flags: n bytes, host. */
+int mvs_srt_inliers(mvs_srt* h, double scale, const double R[9], const double t[3], double pixel_thr,
+                    uint8_t* flags, double* err_sum, int64_t* n_inliers);
+
+/* [ref: Processor/Processor.cpp:177-269 RemoveOutliers] `rounds` (3) rounds of: 200-hypothesis
+ * RANSAC on the surviving matches, symmetric reprojection test with the threshold
+ * pixel_err * adapt_ratio^round, compaction.  keep_idx (capacity n) receives the indices of the
+ * surviving matches in their original order; err = err_all / size of the last round;
+ * inlier_ratio is 0 as in the reference (the code that would update it is commented out, :243-253).
+ * Hypothesis samples come from the counter-based RNG with seed + round. */
+typedef struct mvs_outlier_params {
+  int32_t rounds;      /* 3   [ref: Processor.cpp:198] */
+  int32_t iter_num;    /* 200 [ref: Processor.cpp:202] */
+  double pixel_err;    /* ParamParser::pixel_err (55; config.txt 60) */
+  double adapt_ratio;  /* ParamParser::adapt_pixel_err_ratio (0.6; config.txt 0.75) */
+  uint64_t seed;
+} mvs_outlier_params;
+int mvs_outlier_default_params(mvs_outlier_params* p);
+int mvs_remove_outliers(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, int64_t n,
+                        const mvs_camera* cam1, const mvs_camera* cam2,
+                        const mvs_outlier_params* params, int32_t* keep_idx, int64_t* n_keep,
+                        double* err, double* inlier_ratio);
 
 /* ---------------------------------------------------------------- point-set utilities ------ */
 /* v = s R p + t ; n = R n. [ref: Alignment/Alignment.cpp:31-34, Processor/Processor.cpp:1025-1026]
@@ -287,6 +311,20 @@ int mvs_model2depth_dev(mvs_ctx* ctx, const float* pts_xyzw_dev, int64_t n,
 /* [ref: Common/Utils.h:166-185 LoadDepth/SaveDepth] */
 int mvs_save_depth_raw(const char* filename, const float* inv_depth, int w, int h);
 int mvs_load_depth_raw(const char* filename, float* inv_depth, int w, int h);
+/* [ref: Depth2Model/Depth2Model.cpp:7-82 SaveModel] inverse-depth image -> triangle mesh on the
+ * pixel grid: a vertex per pixel with min_dsp <= d <= max_dsp (row-major order), two triangles per
+ * quad when all three depth differences are <= smooth_threshold * (max_dsp - min_dsp) / 100.
+ * out_xyz capacity w*h*3 doubles, tex_index capacity w*h (pixel id of each vertex), facets capacity
+ * 6*(w-1)*(h-1) ints; any of them may be NULL to query the counts only. */
+int mvs_depth2model(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam, double min_dsp,
+                    double max_dsp, double smooth_threshold, double* out_xyz, int32_t* tex_index,
+                    int32_t* facets, int64_t* n_points, int64_t* n_facets);
+/* [ref: Processor/Processor.cpp:66-115 CheckConsistencyCore] zeroes every pixel of `depth` (w*h
+ * inverse depths, in place) that is outside [min_dsp, max_dsp] or whose 3-D point does not
+ * re-project within reproj_err pixels through every reference frame.  ref_depths: nref x w*h. */
+int mvs_check_consistency(mvs_ctx* ctx, float* depth, const mvs_camera* cam, const float* ref_depths,
+                          const mvs_camera* ref_cams, int nref, double min_dsp, double max_dsp,
+                          double reproj_err);
 /* [ref: Image3D/Image3D.cpp:92-106 SolveUnProjectionD] inverse-depth image -> world points;
  * valid iff min_dsp <= d <= max_dsp. out_xyz: w*h*3 doubles, valid: w*h flags. */
 int mvs_unproject_depth(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam,

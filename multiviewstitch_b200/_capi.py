@@ -38,6 +38,12 @@ class AlignParams(C.Structure):
                 ("neck_label", C.c_int32), ("reserved", C.c_int32)]
 
 
+class OutlierParams(C.Structure):
+    """mvs_outlier_params [ref: Processor/Processor.cpp:177-269]"""
+    _fields_ = [("rounds", C.c_int32), ("iter_num", C.c_int32), ("pixel_err", C.c_double),
+                ("adapt_ratio", C.c_double), ("seed", C.c_uint64)]
+
+
 class GNParams(C.Structure):
     _fields_ = [("gn_iters", C.c_int32), ("pcg_iters", C.c_int32), ("corr_mode", C.c_int32),
                 ("outer_rounds", C.c_int32), ("w_rot", C.c_double), ("w_reg", C.c_double),

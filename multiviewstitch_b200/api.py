@@ -12,7 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import AlignParams, Camera, GNParams, MvsError, check, lib  # noqa: F401
+from ._capi import AlignParams, Camera, GNParams, MvsError, OutlierParams, check, lib  # noqa: F401
 
 
 def _f32(a):
@@ -240,6 +240,7 @@ class SRTSolver:
         """matches as two n x 3 arrays (first, second). float64 -> double planes on the device;
         float32 n x 4 -> float4 layout."""
         p = np.asarray(p)
+        self._n = len(p)
         if p.dtype == np.float32 and p.ndim == 2 and p.shape[1] == 4:
             p4, q4 = _f32(p), _f32(q)
             check(lib().mvs_srt_set_input_f32(self._h, _ptr(p4, C.c_float), _ptr(q4, C.c_float),
@@ -253,6 +254,7 @@ class SRTSolver:
                                       C.byref(cam2) if cam2 else None))
 
     def SetInputDev(self, p_ptr: int, q_ptr: int, n: int, cam1=None, cam2=None):
+        self._n = n
         check(lib().mvs_srt_set_input_dev_f32(self._h, _dev(p_ptr), _dev(q_ptr), C.c_int64(n),
                                               C.byref(cam1) if cam1 else None,
                                               C.byref(cam2) if cam2 else None))
@@ -285,12 +287,36 @@ class SRTSolver:
             return s.value, R.reshape(3, 3), t, be.value, bi.value
         return s.value, R.reshape(3, 3), t
 
+    def Inliers(self, scale, R, t, pixel_thr):
+        """[ref: Processor/Processor.cpp:210-239] -> (flags uint8, err_all sum, n_inliers)"""
+        R, t = _f64(R).reshape(9), _f64(t).reshape(3)
+        flags = np.empty(self._n, np.uint8)
+        es, ni = C.c_double(), C.c_int64()
+        check(lib().mvs_srt_inliers(self._h, C.c_double(scale), _ptr(R, C.c_double),
+                                    _ptr(t, C.c_double), C.c_double(pixel_thr),
+                                    _ptr(flags, C.c_uint8), C.byref(es), C.byref(ni)))
+        return flags, es.value, ni.value
+
     def ResidualError(self, scale, R, t):
         R, t = _f64(R).reshape(9), _f64(t).reshape(3)
         e = C.c_double()
         check(lib().mvs_srt_residual(self._h, C.c_double(scale), _ptr(R, C.c_double),
                                      _ptr(t, C.c_double), C.byref(e)))
         return e.value
+
+
+def remove_outliers(p, q, cam1: Camera, cam2: Camera, rounds=3, iter_num=200, pixel_err=55.0,
+                    adapt_ratio=0.6, seed=0, ctx: Context | None = None):
+    """[ref: Processor/Processor.cpp:177-269 RemoveOutliers] -> (kept match indices, err, inlier_ratio)"""
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    prm = OutlierParams(rounds, iter_num, pixel_err, adapt_ratio, seed)
+    keep = np.empty(len(p), np.int32)
+    nk = C.c_int64()
+    err, ir = C.c_double(), C.c_double()
+    check(lib().mvs_remove_outliers(_ctxh(ctx), _ptr(p, C.c_double), _ptr(q, C.c_double),
+                                    C.c_int64(len(p)), C.byref(cam1), C.byref(cam2), C.byref(prm),
+                                    _ptr(keep, C.c_int32), C.byref(nk), C.byref(err), C.byref(ir)))
+    return keep[:nk.value].copy(), err.value, ir.value
 
 
 def srt_draw_triples(n: int, iter_num: int, seed: int):
@@ -696,6 +722,34 @@ def load_depth_raw(filename: str, w: int, h: int):
     a = np.empty((h, w), np.float32)
     check(lib().mvs_load_depth_raw(filename.encode(), _ptr(a, C.c_float), C.c_int(w), C.c_int(h)))
     return a
+
+
+def depth2model(inv_depth, cam: Camera, min_dsp: float, max_dsp: float, smooth_threshold: float,
+                ctx: Context | None = None):
+    """[ref: Depth2Model/Depth2Model.cpp:7-82 SaveModel] -> (point3d, texIndex, facets)"""
+    a = _f32(inv_depth).reshape(cam.h, cam.w)
+    n, nf = C.c_int64(), C.c_int64()
+    args = (_ctxh(ctx), _ptr(a, C.c_float), C.byref(cam), C.c_double(min_dsp), C.c_double(max_dsp),
+            C.c_double(smooth_threshold))
+    check(lib().mvs_depth2model(*args, None, None, None, C.byref(n), C.byref(nf)))
+    xyz = np.empty((n.value, 3), np.float64)
+    tex = np.empty(n.value, np.int32)
+    fac = np.empty((nf.value, 3), np.int32)
+    check(lib().mvs_depth2model(*args, _ptr(xyz, C.c_double), _ptr(tex, C.c_int32),
+                                _ptr(fac, C.c_int32), C.byref(n), C.byref(nf)))
+    return xyz, tex, fac
+
+
+def check_consistency(depth, cam: Camera, ref_depths, ref_cams, min_dsp, max_dsp, reproj_err,
+                      ctx: Context | None = None):
+    """[ref: Processor/Processor.cpp:66-115 CheckConsistencyCore] -> filtered inverse-depth map"""
+    d = _f32(depth).reshape(cam.h, cam.w).copy()
+    rd = _f32(ref_depths).reshape(len(ref_cams), cam.h, cam.w)
+    arr = (Camera * max(1, len(ref_cams)))(*ref_cams)
+    check(lib().mvs_check_consistency(_ctxh(ctx), _ptr(d, C.c_float), C.byref(cam),
+                                      _ptr(rd, C.c_float), arr, C.c_int(len(ref_cams)),
+                                      C.c_double(min_dsp), C.c_double(max_dsp), C.c_double(reproj_err)))
+    return d
 
 
 def unproject_depth(inv_depth, cam: Camera, min_dsp: float, max_dsp: float,

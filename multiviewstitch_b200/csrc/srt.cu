@@ -320,6 +320,48 @@ struct mvs_srt {
   DevBuf<int> triples;
 };
 
+// Processor/Processor.cpp:210-239: per-match symmetric reprojection test under one transform
+template <class Acc>
+__global__ void __launch_bounds__(kSrtThreads)
+    k_srt_inliers(Acc acc, int64_t n, CamPair cams, const double* __restrict__ hyp, double thr,
+                  unsigned char* __restrict__ flags, double* partials, unsigned* ticket,
+                  double* out) {
+  __shared__ double smem[32 * 2];
+  __shared__ double H[kHypStride];
+  if (threadIdx.x < kHypStride) H[threadIdx.x] = hyp[threadIdx.x];
+  __syncthreads();
+  double v[2] = {0.0, 0.0};
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    double P[3], Q[3];
+    acc.load(i, P, Q);
+    int u2, v2, u1_, v1_, u1, v1, u2_, v2_;
+    project_rn(cams.c2, Q[0], Q[1], Q[2], u2, v2);
+    project_rn(cams.c1, P[0], P[1], P[2], u1_, v1_);
+    double tp[3], tq[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      tp[a] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(H[3 * a], P[0]), __dmul_rn(H[3 * a + 1], P[1])),
+                                  __dmul_rn(H[3 * a + 2], P[2])),
+                        H[9 + a]);
+    double d0 = __dsub_rn(Q[0], H[9]), d1 = __dsub_rn(Q[1], H[10]), d2 = __dsub_rn(Q[2], H[11]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      tq[a] = __dadd_rn(__dadd_rn(__dmul_rn(H[12 + 3 * a], d0), __dmul_rn(H[12 + 3 * a + 1], d1)),
+                        __dmul_rn(H[12 + 3 * a + 2], d2));
+    project_rn(cams.c2, tp[0], tp[1], tp[2], u1, v1);
+    project_rn(cams.c1, tq[0], tq[1], tq[2], u2_, v2_);
+    double e1 = pix_dist(u1, v1, u2, v2);
+    double e2 = pix_dist(u1_, v1_, u2_, v2_);
+    bool in = (e1 <= thr) && (e2 <= thr);
+    flags[i] = in ? 1 : 0;
+    v[0] += __dmul_rn(__dadd_rn(e1, e2), 0.5);
+    v[1] += in ? 1.0 : 0.0;
+  }
+  grid_reduce_sum<2>(v, smem, partials, ticket, out);
+}
+
 namespace {
 
 int srt_prepare(mvs_srt* h) {
@@ -529,6 +571,47 @@ int mvs_srt_residual(mvs_srt* h, double scale, const double R[9], const double t
   double e = 0;
   MVS_TRY(d2h_sync(h->ctx, &e, h->errs.p, sizeof(double)));
   *err = e;
+  return MVS_OK;
+}
+
+int mvs_srt_inliers(mvs_srt* h, double scale, const double R[9], const double t[3], double pixel_thr,
+                    uint8_t* flags, double* err_sum, int64_t* n_inliers) {
+  MVS_TRY(check_ready(h));
+  MVS_REQUIRE(R && t && flags, "null argument");
+  if (!h->have_cams) {
+    set_error("SRT inlier test needs both cameras (set_input was given NULL)");
+    return MVS_ERR_STATE;
+  }
+  mvs_ctx* ctx = h->ctx;
+  MVS_TRY(ctx_ensure_device(ctx));
+  MVS_TRY(srt_prepare(h));
+  double rec[kHypStride];
+  make_hyp_record(scale, R, t, rec);
+  MVS_TRY(h->hyps.reserve(kHypStride));
+  MVS_TRY(pinned_reserve(ctx, sizeof(rec)));
+  memcpy(ctx->pinned, rec, sizeof(rec));
+  MVS_TRY(h2d(ctx, h->hyps.p, ctx->pinned, sizeof(rec)));
+  DevBuf<unsigned char> dflags;
+  MVS_TRY(dflags.reserve((size_t)h->n));
+  int grid = grid_for(ctx, h->n, kSrtThreads, 4);
+  MVS_TRY(h->partials.reserve((size_t)grid * 2 + 16));
+  {
+    ProfScope ps(ctx, "srt_inliers");
+    if (h->mode == 1)
+      k_srt_inliers<AccF64><<<grid, kSrtThreads, 0, ctx->stream>>>(
+          AccF64{h->planes.p, h->n}, h->n, h->cams, h->hyps.p, pixel_thr, dflags.p, h->partials.p,
+          h->ticket.p, h->res.p + R_ACC);
+    else
+      k_srt_inliers<AccF4><<<grid, kSrtThreads, 0, ctx->stream>>>(
+          AccF4{h->p4, h->q4}, h->n, h->cams, h->hyps.p, pixel_thr, dflags.p, h->partials.p,
+          h->ticket.p, h->res.p + R_ACC);
+  }
+  MVS_CUDA(cudaGetLastError());
+  double sums[2];
+  MVS_CUDA(cudaMemcpyAsync(flags, dflags.p, (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
+  MVS_TRY(d2h_sync(ctx, sums, h->res.p + R_ACC, sizeof(sums)));
+  if (err_sum) *err_sum = sums[0];
+  if (n_inliers) *n_inliers = (int64_t)sums[1];
   return MVS_OK;
 }
 

@@ -400,3 +400,51 @@ def unproject_depth(inv_depth, cam, min_dsp, max_dsp):
     lib().orc_unproject_depth(_p(a, C.c_float), C.byref(cam), C.c_double(min_dsp),
                               C.c_double(max_dsp), _p(out, C.c_double), _p(valid, C.c_int32))
     return out, valid
+
+
+# ----------------------------------------------------------------------------- pipeline glue
+def srt_inliers(p, q, cam1, cam2, scale, R, t, pixel_thr):
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    R, t = _f64(R).reshape(9), _f64(t).reshape(3)
+    flags = np.empty(len(p), np.uint8)
+    fn = lib().orc_srt_inliers
+    fn.restype = C.c_double
+    e = fn(_p(p, C.c_double), _p(q, C.c_double), C.c_int64(len(p)), C.byref(cam1), C.byref(cam2),
+           C.c_double(scale), _p(R, C.c_double), _p(t, C.c_double), C.c_double(pixel_thr),
+           _p(flags, C.c_uint8))
+    return flags, e
+
+
+def remove_outliers(p, q, cam1, cam2, rounds=3, iter_num=200, pixel_err=55.0, adapt_ratio=0.6, seed=0):
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    keep = np.empty(len(p), np.int32)
+    nk = C.c_int64()
+    err, ir = C.c_double(), C.c_double()
+    lib().orc_remove_outliers(_p(p, C.c_double), _p(q, C.c_double), C.c_int64(len(p)),
+                              C.byref(cam1), C.byref(cam2), C.c_int(rounds), C.c_int(iter_num),
+                              C.c_double(pixel_err), C.c_double(adapt_ratio), C.c_uint64(seed),
+                              _p(keep, C.c_int32), C.byref(nk), C.byref(err), C.byref(ir))
+    return keep[:nk.value].copy(), err.value, ir.value
+
+
+def depth2model(inv_depth, cam, min_dsp, max_dsp, smooth_threshold):
+    a = _f32(inv_depth).reshape(cam.h, cam.w)
+    npx = cam.h * cam.w
+    xyz = np.empty((npx, 3), np.float64)
+    tex = np.empty(npx, np.int32)
+    fac = np.empty((2 * max(cam.h - 1, 0) * max(cam.w - 1, 0), 3), np.int32)
+    n, nf = C.c_int64(), C.c_int64()
+    lib().orc_depth2model(_p(a, C.c_float), C.byref(cam), C.c_double(min_dsp), C.c_double(max_dsp),
+                          C.c_double(smooth_threshold), _p(xyz, C.c_double), _p(tex, C.c_int32),
+                          _p(fac, C.c_int32), C.byref(n), C.byref(nf))
+    return xyz[:n.value].copy(), tex[:n.value].copy(), fac[:nf.value].copy()
+
+
+def check_consistency(depth, cam, ref_depths, ref_cams, min_dsp, max_dsp, reproj_err):
+    d = _f32(depth).reshape(cam.h, cam.w).copy()
+    rd = _f32(ref_depths).reshape(len(ref_cams), cam.h, cam.w)
+    arr = (Camera * max(1, len(ref_cams)))(*ref_cams)
+    lib().orc_check_consistency(_p(d, C.c_float), C.byref(cam), _p(rd, C.c_float), arr,
+                                C.c_int(len(ref_cams)), C.c_double(min_dsp), C.c_double(max_dsp),
+                                C.c_double(reproj_err))
+    return d
