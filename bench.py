@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="objects", choices=["objects", "shard"])
+    ap.add_argument("--mode", default="objects", choices=["objects", "shard", "pairs"])
+    ap.add_argument("--pairs", type=int, default=28, help="view pairs of --mode pairs (C(8,2) = 28)")
     ap.add_argument("--side", type=int, default=408, help="cube-sphere grid side (verts = 6*side^2+2)")
     ap.add_argument("--nodes", type=int, default=4096)
     ap.add_argument("--gn-iters", type=int, default=10)
@@ -290,6 +291,91 @@ def secondary_c2(args, api, ctx, stream, peak):
     return out
 
 
+def run_pairs(args):
+    """configs[3] (C4): 28 = C(8,2) view pairs of an 8-view turntable, each pair the C1 workload
+    (two 640x480 depth maps -> unproject -> RemoveOutliers -> SRT -> Depth2Model mesh -> apply ->
+    deformation -> Model2Depth), sharded pair -> rank u % N with no data-path collective
+    (mvs_partition_units).  A step = every rank's share of the pairs once, host buffers in and out
+    (the depth maps live in host memory, as the reference reads them from disk)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from multiviewstitch_b200 import api, pipeline, _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    ctx = api.Context(local, stream.cuda_stream)
+    part = (C.c_int64 * 3)()
+    _capi.check(_capi.lib().mvs_partition_units(C.c_int64(args.pairs), C.c_int(world), C.c_int(rank), part))
+    mine = [part[0] + k * part[1] for k in range(part[2])]
+    work = []
+    with torch.cuda.stream(stream):
+        m2d = api.Model2Depth(ctx)
+        for u in mine:  # setup: the pair's two depth maps + matches (not timed)
+            sc = pipeline.make_scene(side=72, view_angle_deg=10.0 + 1.5 * u, seed=0)
+            ca, cb = api.make_camera(*sc["cam_a"]), api.make_camera(*sc["cam_b"])
+            m2d.SetInput([sc["verts_a"], sc["verts_b"]], [None, None], [sc["faces"], sc["faces"]], [[ca], [cb]])
+            da, db = m2d.render(0)[0], m2d.render(1)[0]
+            pa, va = api.unproject_depth(da, ca, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
+            pb, vb = api.unproject_depth(db, cb, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
+            mt = pipeline.lattice_matches(pa, va, sc["cam_b"], vb, sc["planted"], 640, 480, seed=u)
+            work.append((da, ca, db, cb, mt, sc["planted"], u))
+
+        def step():
+            return [pipeline.stitch_pair(da, ca, db, cb, mt, ctx, n_nodes=512, gn_iters=4, seed=u)
+                    for da, ca, db, cb, mt, _, u in work]
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(max(3, args.warmup)):
+            outs = step()
+        ctx.launch_count_reset()
+        clocks = Clocks(local)
+        if rank == 0:
+            clocks.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(args.steps)]
+        barrier()
+        for s in range(args.steps):
+            ev[s][0].record(stream)
+            outs = step()
+            ev[s][1].record(stream)
+        barrier()
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        launches = ctx.launch_count()
+        clk = clocks.stop() if rank == 0 else None
+    # every pair must recover its planted similarity
+    worst = 0.0
+    for o, wk in zip(outs, work):
+        ps, pR, pt = wk[5]
+        worst = max(worst, abs(o["scale"] - ps) / ps, float(np.abs(o["R"] - pR).max()))
+    t = torch.tensor([dev_ms, worst], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, worst = t[0].item(), t[1].item()
+    if rank == 0:
+        line = {"metric": "view_pairs_per_s", "value": args.pairs * args.steps / (dev_ms * 1e-3),
+                "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+                "config": {"workload": f"C4: {args.pairs} view pairs (two 640x480 depth maps each) sharded "
+                                       "pair -> rank u % N, SRT + deformation + Model2Depth per pair",
+                           "pairs_on_busiest_rank": -(-args.pairs // world), "l2": "host buffers per pair"},
+                "max_srt_error_vs_planted": worst, "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -497,6 +583,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "pairs":
+        run_pairs(args)
     else:
         run_b200(args)
 

@@ -93,29 +93,53 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// The stream of the context the calling thread last entered (ctx_ensure_device): device buffers
+// are allocated and freed in that stream's order from the cached stream-ordered pool, so the many
+// temporaries of the host-buffer entry points cost microseconds instead of a cudaMalloc/cudaFree
+// pair (each of which synchronises the device).
+struct AllocStream {
+  cudaStream_t stream = nullptr;
+  bool valid = false;
+};
+AllocStream& alloc_stream();
+
 // Simple owning device buffer (typed), grows but never shrinks.
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;  // elements
+  cudaStream_t st = nullptr;  // stream the block was allocated on (async pool) ...
+  bool async = false;         // ... or plain cudaMalloc
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (async)
+        cudaFreeAsync(p, st);
+      else
+        cudaFree(p);
+    }
     p = nullptr;
     cap = 0;
   }
   int reserve(size_t n) {
     if (n <= cap) return MVS_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
+    release();
     size_t bytes = (n ? n : 1) * sizeof(T);
-    cudaError_t e = cudaMalloc((void**)&p, bytes);
+    AllocStream& as = alloc_stream();
+    cudaError_t e;
+    if (as.valid) {
+      e = cudaMallocAsync((void**)&p, bytes, as.stream);
+      st = as.stream;
+      async = true;
+    } else {
+      e = cudaMalloc((void**)&p, bytes);
+      async = false;
+    }
     if (e != cudaSuccess) {
-      set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
       p = nullptr;
       return MVS_ERR_CUDA;
     }

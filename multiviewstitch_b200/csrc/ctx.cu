@@ -16,12 +16,20 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+AllocStream& alloc_stream() {
+  static thread_local AllocStream as;
+  return as;
+}
+
 int ctx_ensure_device(mvs_ctx* ctx) {
   if (!ctx) {
     set_error("null context");
     return MVS_ERR_INVALID_ARG;
   }
   MVS_CUDA(cudaSetDevice(ctx->device));
+  AllocStream& as = alloc_stream();
+  as.stream = ctx->stream;
+  as.valid = true;
   return MVS_OK;
 }
 

@@ -82,20 +82,43 @@ __global__ void __launch_bounds__(256)
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence();
-    float b = -1.0f;
-    int id = 0x7fffffff;
-    for (unsigned k = 0; k < gridDim.x; ++k) {
-      float v = __ldcg(pval + k);
-      int ix = __ldcg(pidx + k);
-      if (v > b || (v == b && ix < id)) {
-        b = v;
-        id = ix;
-      }
+  if (!is_last) return;
+  // the last CTA picks the winner among the per-CTA candidates: every thread takes a strided share
+  // (independent loads), then the same warp / CTA argmax tree as above — (value desc, index asc)
+  __threadfence();
+  best = -1.0f;
+  bi = 0x7fffffff;
+  for (unsigned k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
+    float v = __ldcg(pval + k);
+    int ix = __ldcg(pidx + k);
+    if (v > best || (v == best && ix < bi)) {
+      best = v;
+      bi = ix;
     }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+    sv[warp] = best;
+    si[warp] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) {
+        best = sv[w];
+        bi = si[w];
+      }
     out_ids[step] = cur;
-    *cur_io = id;
+    *cur_io = bi;
     *ticket = 0u;
   }
 }
