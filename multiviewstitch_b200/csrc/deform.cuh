@@ -62,6 +62,14 @@ struct mvs_deform {
   mvs::DevBuf<int> run_slots;  // nruns x 20
   mvs::DevBuf<int> run_start;  // nruns + 1: first sorted vertex of each run
   int64_t nruns = 0;
+  // assembly groups: kGrpRuns consecutive runs share one shared-memory accumulator set.  Only the
+  // upper triangle of J^T J is accumulated (block (j,l), j <= l); tslot mirrors it on conversion.
+  mvs::DevBuf<float4> run_g;            // nruns x 4: positions of the run's four nodes (.w = valid)
+  mvs::DevBuf<unsigned char> run_local; // nruns x 16: group-local accumulator of each of the 14 tiles
+  mvs::DevBuf<int> grp_n;               // ngroups: distinct accumulators of the group
+  mvs::DevBuf<int> grp_dst;             // ngroups x kGrpMax: first sys64 element of each accumulator
+  mvs::DevBuf<int> tslot;               // nnz: pattern slot of the transposed block
+  int64_t ngroups = 0;
   mvs::DevBuf<float> Minv;  // m x 144
   mvs::DevBuf<float> x;     // m x 12
   mvs::DevBuf<float> pcg;   // r, z, p0, p1, q, delta : 6 x m x 12
@@ -102,6 +110,9 @@ struct mvs_deform {
 };
 
 namespace mvs {
+
+constexpr int kGrpRuns = 8;             // runs per assembly group
+constexpr int kGrpMax = 14 * kGrpRuns;  // 10 upper-triangle block tiles + 4 gradient tiles per run
 
 // scal[] slots
 enum { S_RZ = 0, S_PQ = 1, S_RZ_NEW = 2, S_BNORM2 = 3, S_RNORM2 = 4, S_EFIT = 8, S_EROT = 9,

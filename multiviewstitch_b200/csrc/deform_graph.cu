@@ -327,8 +327,9 @@ __device__ __forceinline__ int find_slot_dev(const int* __restrict__ row_ptr,
 // heads fill the run's slot table (16 pattern slots (a,b) row-major, then the 4 node ids)
 __global__ void k_run_table(const int4* __restrict__ vidx, const int* __restrict__ flag_scan,
                             int64_t n, const int* __restrict__ row_ptr,
-                            const int* __restrict__ col, float4* __restrict__ v,
-                            int* __restrict__ run_slots, int* __restrict__ run_start) {
+                            const int* __restrict__ col, const float4* __restrict__ g,
+                            float4* __restrict__ v, int* __restrict__ run_slots,
+                            int* __restrict__ run_start, float4* __restrict__ run_g) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int4 id = vidx[i];
@@ -348,7 +349,62 @@ __global__ void k_run_table(const int4* __restrict__ vidx, const int* __restrict
     for (int b = 0; b < 4; ++b)
       out[4 * a + b] = (js[a] >= 0 && js[b] >= 0) ? find_slot_dev(row_ptr, col, js[a], js[b]) : -1;
     out[16 + a] = js[a];
+    float4 gj = js[a] >= 0 ? g[js[a]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    gj.w = js[a] >= 0 ? 1.0f : 0.0f;
+    run_g[(size_t)run * 4 + a] = gj;
   }
+}
+
+// tile t of a run: t < 10 the block tile (a, b), a <= b; t = 10..13 the gradient tile of node t - 10
+__constant__ int c_tile_a[10] = {0, 1, 2, 3, 0, 0, 0, 1, 1, 2};
+__constant__ int c_tile_b[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
+
+// One thread per assembly group: the distinct destinations (first sys64 element) of the group's
+// tiles and, per run, the group-local accumulator index of each tile (255 = no destination).
+__global__ void k_group_table(const int* __restrict__ run_slots, int64_t nruns, int64_t nnz,
+                              int64_t ngroups, int* __restrict__ grp_n, int* __restrict__ grp_dst,
+                              unsigned char* __restrict__ run_local) {
+  int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (q >= ngroups) return;
+  int* dst = grp_dst + (size_t)q * kGrpMax;
+  int cnt = 0;
+  int64_t r1 = min(nruns, (q + 1) * (int64_t)kGrpRuns);
+  for (int64_t r = q * kGrpRuns; r < r1; ++r) {
+    const int* rs = run_slots + (size_t)r * 20;
+    for (int t = 0; t < 14; ++t) {
+      int d;
+      if (t < 10) {
+        int sl = rs[4 * c_tile_a[t] + c_tile_b[t]];
+        d = sl < 0 ? -1 : sl * 16;
+      } else {
+        int j = rs[16 + t - 10];
+        d = j < 0 ? -1 : (int)(nnz * 16 + (int64_t)j * 12);
+      }
+      int loc = 255;
+      if (d >= 0) {
+        for (int i = 0; i < cnt; ++i)
+          if (dst[i] == d) {
+            loc = i;
+            break;
+          }
+        if (loc == 255) {
+          dst[cnt] = d;
+          loc = cnt++;
+        }
+      }
+      run_local[(size_t)r * 16 + t] = (unsigned char)loc;
+    }
+  }
+  grp_n[q] = cnt;
+}
+
+// tslot[e] = slot of block (l, j) for the entry e = (j, l)
+__global__ void k_transposed_slots(const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                   int64_t m, int* __restrict__ tslot) {
+  int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  for (int t = row_ptr[j]; t < row_ptr[j + 1]; ++t)
+    tslot[t] = find_slot_dev(row_ptr, col, col[t], (int)j);
 }
 
 // ------------------------------------------------------------------ build_graph
@@ -478,12 +534,27 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
     int nruns = 0;
     MVS_TRY(d2h_sync(ctx, &nruns, rflag.p + n, sizeof(int)));
     h->nruns = nruns;
+    if ((int64_t)nnz * 16 + m * 12 >= (int64_t)1 << 31) {
+      set_error("build_graph: normal-equation system exceeds 2^31 elements");
+      return MVS_ERR_CAPACITY;
+    }
+    h->ngroups = (nruns + kGrpRuns - 1) / kGrpRuns;
     MVS_TRY(h->run_slots.reserve((size_t)nruns * 20));
     MVS_TRY(h->run_start.reserve((size_t)nruns + 1));
+    MVS_TRY(h->run_g.reserve((size_t)nruns * 4));
+    MVS_TRY(h->run_local.reserve((size_t)nruns * 16));
+    MVS_TRY(h->grp_n.reserve((size_t)h->ngroups));
+    MVS_TRY(h->grp_dst.reserve((size_t)h->ngroups * kGrpMax));
+    MVS_TRY(h->tslot.reserve((size_t)nnz));
     {
-      ProfScope ps(ctx, "run_table");
+      ProfScope ps(ctx, "run_table", 3);
       k_run_table<<<div_up(n, 256), 256, 0, st>>>(h->vidx.p, rflag.p, n, h->row_ptr.p, h->col.p,
-                                                  h->v.p, h->run_slots.p, h->run_start.p);
+                                                  h->g.p, h->v.p, h->run_slots.p, h->run_start.p,
+                                                  h->run_g.p);
+      k_group_table<<<div_up(h->ngroups, 64), 64, 0, st>>>(h->run_slots.p, nruns, nnz, h->ngroups,
+                                                           h->grp_n.p, h->grp_dst.p,
+                                                           h->run_local.p);
+      k_transposed_slots<<<div_up(m, 128), 128, 0, st>>>(h->row_ptr.p, h->col.p, m, h->tslot.p);
     }
     int n32 = (int)n;
     MVS_CUDA(cudaMemcpyAsync(h->run_start.p + nruns, &n32, sizeof(int), cudaMemcpyHostToDevice, st));

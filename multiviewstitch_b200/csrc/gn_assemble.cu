@@ -178,7 +178,6 @@ int gn_deform_and_correspond(mvs_deform* h) {
 // ------------------------------------------------------------------ fit assembly
 constexpr int kAsmWarps = 4;
 constexpr int kRecStride = 20;
-constexpr int kOutTiles = 20;  // 16 block tiles (a,b) row-major + 4 rhs tiles
 
 __device__ __forceinline__ int find_slot(const int* __restrict__ row_ptr,
                                          const int* __restrict__ col, int j, int l) {
@@ -196,29 +195,38 @@ __device__ __forceinline__ void fx_add(long long* addr, float v, float scale) {
             (unsigned long long)__float2ll_rn(v * scale));
 }
 
-// One warp takes one tuple run (consecutive sorted vertices that share their four nodes, avg ~22
-// at C3) at a time, 32 vertices per pass: per-vertex records (b_a = sqrt(w_fit omega) w_a (d_a, 1),
-// a = 0..3, and the scaled residual) are staged in shared memory, 14 tile lanes x 2 half-warps
-// accumulate the 10 distinct 4x4 products b_a b_b^T and the 4 gradient tiles b_a r^T in registers
-// over the whole run, then the result tiles are laid out in shared memory in the order of the
-// run's precomputed slot table and flushed once by the whole warp — 16 consecutive lanes hit 16
-// consecutive int64 — as fixed-point atomics.  No pattern search, one flush per run.
-__global__ void __launch_bounds__(kAsmWarps * 32, 8)
-    k_assemble_fit(const float4* __restrict__ v, const int4* __restrict__ vidx,
-                   const float4* __restrict__ vw, const float4* __restrict__ resid,
-                   const float4* __restrict__ g, const int* __restrict__ run_slots,
-                   const int* __restrict__ run_start, long long* __restrict__ B64,
-                   long long* __restrict__ rhs64, int64_t begin, int64_t end, float w_fit,
-                   float fx_scale) {
+// The kernel is bound by the issue rate of the global reductions (RED: ~1.3 cycles per lane per SM),
+// not by the 48 B/vertex stream, so the design minimises reductions per vertex:
+//   * only the upper triangle of J^T J is accumulated (10 of the 16 block pairs of a vertex; the
+//     conversion pass mirrors it);
+//   * a warp owns a GROUP of kGrpRuns consecutive tuple runs (a run = consecutive sorted vertices
+//     that share their four nodes, ~22 vertices at C3).  Runs of a group mostly share their primary
+//     node, so their tiles hit the same blocks: the group keeps one shared-memory accumulator per
+//     distinct destination (table built with the graph) and flushes each ONCE, as fixed-point
+//     integer atomics (exactly commutative: bitwise reproducible);
+//   * per run: the per-vertex records b_a = sqrt(w_fit omega) w_a (v - g_a, 1), a = 0..3, and the
+//     scaled residual are staged in shared memory, 14 tile lanes x 2 half-warps accumulate the 10
+//     products b_a b_b^T (a <= b) and the 4 gradient tiles b_a r^T in registers;
+//   * the next 32 vertices (resid, v, vw: 3 x 16 B each; node ids are not read — the run table
+//     carries the node positions) are in flight while the current ones are processed.
+struct AsmRaw {
+  float4 rs, vi, w;
+};
+
+__global__ void __launch_bounds__(kAsmWarps * 32, 5)
+    k_assemble_fit(const float4* __restrict__ v, const float4* __restrict__ vw,
+                   const float4* __restrict__ resid, const float4* __restrict__ run_g,
+                   const unsigned char* __restrict__ run_local, const int* __restrict__ run_start,
+                   const int* __restrict__ grp_n, const int* __restrict__ grp_dst,
+                   long long* __restrict__ sys64, int nnz16, int nruns, int64_t begin, int64_t end,
+                   float w_fit, float fx_scale) {
   __shared__ __align__(16) float rec[kAsmWarps][32][kRecStride];
-  __shared__ __align__(16) float outt[kAsmWarps][kOutTiles][16];
-  __shared__ int slots[kAsmWarps][kOutTiles];
+  __shared__ __align__(16) float accs[kAsmWarps][kGrpMax][16];
   const unsigned full = 0xffffffffu;
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int nwarps = gridDim.x * kAsmWarps;
-  int wg = blockIdx.x * kAsmWarps + warp;
-  // tile table: 10 (a,b) block tiles (a<=b) then 4 rhs tiles
-  int half = lane >> 4, t = lane & 15;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * kAsmWarps;
+  const int wg = blockIdx.x * kAsmWarps + warp;
+  const int half = lane >> 4, t = lane & 15;
   int ta, tb;
   switch (t) {
     case 0: ta = 0; tb = 0; break;
@@ -231,49 +239,94 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 8)
     case 7: ta = 1; tb = 2; break;
     case 8: ta = 1; tb = 3; break;
     case 9: ta = 2; tb = 3; break;
-    default: ta = (t - 10) & 3; tb = 4; break;  // rhs tiles read the residual slot (cols 16..19)
+    default: ta = (t - 10) & 3; tb = 4; break;  // gradient tiles read the residual (cols 16..19)
   }
   // runs that intersect this rank's vertex range
   const int run_lo = __float_as_int(__ldg(&v[begin].w));
   const int run_hi = __float_as_int(__ldg(&v[end - 1].w));
-  for (int run = run_lo + wg; run <= run_hi; run += nwarps) {
-    int64_t rs0 = max((int64_t)__ldg(run_start + run), begin);
-    int64_t rs1 = min((int64_t)__ldg(run_start + run + 1), end);
-    if (lane < kOutTiles) slots[warp][lane] = __ldg(run_slots + (size_t)run * 20 + lane);
+  auto fetch = [&](int64_t i) {
+    AsmRaw r;
+    i = min(i, end - 1);  // lanes past the run are masked when the pass is processed
+    r.rs = __ldg(resid + i);
+    r.vi = __ldg(v + i);
+    r.w = __ldg(vw + i);
+    return r;
+  };
+  for (int q = run_lo / kGrpRuns + wg; q <= run_hi / kGrpRuns; q += nwarps) {
+    const int r_base = q * kGrpRuns;
+    const int r_first = max(r_base, run_lo), r_last = min(r_base + kGrpRuns - 1, run_hi);
+    // lane l <= kGrpRuns: first vertex of run r_base + l
+    const int my_rs = __ldg(run_start + min(r_base + min(lane, kGrpRuns), nruns));
+    const int L = __ldg(grp_n + q);
+    for (int k = lane; k < L * 4; k += 32)
+      reinterpret_cast<float4*>(&accs[warp][0][0])[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int run = r_first;
+    int64_t rs1 = min((int64_t)__shfl_sync(full, my_rs, run - r_base + 1), end);
+    int64_t base = max((int64_t)__shfl_sync(full, my_rs, run - r_base), begin);
+    AsmRaw raw = fetch(base + lane);
+    float4 mg = make_float4(0.f, 0.f, 0.f, 0.f);
+    int mloc = 255;
+    if (lane < 4) mg = __ldg(run_g + (size_t)run * 4 + lane);
+    if (lane < 14) mloc = __ldg(run_local + (size_t)run * 16 + lane);
+    bool new_run = true;
+    float gx[4], gy[4], gz[4], gv[4];
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-    for (int64_t base = rs0; base < rs1; base += 32) {
-      int64_t i = base + lane;
+    int loc = 255;
+    __syncwarp();
+    for (;;) {
+      if (new_run) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          gx[a] = __shfl_sync(full, mg.x, a);
+          gy[a] = __shfl_sync(full, mg.y, a);
+          gz[a] = __shfl_sync(full, mg.z, a);
+          gv[a] = __shfl_sync(full, mg.w, a);
+        }
+        loc = mloc;
+      }
+      const int cnt = (int)min((int64_t)32, rs1 - base);
+      // ---- next pass: same run, or the first pass of the next run of the group
+      int nrun = run;
+      int64_t nbase = base + 32, nrs1 = rs1;
+      if (nbase >= rs1) {
+        nrun = run + 1;
+        if (nrun <= r_last) {
+          nbase = max((int64_t)__shfl_sync(full, my_rs, nrun - r_base), begin);
+          nrs1 = min((int64_t)__shfl_sync(full, my_rs, nrun - r_base + 1), end);
+        }
+      }
+      const bool has_next = nrun <= r_last;
+      AsmRaw raw_n = raw;
+      if (has_next) {
+        raw_n = fetch(nbase + lane);
+        if (nrun != run) {
+          if (lane < 4) mg = __ldg(run_g + (size_t)nrun * 4 + lane);
+          if (lane < 14) mloc = __ldg(run_local + (size_t)nrun * 16 + lane);
+        }
+      }
+      // ---- records of this pass
       float r0[kRecStride];
 #pragma unroll
       for (int k = 0; k < kRecStride; ++k) r0[k] = 0.f;
-      if (i < rs1) {
-        float4 rs = __ldg(resid + i);
-        if (rs.w > 0.f) {
-          float s = sqrtf(w_fit * rs.w);
-          float4 vi = __ldg(v + i);
-          float4 w = __ldg(vw + i);
-          int4 id = __ldg(vidx + i);
-          int ids[4] = {id.x, id.y, id.z, id.w};
-          float ws[4] = {w.x, w.y, w.z, w.w};
+      if (lane < cnt && raw.rs.w > 0.f) {
+        float s = sqrtf(w_fit * raw.rs.w);
+        float ws[4] = {raw.w.x, raw.w.y, raw.w.z, raw.w.w};
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            if (ids[a] >= 0) {
-              float4 gj = __ldg(g + ids[a]);
-              float sw = s * ws[a];
-              r0[4 * a + 0] = sw * (vi.x - gj.x);
-              r0[4 * a + 1] = sw * (vi.y - gj.y);
-              r0[4 * a + 2] = sw * (vi.z - gj.z);
-              r0[4 * a + 3] = sw;
-            }
+        for (int a = 0; a < 4; ++a) {
+          if (gv[a] > 0.f) {
+            float sw = s * ws[a];
+            r0[4 * a + 0] = sw * (raw.vi.x - gx[a]);
+            r0[4 * a + 1] = sw * (raw.vi.y - gy[a]);
+            r0[4 * a + 2] = sw * (raw.vi.z - gz[a]);
+            r0[4 * a + 3] = sw;
           }
-          r0[16] = s * rs.x;
-          r0[17] = s * rs.y;
-          r0[18] = s * rs.z;
         }
+        r0[16] = s * raw.rs.x;
+        r0[17] = s * raw.rs.y;
+        r0[18] = s * raw.rs.z;
       }
-      __syncwarp();  // the previous pass has been consumed
       {
         float4* dst = reinterpret_cast<float4*>(&rec[warp][lane][0]);
 #pragma unroll
@@ -281,11 +334,10 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 8)
           dst[k] = make_float4(r0[4 * k], r0[4 * k + 1], r0[4 * k + 2], r0[4 * k + 3]);
       }
       __syncwarp();
-      int cnt = (int)min((int64_t)32, rs1 - base);
       if (t < 14) {
-        // members mi = half, half + 2, ...; records past cnt are zero (whole pass is rewritten every
-        // time), so the loop runs in steps of two members without a tail
-        int cnt4 = (cnt + 3) & ~3;
+        // members mi = half, half + 2, ...; records past cnt are zero (the whole pass is rewritten
+        // every time), so the loop runs two members per step without a tail
+        const int cnt4 = (cnt + 3) & ~3;
         for (int mi = half; mi < cnt4; mi += 4) {
           const float4 ba0 = *reinterpret_cast<const float4*>(&rec[warp][mi][4 * ta]);
           const float4 bb0 = *reinterpret_cast<const float4*>(&rec[warp][mi][4 * tb]);
@@ -301,53 +353,66 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 8)
           acc[12] += ba1.w * bb1.x; acc[13] += ba1.w * bb1.y; acc[14] += ba1.w * bb1.z; acc[15] += ba1.w * bb1.w;
         }
       }
-    }
+      new_run = nrun != run;
+      if (new_run) {
+        // ---- the run is complete: fold the two half-warps, add the tiles to the group accumulators
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] += __shfl_xor_sync(full, acc[k], 16);
-    if (half == 0 && t < 14) {
-      if (t < 10) {
-        float4* o = reinterpret_cast<float4*>(&outt[warp][4 * ta + tb][0]);
-        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        o[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
-        o[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
-        if (ta != tb) {  // the transposed block (j_b, j_a)
-          float4* o2 = reinterpret_cast<float4*>(&outt[warp][4 * tb + ta][0]);
-          o2[0] = make_float4(acc[0], acc[4], acc[8], acc[12]);
-          o2[1] = make_float4(acc[1], acc[5], acc[9], acc[13]);
-          o2[2] = make_float4(acc[2], acc[6], acc[10], acc[14]);
-          o2[3] = make_float4(acc[3], acc[7], acc[11], acc[15]);
+        for (int k = 0; k < 16; ++k) acc[k] += __shfl_xor_sync(full, acc[k], 16);
+        if (half == 0 && t < 14 && loc != 255) {
+          float4* o = reinterpret_cast<float4*>(&accs[warp][loc][0]);
+          if (t < 10) {
+            float4 o0 = o[0], o1 = o[1], o2 = o[2], o3 = o[3];
+            o0.x += acc[0]; o0.y += acc[1]; o0.z += acc[2]; o0.w += acc[3];
+            o1.x += acc[4]; o1.y += acc[5]; o1.z += acc[6]; o1.w += acc[7];
+            o2.x += acc[8]; o2.y += acc[9]; o2.z += acc[10]; o2.w += acc[11];
+            o3.x += acc[12]; o3.y += acc[13]; o3.z += acc[14]; o3.w += acc[15];
+            o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+          } else {
+            // rhs_j[3c + r] = sum b_a[c] * r[r]   (acc[4c + r], r < 3)
+            float4 o0 = o[0], o1 = o[1], o2 = o[2];
+            o0.x += acc[0]; o0.y += acc[1]; o0.z += acc[2]; o0.w += acc[4];
+            o1.x += acc[5]; o1.y += acc[6]; o1.z += acc[8]; o1.w += acc[9];
+            o2.x += acc[10]; o2.y += acc[12]; o2.z += acc[13]; o2.w += acc[14];
+            o[0] = o0; o[1] = o1; o[2] = o2;
+          }
         }
-      } else {
-        // rhs_j[3c + r] = sum b_a[c] * r[r]   (acc[4c + r], r < 3)
-        float* o = &outt[warp][16 + ta][0];
-        o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[4];
-        o[4] = acc[5]; o[5] = acc[6]; o[6] = acc[8]; o[7] = acc[9];
-        o[8] = acc[10]; o[9] = acc[12]; o[10] = acc[13]; o[11] = acc[14];
-      }
-    }
-    __syncwarp();
 #pragma unroll
-    for (int k = lane; k < kOutTiles * 16; k += 32) {
-      int tile = k >> 4, e = k & 15;
-      int sl = slots[warp][tile];
-      if (sl < 0) continue;
-      float val = outt[warp][tile][e];
-      if (tile < 16)
-        fx_add(B64 + (size_t)sl * 16 + e, val, fx_scale);
-      else if (e < 12)
-        fx_add(rhs64 + (size_t)sl * 12 + e, val, fx_scale);
+        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+      }
+      __syncwarp();  // this pass's records are consumed; accumulator updates are visible
+      if (!has_next) break;
+      run = nrun;
+      base = nbase;
+      rs1 = nrs1;
+      raw = raw_n;
+    }
+    // ---- flush the group: 16 consecutive lanes hit 16 consecutive int64
+    const int* gd = grp_dst + (size_t)q * kGrpMax;
+    for (int k = lane; k < L * 16; k += 32) {
+      const int tile = k >> 4, e = k & 15;
+      const int d = __ldg(gd + tile);
+      if (e < (d >= nnz16 ? 12 : 16)) fx_add(sys64 + d + e, accs[warp][tile][e], fx_scale);
     }
     __syncwarp();
   }
 }
 
-// fixed point -> float32 system
+// fixed point -> float32 system; the lower triangle of the block pattern is the transpose of the
+// accumulated upper triangle (tslot[e] = slot of the transposed block; rows ascend, so e is a
+// lower-triangle entry iff tslot[e] < e)
 __global__ void k_sys_convert(const long long* __restrict__ in, float* __restrict__ out, int64_t n,
-                              float inv_scale) {
+                              int64_t nnz16, const int* __restrict__ tslot, float inv_scale) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) out[i] = (float)((double)in[i] * (double)inv_scale);
+  for (; i < n; i += stride) {
+    int64_t src = i;
+    if (i < nnz16) {
+      int e = (int)(i >> 4), el = (int)(i & 15);
+      int te = __ldg(tslot + e);
+      if (te < e) src = (int64_t)te * 16 + (((el & 3) << 2) | (el >> 2));
+    }
+    out[i] = (float)((double)in[src] * (double)inv_scale);
+  }
 }
 
 // ------------------------------------------------------------------ node terms
@@ -437,14 +502,13 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) gl[3 * c + rr] += w_reg * a[c] * r[rr];
       }
-      long long* Bjl = B + (size_t)find_slot(row_ptr, col, (int)j, l) * 16;
-      long long* Blj = B + (size_t)find_slot(row_ptr, col, l, (int)j) * 16;
+      // coupling block: B_jl[c][3] = B_lj[3][c] = -w a_c; only the upper-triangle copy is
+      // accumulated (k_sys_convert mirrors it)
+      long long* Bup = B + (size_t)(j < l ? find_slot(row_ptr, col, (int)j, l)
+                                          : find_slot(row_ptr, col, l, (int)j)) * 16;
       long long* Bll = B + (size_t)find_slot(row_ptr, col, l, l) * 16;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        fx_add(Bjl + 4 * c + 3, -w_reg * a[c], fxs);
-        fx_add(Blj + 12 + c, -w_reg * a[c], fxs);
-      }
+      for (int c = 0; c < 4; ++c) fx_add(Bup + (j < l ? 4 * c + 3 : 12 + c), -w_reg * a[c], fxs);
       fx_add(Bll + 15, w_reg, fxs);
 #pragma unroll
       for (int rr = 0; rr < 3; ++rr) fx_add(rhs + (size_t)l * 12 + 9 + rr, -w_reg * r[rr], fxs);
@@ -559,12 +623,12 @@ int gn_assemble(mvs_deform* h) {
   int64_t b = h->shard_begin(), e = h->shard_end();
   if (e > b) {
     ProfScope ps(ctx, "gn_assemble_fit");
-    int64_t warps_needed = std::min<int64_t>(h->nruns, (e - b + 7) / 8);
+    int64_t warps_needed = std::min<int64_t>(h->ngroups, (e - b + 63) / 64);
     int grid = (int)std::min<int64_t>((warps_needed + kAsmWarps - 1) / kAsmWarps,
-                                      (int64_t)ctx->num_sms * 12);
-    k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(h->v.p, h->vidx.p, h->vw.p, h->resid.p, h->g.p,
-                                                    h->run_slots.p, h->run_start.p, h->B64(),
-                                                    h->rhs64(), b, e, (float)h->prm.w_fit, fxs);
+                                      (int64_t)ctx->num_sms * 5);
+    k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(
+        h->v.p, h->vw.p, h->resid.p, h->run_g.p, h->run_local.p, h->run_start.p, h->grp_n.p,
+        h->grp_dst.p, h->sys64.p, (int)(h->nnz * 16), (int)h->nruns, b, e, (float)h->prm.w_fit, fxs);
   }
   MVS_CUDA(cudaGetLastError());
   if (ctx->comm && ctx->nranks > 1) {
@@ -580,7 +644,8 @@ int gn_assemble(mvs_deform* h) {
         h->Rot(), h->rhs64(), (float)h->prm.w_rot, (float)h->prm.w_reg, fxs);
     // sys = [B | rhs | Rot]: B and rhs are contiguous in both buffers
     k_sys_convert<<<grid_for(ctx, (int64_t)h->sys64_count(), 256, 4), 256, 0, st>>>(
-        h->sys64.p, h->sys.p, (int64_t)h->sys64_count(), (float)(1.0 / h->fx_scale));
+        h->sys64.p, h->sys.p, (int64_t)h->sys64_count(), h->nnz * 16, h->tslot.p,
+        (float)(1.0 / h->fx_scale));
   }
   {
     ProfScope ps(ctx, "gn_precond");

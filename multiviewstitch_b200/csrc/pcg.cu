@@ -8,19 +8,22 @@
 //     iteration only vectors move (L2-resident);
 //   * 16 lanes per node row (12 active: one per unknown); r, z, p, delta of a row live in
 //     registers for the whole solve (RS row slots per lane group);
-//   * two grid-wide barriers per iteration (after p.q and after r.z); dot products are float64 with
-//     a fixed reduction order (lane -> warp -> CTA partial in global memory -> every CTA adds the
-//     partials in CTA order), so the solve is bit-reproducible run to run;
+//   * two grid-wide exchanges per iteration (after p.q and after r.z).  The barrier and the dot
+//     product are ONE step: every CTA release-stores its float64 partial into its slot of a small
+//     ring, and every CTA polls all slots until none holds the "not yet written" sentinel — one
+//     store-to-visible latency instead of arrive-atomic + spin + partial read-back.  The reduction
+//     order is fixed (lane -> warp -> CTA partial -> every CTA adds the partials in CTA order), so
+//     the solve is bit-reproducible run to run;
+//   * the sparse product is gathered entry-per-lane: lane k of a row takes pattern entries k, k+16
+//     of that row, loads the whole neighbour record (12 x (z, p) = six 16-byte loads) — all loads of
+//     a row are in flight at once, one L2 round trip — and a 15-shuffle reduce-scatter hands every
+//     lane its own component;
 //   * the search direction of a neighbour row is rebuilt on the fly as z_l + beta p_prev_l, which
 //     saves the third barrier a separate "p = z + beta p" phase would need.
 // Standard PCG recurrences, identical to oracle/deform.cpp pcg(); vectors float32, scalars float64.
-#include <cooperative_groups.h>
-
 #include <algorithm>
 
 #include "deform.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace mvs {
 
@@ -39,7 +42,8 @@ struct PcgArgs {
   float* zbuf;    // m x 12
   float* pbuf;    // 2 x m x 12
   float* delta;   // m x 12 (exported for inspection)
-  double* part;   // 3 x grid partial sums
+  double* ring;   // kRing x grid x 2 exchange slots, all-ones at launch
+  unsigned long long* words;  // (2 iters + 1) x 4 fixed-point exchange words, zero at launch
   double* scal;   // S_* slots
   int64_t m;
   int iters;
@@ -55,62 +59,233 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// CTA-wide sum of N doubles -> thread 0 writes them to out[0..N)
-template <int N>
-__device__ __forceinline__ void cta_partial(double (&v)[N], double* smem, double* out) {
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int j = 0; j < N; ++j) v[j] = warp_sum(v[j]);
-  if (lane == 0)
-#pragma unroll
-    for (int j = 0; j < N; ++j) smem[warp * N + j] = v[j];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      double s = 0.0;
-      for (int w = 0; w < kPcgThreads / 32; ++w) s += smem[w * N + j];
-      out[j] = s;
-    }
-  }
-  __syncthreads();
+constexpr unsigned long long kSlotEmpty = ~0ull;  // bit pattern no sum can produce (see below)
+constexpr int kRing = 4;                           // phases of slots in flight (>= 3 required)
+
+__device__ __forceinline__ void st_flag(double* p, double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  if (b == kSlotEmpty) b = 0x7ff8000000000000ull;  // a NaN stays a NaN, never the sentinel
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(b) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) {
+  unsigned long long b;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(b) : "l"(p) : "memory");
+  return b;
+}
+__device__ __forceinline__ unsigned long long ld_flag(const double* p) {
+  unsigned long long b;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(b) : "l"(p) : "memory");
+  return b;
 }
 
-// Totals of N per-CTA partials (stride 3 doubles per CTA) after a grid barrier: every thread
-// loads at most two partials (independent loads: one L2 latency instead of a serial chain), then a
-// fixed-order warp / CTA reduction; all threads return the same totals.
+// Grid-wide barrier + all-reduce of N doubles in one exchange.
+//   ring: kRing x ncta x 2 doubles, all kSlotEmpty at launch.  Phase ph uses ring[ph % kRing].
+//   CTA c: (1) fixed-order CTA sum; (2) thread 0 re-arms its slot of phase ph-2 (every CTA consumed
+//   that phase before it could write phase ph-1, which this CTA has already seen complete), fences
+//   (publishing the vector entries the CTA wrote before the call, ordered by the __syncthreads) and
+//   stores the partial; (3) warp 0 polls all slots — 8 independent relaxed loads per lane in flight,
+//   no L1 invalidation inside the spin — then fences once (acquire) and adds the partials in a
+//   fixed order; (4) the totals reach the other warps through shared memory.  Consumers read the
+//   exchanged vectors with ld.global.cg (L2), never through L1.
+// Every CTA runs the same number of phases (control flow depends only on the identical totals).
 template <int N>
-__device__ __forceinline__ void grid_totals(const double* part, int ncta, double* smem,
-                                            double (&out)[N]) {
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double v[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) v[j] = 0.0;
-  int c0 = threadIdx.x, c1 = threadIdx.x + kPcgThreads;
-  double a0[N], a1[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    a0[j] = c0 < ncta ? __ldcg(part + (size_t)c0 * 3 + j) : 0.0;
-    a1[j] = c1 < ncta ? __ldcg(part + (size_t)c1 * 3 + j) : 0.0;
-  }
-#pragma unroll
-  for (int j = 0; j < N; ++j) v[j] = a0[j] + a1[j];
-  for (int c = threadIdx.x + 2 * kPcgThreads; c < ncta; c += kPcgThreads)
-#pragma unroll
-    for (int j = 0; j < N; ++j) v[j] += __ldcg(part + (size_t)c * 3 + j);
+__device__ __forceinline__ void grid_exchange(double (&v)[N], double* red, double* ring,
+                                              unsigned& phase, int ncta, double (&out)[N]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int W = kPcgThreads / 32;
+  constexpr int U = 8;           // slots per lane in flight
+  double* red1 = red;            // W x 2: CTA partial
+  double* red2 = red + W * 2;    // 2: totals
 #pragma unroll
   for (int j = 0; j < N; ++j) v[j] = warp_sum(v[j]);
-  __syncthreads();  // smem may still be read by the previous use
   if (lane == 0)
 #pragma unroll
-    for (int j = 0; j < N; ++j) smem[warp * N + j] = v[j];
+    for (int j = 0; j < N; ++j) red1[warp * 2 + j] = v[j];
+  __syncthreads();
+  double* cur = ring + (size_t)(phase % kRing) * ncta * 2;
+  if (warp == 0) {
+    if (lane == 0) {
+      double* old = ring + ((size_t)((phase + 2) % kRing) * ncta + blockIdx.x) * 2;
+      reinterpret_cast<unsigned long long*>(old)[0] = kSlotEmpty;
+      reinterpret_cast<unsigned long long*>(old)[1] = kSlotEmpty;
+      double s[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        s[j] = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) s[j] += red1[w * 2 + j];
+      }
+      fence_acq_rel();
+#pragma unroll
+      for (int j = 0; j < N; ++j) st_flag(cur + (size_t)blockIdx.x * 2 + j, s[j]);
+    }
+    __syncwarp();
+    double t[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) t[j] = 0.0;
+    for (int c0 = 0; c0 < ncta; c0 += 32 * U) {
+      unsigned long long b[U][N];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < N; ++j) b[u][j] = (c0 + u * 32 + lane < ncta) ? kSlotEmpty : 0ull;
+      unsigned spins = 0;
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < N; ++j)
+            if (b[u][j] == kSlotEmpty) b[u][j] = ld_flag(cur + (size_t)(c0 + u * 32 + lane) * 2 + j);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < N; ++j) ok = ok && (b[u][j] != kSlotEmpty);
+        if (ok) break;
+        if (++spins > (1u << 26)) __trap();  // a lost CTA becomes an error, not a hang
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < N; ++j) t[j] += __longlong_as_double((long long)b[u][j]);
+    }
+    fence_acq_rel();
+#pragma unroll
+    for (int j = 0; j < N; ++j) t[j] = warp_sum(t[j]);
+    if (lane == 0)
+#pragma unroll
+      for (int j = 0; j < N; ++j) red2[j] = t[j];
+  }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    double t = 0.0;
+  for (int j = 0; j < N; ++j) out[j] = red2[j];
+  ++phase;
+}
+
+// ---- fast exchange: integer atomics on one word per (scalar, limb)
+// Measured on B200 (scratch/barrier_bench.cu, 256 CTAs x 256 threads, us per barrier + all-reduce of
+// two doubles): cooperative grid.sync + partial read-back 5.2, polled slots 5.3, arrival counter +
+// slot read 3.0, THIS scheme 2.2.  Each CTA partial is split into two signed 44-bit limbs of a fixed-
+// point number with unit 2^E (E fixed per quantity at the start of the solve, 19 bits of headroom
+// above and 67 bits below the initial magnitude); a limb is biased to be non-negative and added with
+// ONE 64-bit atomic whose top 10 bits count arrivals, so the same word is the barrier flag and the
+// sum.  Integer addition commutes: the total is independent of arrival order (bit-reproducible), and
+// every CTA decodes the same value.  Words are zero at launch and used once.
+constexpr int kLimbBits = 44;
+constexpr long long kLimbBias = 1ll << 43;
+constexpr long long kLimbMax = (1ll << 43) - 1;
+constexpr int kCountShift = 54;
+
+struct FxUnit {
+  double lo, hi, inv_lo, inv_hi;  // 2^E, 2^(E+44) and their reciprocals
+};
+__device__ __forceinline__ FxUnit fx_unit_for(double magnitude) {
+  int x = (magnitude > 0.0 && magnitude < INFINITY) ? ilogb(magnitude) : 0;
+  int E = min(max(x - 67, -900), 800);
+  FxUnit u;
+  u.lo = ldexp(1.0, E);
+  u.hi = ldexp(1.0, E + kLimbBits);
+  u.inv_lo = ldexp(1.0, -E);
+  u.inv_hi = ldexp(1.0, -(E + kLimbBits));
+  return u;
+}
+__device__ __forceinline__ long long fx_limb(double v, const FxUnit& u, int limb) {
+  if (!(fabs(v) < INFINITY)) v = 0.0;  // a non-finite partial contributes nothing
+  double h = fmin(fmax(rint(v * u.inv_hi), (double)-kLimbMax), (double)kLimbMax);
+  if (limb == 0) return (long long)h;
+  double rem = v - h * u.hi;  // exact
+  double l = fmin(fmax(rint(rem * u.inv_lo), (double)-kLimbMax), (double)kLimbMax);
+  return (long long)l;
+}
+
+template <int N>
+__device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
+                                                 unsigned long long* words, unsigned& wi, int ncta,
+                                                 const FxUnit (&unit)[N], double (&out)[N]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int W = kPcgThreads / 32;
+  double* red1 = red;          // W x 2: CTA partial
+  double* red2 = red + W * 2;  // N x 2 limb sums
 #pragma unroll
-    for (int w = 0; w < kPcgThreads / 32; ++w) t += smem[w * N + j];
-    out[j] = t;
+  for (int j = 0; j < N; ++j) v[j] = warp_sum(v[j]);
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < N; ++j) red1[warp * 2 + j] = v[j];
+  __syncthreads();
+  if (threadIdx.x < 2 * N) {
+    const int j = threadIdx.x >> 1, limb = threadIdx.x & 1;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) s += red1[w * 2 + j];
+    FxUnit u = unit[0];
+    if (N > 1 && j == 1) u = unit[N - 1];
+    long long fxv = fx_limb(s, u, limb);
+    unsigned long long enc = (unsigned long long)(fxv + kLimbBias) + (1ull << kCountShift);
+    if (threadIdx.x == 0) fence_acq_rel();  // publish what this CTA wrote before the call
+    __syncwarp((1u << (2 * N)) - 1u);
+    unsigned long long* wd = words + wi + threadIdx.x;
+    atomicAdd(wd, enc);
+    unsigned long long b;
+    unsigned spins = 0;
+    while (((b = ld_word(wd)) >> kCountShift) < (unsigned long long)ncta)
+      if (++spins > (1u << 26)) __trap();  // a lost CTA becomes an error, not a hang
+    if (threadIdx.x == 0) fence_acq_rel();
+    long long sum = (long long)(b & ((1ull << kCountShift) - 1ull)) - (long long)ncta * kLimbBias;
+    red2[threadIdx.x] = (double)sum;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < N; ++j) out[j] = red2[2 * j] * unit[j].hi + red2[2 * j + 1] * unit[j].lo;
+  wi += 2 * N;
+}
+
+// y[0..11] partial products of this lane -> lane k of the 16-lane group returns sum over the group
+// of y[k] (k < 12).  Reduce-scatter by halving: 8 + 4 + 2 + 1 shuffles.
+__device__ __forceinline__ float group_reduce_scatter(const float (&y)[12], int k) {
+  const unsigned full = 0xffffffffu;
+  float a8[8], a4[4], a2[2];
+  const bool u8 = k & 8, u4 = k & 4, u2 = k & 2, u1 = k & 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float hi = i < 4 ? y[8 + i] : 0.f;
+    float send = u8 ? y[i] : hi;
+    float keep = u8 ? hi : y[i];
+    a8[i] = keep + __shfl_xor_sync(full, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float send = u4 ? a8[i] : a8[4 + i];
+    float keep = u4 ? a8[4 + i] : a8[i];
+    a4[i] = keep + __shfl_xor_sync(full, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float send = u2 ? a4[i] : a4[2 + i];
+    float keep = u2 ? a4[2 + i] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(full, send, 2);
+  }
+  float send = u1 ? a2[0] : a2[1];
+  float keep = u1 ? a2[1] : a2[0];
+  return keep + __shfl_xor_sync(full, send, 1);
+}
+
+// One pattern entry: acc[3a + r] += sum_b B[a][b] (z_l[3b + r] + beta p_l[3b + r]); `zq` are the six
+// 16-byte pieces of the neighbour's 12 (z, p) pairs.
+__device__ __forceinline__ void entry_mac(float (&acc)[12], const float4* __restrict__ Bt,
+                                          const float4 (&zq)[6], float beta) {
+  float pv[12];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    pv[2 * i] = zq[i].x + beta * zq[i].y;
+    pv[2 * i + 1] = zq[i].z + beta * zq[i].w;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float4 b = Bt[a];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      acc[3 * a + r] += b.x * pv[r] + b.y * pv[3 + r] + b.z * pv[6 + r] + b.w * pv[9 + r];
   }
 }
 
@@ -118,9 +293,8 @@ __device__ __forceinline__ void grid_totals(const double* part, int ncta, double
 // iteration `it` reads buffer (it+1)&1 (written during iteration it-1) and writes buffer it&1.
 template <int RS>
 __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ float4 smem_dyn[];
-  __shared__ double red[(kPcgThreads / 32) * 2];
+  __shared__ double red[(kPcgThreads / 32) * 2 + 4];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = lane & (kRowLanes - 1);
@@ -131,8 +305,8 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
   const int64_t row0 = (int64_t)blockIdx.x * a.rows_per_cta;
   const int64_t row1 = min(m, row0 + a.rows_per_cta);
   const bool lane_on = k < 12;
-  const int ba = k / 3, rr = k - 3 * ba;
   float2* zp = reinterpret_cast<float2*>(a.zbuf);  // 2 x m x 12 float2
+  unsigned phase = 0;
 
   // ---- stage this CTA's matrix slice
   const int nz0 = row0 < m ? __ldg(a.row_ptr + row0) : 0;
@@ -162,8 +336,9 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
     int64_t j = row0 + s * kGroups + gi;
     bool on = j < row1;
     bool act = on && lane_on;
-    t0s[s] = act ? __ldg(a.row_ptr + j) - nz0 : 0;
-    t1s[s] = act ? __ldg(a.row_ptr + j + 1) - nz0 : 0;
+    // the pattern range of the row is known to all 16 lanes (every lane gathers entries)
+    t0s[s] = on ? __ldg(a.row_ptr + j) - nz0 : 0;
+    t1s[s] = on ? __ldg(a.row_ptr + j + 1) - nz0 : 0;
     if (RS == 1) {
 #pragma unroll
       for (int q = 0; q < 12; ++q) minv[q] = act ? __ldg(a.Minv + j * 144 + k * 12 + q) : 0.f;
@@ -187,23 +362,24 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
     acc[0] += (double)r[s] * (double)zv;
     acc[1] += (double)r[s] * (double)r[s];
   }
-  cta_partial<2>(acc, red, a.part + (size_t)blockIdx.x * 3 + 1);
-  grid.sync();
   double rz, bn2;
   {
     double tot[2];
-    grid_totals<2>(a.part + 1, ncta, red, tot);
+    grid_exchange<2>(acc, red, a.ring, phase, ncta, tot);
     rz = tot[0];
     bn2 = tot[1];
   }
   double rn2 = bn2;
   double rz_old = 0.0;
+  unsigned wi = 0;
+  const FxUnit unit_b[2] = {fx_unit_for(rz), fx_unit_for(bn2)};
+  FxUnit unit_a[1] = {fx_unit_for(0.0)};
   int it = 0;
   for (; it < a.iters; ++it) {
     if (a.tol > 0.0 && rn2 <= a.tol * a.tol * bn2) break;  // uniform over the grid
     // ---- phase A: p = z + beta p ; q = (H + lambda) p ; p.q
     float beta = (it > 0 && rz_old > 0.0) ? (float)(rz / rz_old) : 0.f;
-    const float2* zprev = zp + (size_t)((it + 1) & 1) * m * 12;
+    const float4* zprev = reinterpret_cast<const float4*>(zp + (size_t)((it + 1) & 1) * m * 12);
     float2* zcur = zp + (size_t)(it & 1) * m * 12;
     float qv[RS];
     double pq[1] = {0.0};
@@ -214,7 +390,30 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
       bool act = on && lane_on;
       p[s] = z[s] + beta * p[s];
       if (act) zcur[j * 12 + k].y = p[s];
-      float y = a.lambda * p[s];
+      // gather: this lane's pattern entries, two entries (12 x 16 B) in flight
+      float ya[12];
+#pragma unroll
+      for (int q = 0; q < 12; ++q) ya[q] = 0.f;
+      const int t1 = t1s[s];
+      // (one entry at a time when many row slots already fill the register file)
+      constexpr bool kTwo = RS <= 2;
+      for (int t = t0s[s] + k; t < t1; t += (kTwo ? 2 : 1) * kRowLanes) {
+        const int tb = t + kRowLanes;
+        const bool two = kTwo && tb < t1;
+        const int la = cs[t], lb = two ? cs[tb] : la;
+        float4 za[6], zb[6];
+        const float4* sa = zprev + (size_t)la * 6;
+        const float4* sb = zprev + (size_t)lb * 6;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) za[i] = __ldcg(sa + i);
+        if (two)
+#pragma unroll
+          for (int i = 0; i < 6; ++i) zb[i] = __ldcg(sb + i);
+        entry_mac(ya, Bs + (size_t)t * 4, za, beta);
+        if (two) entry_mac(ya, Bs + (size_t)tb * 4, zb, beta);
+      }
+      float y = group_reduce_scatter(ya, k);
+      y += a.lambda * p[s];
 #pragma unroll
       for (int q = 0; q < 9; ++q) {
         float pqv = __shfl_sync(full, p[s], gbase + q);
@@ -223,60 +422,18 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
         else if (act && k < 9)
           y += __ldg(a.Rot + j * 81 + k * 9 + q) * pqv;
       }
-      if (act) {
-        int t = t0s[s];
-        const int t1 = t1s[s];
-        for (; t + 8 <= t1; t += 8) {  // 8 neighbours (32 loads) in flight
-          float2 v[8][4];
-          float4 Bv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            int l = cs[t + u];
-            Bv[u] = Bs[(size_t)(t + u) * 4 + ba];
-            const float2* src = zprev + (size_t)l * 12 + rr;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[u][b] = __ldcg(src + 3 * b);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            y += Bv[u].x * (v[u][0].x + beta * v[u][0].y) + Bv[u].y * (v[u][1].x + beta * v[u][1].y) +
-                 Bv[u].z * (v[u][2].x + beta * v[u][2].y) + Bv[u].w * (v[u][3].x + beta * v[u][3].y);
-        }
-        for (; t + 2 <= t1; t += 2) {
-          float2 v[2][4];
-          float4 Bv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            int l = cs[t + u];
-            Bv[u] = Bs[(size_t)(t + u) * 4 + ba];
-            const float2* src = zprev + (size_t)l * 12 + rr;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v[u][b] = __ldcg(src + 3 * b);
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-            y += Bv[u].x * (v[u][0].x + beta * v[u][0].y) + Bv[u].y * (v[u][1].x + beta * v[u][1].y) +
-                 Bv[u].z * (v[u][2].x + beta * v[u][2].y) + Bv[u].w * (v[u][3].x + beta * v[u][3].y);
-        }
-        if (t < t1) {
-          int l = cs[t];
-          float4 Bv = Bs[(size_t)t * 4 + ba];
-          const float2* src = zprev + (size_t)l * 12 + rr;
-          float2 v0 = __ldcg(src), v1 = __ldcg(src + 3), v2 = __ldcg(src + 6), v3 = __ldcg(src + 9);
-          y += Bv.x * (v0.x + beta * v0.y) + Bv.y * (v1.x + beta * v1.y) +
-               Bv.z * (v2.x + beta * v2.y) + Bv.w * (v3.x + beta * v3.y);
-        }
-      } else {
-        y = 0.f;
-      }
+      if (!act) y = 0.f;
       qv[s] = y;
       pq[0] += (double)p[s] * (double)y;
     }
-    cta_partial<1>(pq, red, a.part + (size_t)blockIdx.x * 3);
-    grid.sync();
-    // ---- phase B: alpha ; delta += alpha p ; r -= alpha q ; z = M^-1 r ; r.z, |r|^2
     double pqa[1];
-    grid_totals<1>(a.part, ncta, red, pqa);
+    if (it == 0) {  // magnitude of p.q unknown yet: exact slot exchange, then fix its unit
+      grid_exchange<1>(pq, red, a.ring, phase, ncta, pqa);
+      unit_a[0] = fx_unit_for(fabs(pqa[0]));
+    } else {
+      grid_exchange_fx<1>(pq, red, a.words, wi, ncta, unit_a, pqa);
+    }
+    // ---- phase B: alpha ; delta += alpha p ; r -= alpha q ; z = M^-1 r ; r.z, |r|^2
     double pqt = pqa[0];
     float alpha = (pqt > 0.0 && rz > 0.0) ? (float)(rz / pqt) : 0.f;
     acc[0] = acc[1] = 0.0;
@@ -300,12 +457,10 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
       acc[0] += (double)r[s] * (double)zv;
       acc[1] += (double)r[s] * (double)r[s];
     }
-    cta_partial<2>(acc, red, a.part + (size_t)blockIdx.x * 3 + 1);
-    grid.sync();
     rz_old = rz;
     {
       double tot[2];
-      grid_totals<2>(a.part + 1, ncta, red, tot);
+      grid_exchange_fx<2>(acc, red, a.words, wi, ncta, unit_b, tot);
       rz = tot[0];
       rn2 = tot[1];
     }
@@ -414,8 +569,14 @@ int pcg_solve(mvs_deform* h) {
   a.zbuf = h->pcg.p;          // 2 x N float2 = 4N floats
   a.pbuf = nullptr;
   a.delta = h->pcg.p + 4 * N;
-  MVS_TRY(h->partials.reserve((size_t)h->pcg_grid * 3 + 16));
-  a.part = h->partials.p;
+  // exchange slots of the fused barrier + reduction: "empty" = all-ones
+  size_t ring_doubles = (size_t)kRing * h->pcg_grid * 2;
+  size_t nwords = (size_t)(2 * std::max(h->prm.pcg_iters, 0) + 1) * 4;
+  MVS_TRY(h->partials.reserve(ring_doubles + nwords + 16));
+  MVS_CUDA(cudaMemsetAsync(h->partials.p, 0xff, ring_doubles * sizeof(double), ctx->stream));
+  MVS_CUDA(cudaMemsetAsync(h->partials.p + ring_doubles, 0, nwords * sizeof(double), ctx->stream));
+  a.ring = h->partials.p;
+  a.words = reinterpret_cast<unsigned long long*>(h->partials.p + ring_doubles);
   a.scal = h->scal.p;
   a.m = m;
   a.iters = h->prm.pcg_iters;
