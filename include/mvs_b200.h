@@ -269,6 +269,28 @@ int mvs_deform_run(mvs_deform* h, double proj_len_err, double proj_dist_err,
                    const mvs_gn_params* params);
 /* [ref: Deformation/Deformation.h:237-240 Deform(tpts,tnormals,threshold)] */
 int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_params* params);
+/* As-rigid-as-possible mode of Deform(): the solver the reference actually runs, CGAL 4.6
+ * Surface_mesh_deformation [ref: Deformation/Deformation.cpp:256-260 insert_roi_vertices(all),
+ * :383-392 every sampled node a control vertex, :393 preprocess(), :398 deform(5, 1e-4), :400
+ * overwrite_initial_geometry()].  CGAL is not vendored: the published algorithm (Sorkine & Alexa
+ * 2007; local rotations + cotangent-Laplacian global solve) is restated, parity with CGAL's own
+ * floating point unpinned.  The global solve is Jacobi-preconditioned CG on the device. */
+typedef struct mvs_arap_params {
+  int32_t iters;     /* local/global iterations, reference: 5 */
+  int32_t cg_iters;  /* CG iterations per global step (upper bound when cg_tol > 0) */
+  double tol;        /* stop when |E_prev - E| <= tol * E, reference: 1e-4; 0 = run all iters */
+  double cg_tol;     /* relative residual stop of the global solve; 0 = run exactly cg_iters */
+} mvs_arap_params;
+int mvs_arap_default_params(mvs_arap_params* p);
+/* control vertices = the sampled nodes (mvs_deform_get_nodes order) moved to ctrl_xyz (m x 3);
+ * result readable with mvs_deform_get_vertices/normals; energy / iterations_run may be NULL. */
+int mvs_deform_arap(mvs_deform* h, const double* ctrl_xyz, const mvs_arap_params* params,
+                    double* energy, int32_t* iterations_run);
+/* [ref: Deformation/Deformation.h:241-245 Deform(tpts,tnormals,projLenErr,projDistErr)] node
+ * correspondences + smoothing (Deformation.cpp:266-381), then the ARAP solve, then
+ * overwrite_initial_geometry (the deformed mesh becomes the rest mesh). */
+int mvs_deform_run_arap(mvs_deform* h, double proj_len_err, double proj_dist_err,
+                        const mvs_arap_params* params);
 /* One Gauss-Newton iteration on device-resident state (bench "step"). */
 int mvs_deform_gn_begin(mvs_deform* h, const mvs_gn_params* params);
 int mvs_deform_gn_step(mvs_deform* h);

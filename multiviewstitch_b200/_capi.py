@@ -51,6 +51,12 @@ class GNParams(C.Structure):
                 ("max_corr_dist2", C.c_double), ("min_corr_cos", C.c_double)]
 
 
+class ArapParams(C.Structure):
+    """mvs_arap_params [ref: Deformation/Deformation.cpp:398 deform(5, 1e-4)]"""
+    _fields_ = [("iters", C.c_int32), ("cg_iters", C.c_int32), ("tol", C.c_double),
+                ("cg_tol", C.c_double)]
+
+
 def declared_symbols() -> list[str]:
     """Every function the header declares (used by the symbol-export test)."""
     txt = HEADER.read_text()

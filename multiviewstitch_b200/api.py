@@ -12,7 +12,8 @@ import ctypes as C
 
 import numpy as np
 
-from ._capi import AlignParams, Camera, GNParams, MvsError, OutlierParams, check, lib  # noqa: F401
+from ._capi import (AlignParams, ArapParams, Camera, GNParams, MvsError, OutlierParams,  # noqa: F401
+                    check, lib)
 
 
 def _f32(a):
@@ -340,6 +341,17 @@ def gn_params(**kw) -> GNParams:
     return p
 
 
+def arap_params(**kw) -> ArapParams:
+    """mvs_arap_params with the library defaults (5 iterations, tolerance 1e-4), overridden by keyword."""
+    p = ArapParams()
+    check(lib().mvs_arap_default_params(C.byref(p)))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown ARAP parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
 class Deformation:
     """[ref: Deformation/Deformation.h:224-252]  Deformation(points, normals, facets);
     UniformSampling(); Deform(tpts, tnormals, projLenErr, projDistErr) / Deform(tpts, tnormals,
@@ -463,6 +475,27 @@ class Deformation:
         else:
             raise TypeError("Deform(tpts, tnormals, threshold) or Deform(tpts, tnormals, "
                             "projLenErr, projDistErr)")
+
+    def DeformARAP(self, tpts, tnormals, projLenErr=100.0, projDistErr=100.0,
+                   params: ArapParams | None = None):
+        """Deform(tpts, tnormals, projLenErr, projDistErr) with the as-rigid-as-possible solver the
+        reference runs through CGAL [ref: Deformation.cpp:232-402, CGAL calls :256-260, :383-400]."""
+        if tpts is not None:
+            self.SetTarget(tpts, tnormals)
+        pp = C.byref(params) if params is not None else None
+        check(lib().mvs_deform_run_arap(self._h, C.c_double(projLenErr), C.c_double(projDistErr), pp))
+
+    def ARAP(self, control_xyz, params: ArapParams | None = None):
+        """ARAP solve with the sampled nodes as control vertices moved to control_xyz (m x 3);
+        returns (energy, iterations run).  Vertices()/Normals() hold the result."""
+        c = _f64(control_xyz).reshape(-1, 3)
+        if len(c) != len(self.Nodes()):
+            raise ValueError("control_xyz must have one row per node")
+        e = C.c_double(0.0)
+        it = C.c_int32(0)
+        pp = C.byref(params) if params is not None else None
+        check(lib().mvs_deform_arap(self._h, _ptr(c, C.c_double), pp, C.byref(e), C.byref(it)))
+        return e.value, it.value
 
     def GNBegin(self, params: GNParams):
         check(lib().mvs_deform_gn_begin(self._h, C.byref(params)))

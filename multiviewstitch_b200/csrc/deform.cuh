@@ -21,6 +21,11 @@
 #include "common.cuh"
 #include "nn_grid.cuh"
 
+namespace mvs {
+struct ArapState;  // arap.cu
+void arap_free(ArapState* a);
+}  // namespace mvs
+
 struct mvs_deform {
   mvs_ctx* ctx = nullptr;
   int64_t n = 0, nf = 0, m = 0;
@@ -96,6 +101,8 @@ struct mvs_deform {
   bool gn_active = false;
   int64_t v_begin = 0, v_end = -1;  // shard of sorted positions owned by this rank
   double energy[3] = {0, 0, 0};
+  // as-rigid-as-possible solver state (arap.cu), built on first use
+  mvs::ArapState* arap = nullptr;
 
   float* B() { return sys.p; }
   // rhs before Rot: m*81 floats would break the 16-byte alignment the vector reductions need
@@ -130,6 +137,11 @@ int gn_assemble(mvs_deform* h);                 // zero + fit pass (+ allreduce)
 int gn_apply_update(mvs_deform* h);             // x += delta
 int gn_final_vertices(mvs_deform* h);           // cur0 / curn0 in original order
 int gn_energy(mvs_deform* h, double energy[3]); // at the current state with the current resid
+int gn_recompute_normals(mvs_deform* h);        // curn0 from cur0 + facets (Deformation.h:86-128)
+
+// arap.cu
+int arap_solve(mvs_deform* h, const double* ctrl_xyz_host, const int32_t* ctrl_ids_host, int64_t m,
+               const mvs_arap_params* prm, double* energy_out, int* iters_out);
 
 // pcg.cu
 int pcg_solve(mvs_deform* h);

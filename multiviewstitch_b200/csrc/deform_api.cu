@@ -152,6 +152,10 @@ static int bake(mvs_deform* h) {
                              ctx->stream));
   h->graph_built = false;  // rebuilt lazily from the new rest geometry
   h->have_targets = false;
+  if (h->arap) {  // cotangent weights belong to the old rest geometry
+    arap_free(h->arap);
+    h->arap = nullptr;
+  }
   if (h->m > 0) {
     std::vector<int32_t> ids = h->node_ids;
     MVS_TRY(mvs_deform_set_nodes(h, ids.data(), (int64_t)ids.size()));
@@ -294,6 +298,7 @@ int mvs_deform_destroy(mvs_deform* h) {
   cudaStreamSynchronize(h->ctx->stream);
   if (h->node_index) mvs_nn_index_destroy(h->node_index);
   if (h->tgt_index) mvs_nn_index_destroy(h->tgt_index);
+  if (h->arap) arap_free(h->arap);
   mvs_ctx* ctx = h->ctx;
   delete h;
   ctx_release(ctx);
@@ -509,6 +514,68 @@ int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_param
   for (int it = 0; it < p.gn_iters; ++it) MVS_TRY(gn_step_impl(h));
   MVS_TRY(gn_final_vertices(h));
   h->gn_active = false;
+  MVS_TRY(bake(h));
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_arap_default_params(mvs_arap_params* p) {
+  if (!p) return MVS_ERR_INVALID_ARG;
+  p->iters = 5;       // Deformation.cpp:398 deform(5, 1e-4)
+  p->cg_iters = 400;
+  p->tol = 1e-4;
+  p->cg_tol = 1e-6;
+  return MVS_OK;
+}
+
+static int validate_arap(const mvs_arap_params* p) {
+  if (p->iters < 1 || p->cg_iters < 1 || !(p->tol >= 0.0) || !(p->cg_tol >= 0.0)) {
+    set_error("arap params: iters and cg_iters must be >= 1, tolerances >= 0");
+    return MVS_ERR_INVALID_ARG;
+  }
+  return MVS_OK;
+}
+
+int mvs_deform_arap(mvs_deform* h, const double* ctrl_xyz, const mvs_arap_params* params,
+                    double* energy, int32_t* iterations_run) {
+  MVS_REQUIRE(h, "null handle");
+  mvs_arap_params def;
+  if (!params) {
+    mvs_arap_default_params(&def);
+    params = &def;
+  }
+  MVS_TRY(validate_arap(params));
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  if (h->m <= 0 || !ctrl_xyz) {
+    set_error("arap: no control vertices (sample nodes first and pass their target positions)");
+    return MVS_ERR_STATE;
+  }
+  int it = 0;
+  MVS_TRY(arap_solve(h, ctrl_xyz, h->node_ids.data(), h->m, params, energy, &it));
+  if (iterations_run) *iterations_run = it;
+  MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_deform_run_arap(mvs_deform* h, double proj_len_err, double proj_dist_err,
+                        const mvs_arap_params* params) {
+  MVS_REQUIRE(h, "null handle");
+  mvs_arap_params def;
+  if (!params) {
+    mvs_arap_default_params(&def);
+    params = &def;
+  }
+  MVS_TRY(validate_arap(params));
+  mvs_ctx* ctx = h->ctx;
+  MVS_TRY(ctx_ensure_device(ctx));
+  MVS_TRY(ensure_graph(h));
+  DevBuf<double> c;
+  DevBuf<int> v;
+  // Deformation.cpp:266-381; every node becomes a control vertex, valid or not (:384 commented)
+  MVS_TRY(deform_node_targets(h, proj_len_err, proj_dist_err, 2, c, v));
+  std::vector<double> ctrl((size_t)h->m * 3);
+  MVS_TRY(d2h_sync(ctx, ctrl.data(), c.p, sizeof(double) * 3 * h->m));
+  MVS_TRY(arap_solve(h, ctrl.data(), h->node_ids.data(), h->m, params, nullptr, nullptr));
   MVS_TRY(bake(h));
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   return MVS_OK;

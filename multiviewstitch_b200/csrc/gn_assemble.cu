@@ -721,6 +721,13 @@ int gn_final_vertices(mvs_deform* h) {
     k_deform_final<<<div_up(n, 256), 256, 0, st>>>(h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p,
                                                    h->perm.p, n, h->cur0.p);
   }
+  return gn_recompute_normals(h);
+}
+
+int gn_recompute_normals(mvs_deform* h) {
+  mvs_ctx* ctx = h->ctx;
+  cudaStream_t st = ctx->stream;
+  int64_t n = h->n;
   MVS_CUDA(cudaMemsetAsync(h->curn0.p, 0, sizeof(float4) * n, st));
   if (h->nf > 0) {
     ProfScope ps(ctx, "vertex_normals", 2);

@@ -63,7 +63,7 @@ def lib():
         _lib.orc_srt_residual.restype = C.c_double
         _lib.orc_srt_scale.restype = C.c_double
         _lib.orc_srt_ransac.restype = C.c_double
-        for name in ("orc_uniform_sampling", "orc_sample_fps"):
+        for name in ("orc_uniform_sampling", "orc_sample_fps", "orc_cot_weights"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = C.c_int64
     return _lib
@@ -448,3 +448,35 @@ def check_consistency(depth, cam, ref_depths, ref_cams, min_dsp, max_dsp, reproj
                                 C.c_int(len(ref_cams)), C.c_double(min_dsp), C.c_double(max_dsp),
                                 C.c_double(reproj_err))
     return d
+
+
+# ----------------------------------------------------------------------------- ARAP
+def arap(pts, facets, ctrl_ids, ctrl_xyz, iters=5, tol=1e-4, cg_iters=400, cg_tol=1e-6):
+    """oracle/arap.cpp orc_arap: returns (deformed n x 3 float64, energy, iterations run)."""
+    pts = _f32(pts).reshape(-1, 3)
+    facets = _i32(facets).reshape(-1, 3)
+    ctrl_ids = _i32(ctrl_ids)
+    ctrl_xyz = _f64(ctrl_xyz).reshape(-1, 3)
+    out = np.empty((len(pts), 3), np.float64)
+    e = C.c_double(0.0)
+    it = C.c_int32(0)
+    lib().orc_arap(_p(pts, C.c_float), C.c_int64(len(pts)), _p(facets, C.c_int32),
+                   C.c_int64(len(facets)), _p(ctrl_ids, C.c_int32), _p(ctrl_xyz, C.c_double),
+                   C.c_int64(len(ctrl_ids)), C.c_int(iters), C.c_double(tol), C.c_int(cg_iters),
+                   C.c_double(cg_tol), _p(out, C.c_double), C.byref(e), C.byref(it))
+    return out, e.value, it.value
+
+
+def cot_weights(pts, facets):
+    """cotangent Laplacian of oracle/arap.cpp as (row_ptr, col, w)."""
+    pts = _f32(pts).reshape(-1, 3)
+    facets = _i32(facets).reshape(-1, 3)
+    n = len(pts)
+    cap = 6 * len(facets) + 1
+    rp = np.empty(n + 1, np.int32)
+    col = np.empty(cap, np.int32)
+    w = np.empty(cap, np.float64)
+    nnz = lib().orc_cot_weights(_p(pts, C.c_float), C.c_int64(n), _p(facets, C.c_int32),
+                                C.c_int64(len(facets)), _p(rp, C.c_int32), _p(col, C.c_int32),
+                                _p(w, C.c_double), C.c_int64(cap))
+    return rp, col[:nnz], w[:nnz]
