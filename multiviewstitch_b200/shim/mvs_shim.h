@@ -213,11 +213,18 @@ class Alignment {
 // [ref: Deformation/Deformation.h:224-252]
 class Deformation {
  public:
+  // Solver behind Deform(tpts, tnormals, projLenErr, projDistErr): the embedded-deformation
+  // Gauss-Newton loop (north_star) or the as-rigid-as-possible solver the reference runs through
+  // CGAL (Deformation.cpp:383-400; deform(5, 1e-4)).
+  enum Solver { GAUSS_NEWTON, ARAP };
+  Solver solver = GAUSS_NEWTON;
   mvs_gn_params gn;
+  mvs_arap_params arap;
   Deformation(const std::vector<Vector3d>& points_, const std::vector<Vector3d>& normals_,
               const std::vector<int>& facets_)
       : n_(points_.size()) {
     check(mvs_gn_default_params(&gn));
+    check(mvs_arap_default_params(&arap));
     check(mvs_deform_create(context(), points_[0].data(),
                             normals_.empty() ? nullptr : normals_[0].data(), (int64_t)points_.size(),
                             facets_.data(), (int64_t)facets_.size() / 3, &h_));
@@ -240,7 +247,10 @@ class Deformation {
   void Deform(const std::vector<Vector3d>& tpts, const std::vector<Vector3d>& tnormals,
               double projLenErr, double projDistErr) {
     set_target(tpts, tnormals);
-    check(mvs_deform_run(h_, projLenErr, projDistErr, &gn));
+    if (solver == ARAP)
+      check(mvs_deform_run_arap(h_, projLenErr, projDistErr, &arap));
+    else
+      check(mvs_deform_run(h_, projLenErr, projDistErr, &gn));
   }
   // replace CGAL's Polyhedron() accessor (Deformation.h:233)
   std::vector<Vector3d> Vertices() const {

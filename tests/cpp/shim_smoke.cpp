@@ -90,6 +90,16 @@ int main() {
     rmean /= out.size();
     std::printf("deformed mean radius %.4f (template 1.00, target 1.06)\n", rmean);
     if (!(rmean > 1.03 && rmean < 1.07)) return 1;
+    // the same call with the solver the reference runs through CGAL (as-rigid-as-possible)
+    Deformation deform2(pts, nrm, facets);
+    deform2.solver = Deformation::ARAP;
+    deform2.Deform(tgt, tn, 100.0, 100.0);
+    auto out2 = deform2.Vertices();
+    double rmean2 = 0;
+    for (auto& p : out2) rmean2 += std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    rmean2 /= out2.size();
+    std::printf("ARAP deformed mean radius %.4f\n", rmean2);
+    if (!(rmean2 > 1.03 && rmean2 < 1.07)) return 1;
     // ---- Model2Depth: fronto-parallel plane renders 1/z
     std::vector<Vector3d> plane = {Vector3d(-10, -10, 4), Vector3d(10, -10, 4), Vector3d(10, 10, 4), Vector3d(-10, 10, 4)};
     Model2Depth::SetInput({plane}, {{}}, {{0, 1, 2, 0, 2, 3}}, {{cam}}, {""});

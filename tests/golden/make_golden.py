@@ -23,7 +23,23 @@ def cams(mod):
     return mod.make_camera(K, R1, t1, w, h), mod.make_camera(K, R2, t2, w, h)
 
 
+def arap_golden():
+    """ARAP mode of Deform() (oracle/arap.cpp): nodes of a sphere mesh as control vertices moved by
+    a rotation, an anisotropic scale and noise; 4 local/global iterations x 300 CG iterations."""
+    rng = np.random.default_rng(77)
+    verts, faces = synth.uv_sphere(36, 26)
+    pts = verts.astype(np.float32)
+    ids = oracle.sample_fps(pts, 30, 0)
+    R = synth.axis_angle([0.2, 1.0, 0.3], 0.35)
+    ctrl = (pts[ids].astype(np.float64) * np.array([1.08, 0.95, 1.02])) @ R.T + 0.02 * rng.normal(size=(30, 3))
+    out, energy, it = oracle.arap(pts, faces, ids, ctrl, iters=4, tol=0.0, cg_iters=300, cg_tol=0.0)
+    rp, col, w = oracle.cot_weights(pts, faces)
+    np.savez(OUT / "arap.npz", pts=pts, faces=faces.astype(np.int32), ids=ids, ctrl=ctrl, out=out,
+             energy=energy, row_ptr=rp, col=col, w=w)
+
+
 def main():
+    arap_golden()
     rng = np.random.default_rng(2024)
     # ---- exact kNN
     t = rng.normal(size=(400, 3)).astype(np.float32)

@@ -21,6 +21,15 @@ def _m2d_cams(mod, g):
 
 
 # ------------------------------------------------------------------ CPU: oracle vs golden
+def test_oracle_arap_golden():
+    g = np.load(G / "arap.npz")
+    rp, col, w = oracle.cot_weights(g["pts"], g["faces"])
+    assert np.array_equal(rp, g["row_ptr"]) and np.array_equal(col, g["col"]) and np.array_equal(w, g["w"])
+    out, energy, it = oracle.arap(g["pts"], g["faces"], g["ids"], g["ctrl"], iters=4, tol=0.0,
+                                  cg_iters=300, cg_tol=0.0)
+    assert it == 4 and np.array_equal(out, g["out"]) and energy == g["energy"]
+
+
 def test_oracle_knn_golden():
     g = np.load(G / "knn.npz")
     for method in ("brute", "kdtree"):
@@ -113,6 +122,20 @@ def test_gpu_deform_golden(ctx):
         d.GNStep()
     d.GNEnd()
     assert np.abs(d.Vertices() - g["out_nn"]).max() <= 1e-4 * diag
+
+
+@pytest.mark.gpu
+def test_gpu_arap_golden(ctx):
+    from multiviewstitch_b200 import api
+    g = np.load(G / "arap.npz")
+    pts = g["pts"]
+    diag = float(np.linalg.norm(pts.max(0) - pts.min(0)))
+    d = api.Deformation(pts, None, g["faces"], ctx)
+    assert np.array_equal(d.SampleFPS(30, 0), g["ids"])
+    e, it = d.ARAP(g["ctrl"], api.arap_params(iters=4, tol=0.0, cg_iters=300, cg_tol=0.0))
+    assert it == 4
+    assert np.abs(d.Vertices() - g["out"]).max() <= 1e-4 * diag
+    assert abs(e - float(g["energy"])) <= 1e-3 * float(g["energy"])
 
 
 @pytest.mark.gpu
