@@ -57,7 +57,8 @@ struct mvs_deform {
   size_t pcg_smem = 0;
   mvs::DevBuf<float> sys;
   // order-independent accumulation: J^T J / J^T r are summed as 64-bit fixed point (integer atomics
-  // commute exactly), then converted to the float32 system above; layout [B: nnz x 16 | rhs: m x 12]
+  // commute exactly), then converted to the float32 system above; only the upper triangle of the
+  // block pattern is stored: layout [U: nup x 16 | rhs: m x 12]
   mvs::DevBuf<long long> sys64;
   double fx_scale = 1.0;   // power of two, set per solve from the magnitude bound
   double diag2 = 1.0;      // squared bbox diagonal of the rest mesh
@@ -74,7 +75,9 @@ struct mvs_deform {
   mvs::DevBuf<int> grp_n;               // ngroups: distinct accumulators of the group
   mvs::DevBuf<int> grp_dst;             // ngroups x kGrpMax: first sys64 element of each accumulator
   mvs::DevBuf<int> tslot;               // nnz: pattern slot of the transposed block
+  mvs::DevBuf<int> uidx;                // nnz: index of the block (or of its transpose) in sys64
   int64_t ngroups = 0;
+  int64_t nup = 0;                      // upper-triangle blocks, diagonal included
   mvs::DevBuf<float> Minv;  // m x 144
   mvs::DevBuf<float> x;     // m x 12
   mvs::DevBuf<float> pcg;   // r, z, p0, p1, q, delta : 6 x m x 12
@@ -109,9 +112,9 @@ struct mvs_deform {
   float* rhs() { return sys.p + (size_t)nnz * 16; }
   float* Rot() { return sys.p + (size_t)nnz * 16 + (size_t)m * 12; }
   size_t sys_floats() const { return (size_t)nnz * 16 + (size_t)m * 81 + (size_t)m * 12; }
-  size_t sys64_count() const { return (size_t)nnz * 16 + (size_t)m * 12; }
+  size_t sys64_count() const { return (size_t)nup * 16 + (size_t)m * 12; }
   long long* B64() { return sys64.p; }
-  long long* rhs64() { return sys64.p + (size_t)nnz * 16; }
+  long long* rhs64() { return sys64.p + (size_t)nup * 16; }
   int64_t shard_begin() const { return v_begin; }
   int64_t shard_end() const { return v_end < 0 ? n : v_end; }
 };

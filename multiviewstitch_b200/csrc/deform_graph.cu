@@ -361,8 +361,9 @@ __constant__ int c_tile_b[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
 
 // One thread per assembly group: the distinct destinations (first sys64 element) of the group's
 // tiles and, per run, the group-local accumulator index of each tile (255 = no destination).
-__global__ void k_group_table(const int* __restrict__ run_slots, int64_t nruns, int64_t nnz,
-                              int64_t ngroups, int* __restrict__ grp_n, int* __restrict__ grp_dst,
+__global__ void k_group_table(const int* __restrict__ run_slots, int64_t nruns,
+                              const int* __restrict__ uidx, int64_t nup, int64_t ngroups,
+                              int* __restrict__ grp_n, int* __restrict__ grp_dst,
                               unsigned char* __restrict__ run_local) {
   int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (q >= ngroups) return;
@@ -375,10 +376,10 @@ __global__ void k_group_table(const int* __restrict__ run_slots, int64_t nruns, 
       int d;
       if (t < 10) {
         int sl = rs[4 * c_tile_a[t] + c_tile_b[t]];
-        d = sl < 0 ? -1 : sl * 16;
+        d = sl < 0 ? -1 : uidx[sl] * 16;
       } else {
         int j = rs[16 + t - 10];
-        d = j < 0 ? -1 : (int)(nnz * 16 + (int64_t)j * 12);
+        d = j < 0 ? -1 : (int)(nup * 16 + (int64_t)j * 12);
       }
       int loc = 255;
       if (d >= 0) {
@@ -398,13 +399,25 @@ __global__ void k_group_table(const int* __restrict__ run_slots, int64_t nruns, 
   grp_n[q] = cnt;
 }
 
-// tslot[e] = slot of block (l, j) for the entry e = (j, l)
+// tslot[e] = slot of block (l, j) for the entry e = (j, l); flag[e] = 1 for the upper triangle
+// (l >= j), whose exclusive scan numbers the blocks kept in sys64
 __global__ void k_transposed_slots(const int* __restrict__ row_ptr, const int* __restrict__ col,
-                                   int64_t m, int* __restrict__ tslot) {
+                                   int64_t m, int* __restrict__ tslot, int* __restrict__ upper) {
   int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= m) return;
-  for (int t = row_ptr[j]; t < row_ptr[j + 1]; ++t)
+  for (int t = row_ptr[j]; t < row_ptr[j + 1]; ++t) {
     tslot[t] = find_slot_dev(row_ptr, col, col[t], (int)j);
+    upper[t] = col[t] >= j ? 1 : 0;
+  }
+}
+
+// uidx[e]: rank of an upper block among the upper blocks; a lower block points at its transpose
+__global__ void k_upper_index(const int* __restrict__ tslot, const int* __restrict__ scan,
+                              int64_t nnz, int* __restrict__ uidx) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int te = tslot[e];
+  uidx[e] = scan[te < e ? te : e];
 }
 
 // ------------------------------------------------------------------ build_graph
@@ -546,15 +559,32 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
     MVS_TRY(h->grp_n.reserve((size_t)h->ngroups));
     MVS_TRY(h->grp_dst.reserve((size_t)h->ngroups * kGrpMax));
     MVS_TRY(h->tslot.reserve((size_t)nnz));
+    MVS_TRY(h->uidx.reserve((size_t)nnz));
     {
-      ProfScope ps(ctx, "run_table", 3);
+      DevBuf<int> upper;
+      MVS_TRY(upper.reserve((size_t)nnz + 2));
+      {
+        ProfScope ps(ctx, "transposed_slots");
+        k_transposed_slots<<<div_up(m, 128), 128, 0, st>>>(h->row_ptr.p, h->col.p, m, h->tslot.p,
+                                                           upper.p);
+      }
+      MVS_CUDA(cudaMemsetAsync(upper.p + nnz, 0, sizeof(int) * 2, st));
+      MVS_TRY(exclusive_scan_inplace(ctx, upper.p, nnz, h->node_index->scan_tmp));
+      int nup = 0;
+      MVS_TRY(d2h_sync(ctx, &nup, upper.p + nnz, sizeof(int)));
+      h->nup = nup;
+      ProfScope ps(ctx, "upper_index");
+      k_upper_index<<<div_up(nnz, 256), 256, 0, st>>>(h->tslot.p, upper.p, nnz, h->uidx.p);
+      MVS_CUDA(cudaStreamSynchronize(st));  // `upper` is released in stream order
+    }
+    {
+      ProfScope ps(ctx, "run_table", 2);
       k_run_table<<<div_up(n, 256), 256, 0, st>>>(h->vidx.p, rflag.p, n, h->row_ptr.p, h->col.p,
                                                   h->g.p, h->v.p, h->run_slots.p, h->run_start.p,
                                                   h->run_g.p);
-      k_group_table<<<div_up(h->ngroups, 64), 64, 0, st>>>(h->run_slots.p, nruns, nnz, h->ngroups,
-                                                           h->grp_n.p, h->grp_dst.p,
+      k_group_table<<<div_up(h->ngroups, 64), 64, 0, st>>>(h->run_slots.p, nruns, h->uidx.p, h->nup,
+                                                           h->ngroups, h->grp_n.p, h->grp_dst.p,
                                                            h->run_local.p);
-      k_transposed_slots<<<div_up(m, 128), 128, 0, st>>>(h->row_ptr.p, h->col.p, m, h->tslot.p);
     }
     int n32 = (int)n;
     MVS_CUDA(cudaMemcpyAsync(h->run_start.p + nruns, &n32, sizeof(int), cudaMemcpyHostToDevice, st));

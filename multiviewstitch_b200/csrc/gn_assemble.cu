@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 5)
                    const float4* __restrict__ resid, const float4* __restrict__ run_g,
                    const unsigned char* __restrict__ run_local, const int* __restrict__ run_start,
                    const int* __restrict__ grp_n, const int* __restrict__ grp_dst,
-                   long long* __restrict__ sys64, int nnz16, int nruns, int64_t begin, int64_t end,
+                   long long* __restrict__ sys64, int nup16, int nruns, int64_t begin, int64_t end,
                    float w_fit, float fx_scale) {
   __shared__ __align__(16) float rec[kAsmWarps][32][kRecStride];
   __shared__ __align__(16) float accs[kAsmWarps][kGrpMax][16];
@@ -391,25 +391,28 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 5)
     for (int k = lane; k < L * 16; k += 32) {
       const int tile = k >> 4, e = k & 15;
       const int d = __ldg(gd + tile);
-      if (e < (d >= nnz16 ? 12 : 16)) fx_add(sys64 + d + e, accs[warp][tile][e], fx_scale);
+      if (e < (d >= nup16 ? 12 : 16)) fx_add(sys64 + d + e, accs[warp][tile][e], fx_scale);
     }
     __syncwarp();
   }
 }
 
-// fixed point -> float32 system; the lower triangle of the block pattern is the transpose of the
-// accumulated upper triangle (tslot[e] = slot of the transposed block; rows ascend, so e is a
-// lower-triangle entry iff tslot[e] < e)
+// fixed point [U: nup x 16 | rhs] -> float32 system [B: nnz x 16 | rhs]; a lower-triangle block is the
+// transpose of its accumulated mirror (tslot[e] = slot of the transposed block; rows ascend, so e is
+// a lower-triangle entry iff tslot[e] < e; uidx[e] = where the block or its mirror sits in U)
 __global__ void k_sys_convert(const long long* __restrict__ in, float* __restrict__ out, int64_t n,
-                              int64_t nnz16, const int* __restrict__ tslot, float inv_scale) {
+                              int64_t nnz16, int64_t nup16, const int* __restrict__ tslot,
+                              const int* __restrict__ uidx, float inv_scale) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    int64_t src = i;
+    int64_t src;
     if (i < nnz16) {
       int e = (int)(i >> 4), el = (int)(i & 15);
-      int te = __ldg(tslot + e);
-      if (te < e) src = (int64_t)te * 16 + (((el & 3) << 2) | (el >> 2));
+      bool lower = __ldg(tslot + e) < e;
+      src = (int64_t)__ldg(uidx + e) * 16 + (lower ? (((el & 3) << 2) | (el >> 2)) : el);
+    } else {
+      src = nup16 + (i - nnz16);
     }
     out[i] = (float)((double)in[src] * (double)inv_scale);
   }
@@ -426,8 +429,8 @@ __global__ void __launch_bounds__(128)
     k_node_terms(const float4* __restrict__ g, const float* __restrict__ x,
                  const int* __restrict__ graph, int gk1, int64_t m,
                  const int* __restrict__ row_ptr, const int* __restrict__ col,
-                 long long* __restrict__ B, float* __restrict__ Rot, long long* __restrict__ rhs,
-                 float w_rot, float w_reg, float fxs) {
+                 const int* __restrict__ uidx, long long* __restrict__ B, float* __restrict__ Rot,
+                 long long* __restrict__ rhs, float w_rot, float w_reg, float fxs) {
   const unsigned full = 0xffffffffu;
   int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kNodeLanes;
   int k = threadIdx.x & (kNodeLanes - 1);
@@ -504,9 +507,8 @@ __global__ void __launch_bounds__(128)
       }
       // coupling block: B_jl[c][3] = B_lj[3][c] = -w a_c; only the upper-triangle copy is
       // accumulated (k_sys_convert mirrors it)
-      long long* Bup = B + (size_t)(j < l ? find_slot(row_ptr, col, (int)j, l)
-                                          : find_slot(row_ptr, col, l, (int)j)) * 16;
-      long long* Bll = B + (size_t)find_slot(row_ptr, col, l, l) * 16;
+      long long* Bup = B + (size_t)__ldg(uidx + find_slot(row_ptr, col, (int)j, l)) * 16;
+      long long* Bll = B + (size_t)__ldg(uidx + find_slot(row_ptr, col, l, l)) * 16;
 #pragma unroll
       for (int c = 0; c < 4; ++c) fx_add(Bup + (j < l ? 4 * c + 3 : 12 + c), -w_reg * a[c], fxs);
       fx_add(Bll + 15, w_reg, fxs);
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(128)
     for (int p = 0; p < 12; ++p) gl[p] += __shfl_xor_sync(full, gl[p], o);
   }
   if (on && k < 4) {
-    long long* Bd = B + (size_t)find_slot(row_ptr, col, (int)j, (int)j) * 16;
+    long long* Bd = B + (size_t)__ldg(uidx + find_slot(row_ptr, col, (int)j, (int)j)) * 16;
     // lane k flushes row k of the 4x4 factor and 3 gradient entries
     float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll
@@ -628,7 +630,7 @@ int gn_assemble(mvs_deform* h) {
                                       (int64_t)ctx->num_sms * 5);
     k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(
         h->v.p, h->vw.p, h->resid.p, h->run_g.p, h->run_local.p, h->run_start.p, h->grp_n.p,
-        h->grp_dst.p, h->sys64.p, (int)(h->nnz * 16), (int)h->nruns, b, e, (float)h->prm.w_fit, fxs);
+        h->grp_dst.p, h->sys64.p, (int)(h->nup * 16), (int)h->nruns, b, e, (float)h->prm.w_fit, fxs);
   }
   MVS_CUDA(cudaGetLastError());
   if (ctx->comm && ctx->nranks > 1) {
@@ -640,11 +642,12 @@ int gn_assemble(mvs_deform* h) {
   {
     ProfScope ps(ctx, "gn_node_terms", 2);
     k_node_terms<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(
-        h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m, h->row_ptr.p, h->col.p, h->B64(),
-        h->Rot(), h->rhs64(), (float)h->prm.w_rot, (float)h->prm.w_reg, fxs);
+        h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m, h->row_ptr.p, h->col.p, h->uidx.p,
+        h->B64(), h->Rot(), h->rhs64(), (float)h->prm.w_rot, (float)h->prm.w_reg, fxs);
     // sys = [B | rhs | Rot]: B and rhs are contiguous in both buffers
-    k_sys_convert<<<grid_for(ctx, (int64_t)h->sys64_count(), 256, 4), 256, 0, st>>>(
-        h->sys64.p, h->sys.p, (int64_t)h->sys64_count(), h->nnz * 16, h->tslot.p,
+    int64_t nout = h->nnz * 16 + h->m * 12;
+    k_sys_convert<<<grid_for(ctx, nout, 256, 4), 256, 0, st>>>(
+        h->sys64.p, h->sys.p, nout, h->nnz * 16, h->nup * 16, h->tslot.p, h->uidx.p,
         (float)(1.0 / h->fx_scale));
   }
   {
