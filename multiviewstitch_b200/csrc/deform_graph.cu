@@ -175,14 +175,26 @@ __device__ __forceinline__ void cswap(int& a, int& b, float& wa, float& wb) {
   }
 }
 
-// sort key: primary (nearest) node in the high word keeps shards spatially compact; a hash of
-// the ascending tuple in the low word makes vertices with identical node sets adjacent.
-__global__ void k_tuple_keys(const int4* __restrict__ vidx, int64_t n,
+__device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// sort key: the Morton code of the centroid of the vertex's four nodes in the high word — a function
+// of the node SET, so vertices with identical sets are adjacent (tuple runs), consecutive runs are
+// neighbours on the surface (coherent walks, shared accumulators in the assembly groups) and a
+// vertex shard touches a compact node subset; a hash of the ascending tuple in the low word keeps
+// different sets with the same code apart.
+__global__ void k_tuple_keys(const int4* __restrict__ vidx, const float4* __restrict__ g,
+                             float3 bmin, float3 inv_ext, int64_t n,
                              unsigned long long* __restrict__ keys, int* __restrict__ vals) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int4 id = vidx[i];
-  int primary = id.x;
   float d0 = 0, d1 = 0, d2 = 0, d3 = 0;
   cswap(id.x, id.y, d0, d1);
   cswap(id.z, id.w, d2, d3);
@@ -195,7 +207,21 @@ __global__ void k_tuple_keys(const int4* __restrict__ vidx, int64_t n,
   h = (h ^ (unsigned)id.z) * 16777619u;
   h = (h ^ (unsigned)id.w) * 16777619u;
   h ^= h >> 15;
-  keys[i] = ((unsigned long long)(unsigned)primary << 32) | h;
+  // centroid of the valid nodes, summed in ascending-id order (identical for every vertex of the set)
+  int ids[4] = {id.x, id.y, id.z, id.w};
+  float cx = 0.f, cy = 0.f, cz = 0.f, cnt = 0.f;
+  for (int a = 0; a < 4; ++a)
+    if (ids[a] >= 0) {
+      float4 p = g[ids[a]];
+      cx += p.x; cy += p.y; cz += p.z;
+      cnt += 1.f;
+    }
+  float ic = cnt > 0.f ? 1.0f / cnt : 0.f;
+  unsigned mx = (unsigned)fminf(fmaxf((cx * ic - bmin.x) * inv_ext.x, 0.f), 1023.f);
+  unsigned my = (unsigned)fminf(fmaxf((cy * ic - bmin.y) * inv_ext.y, 0.f), 1023.f);
+  unsigned mz = (unsigned)fminf(fmaxf((cz * ic - bmin.z) * inv_ext.z, 0.f), 1023.f);
+  unsigned morton = spread10(mx) | (spread10(my) << 1) | (spread10(mz) << 2);
+  keys[i] = ((unsigned long long)morton << 32) | h;
   vals[i] = (int)i;
 }
 
@@ -463,8 +489,16 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
   MVS_TRY(h->perm.reserve((size_t)n));
   MVS_TRY(h->inv_perm.reserve((size_t)n));
   {
+    float gmn[3], gmx[3];
+    MVS_TRY(bbox_host(ctx, h->g.p, m, h->node_index->red, gmn, gmx));
+    float3 bmin = make_float3(gmn[0], gmn[1], gmn[2]);
+    float3 inv_ext;
+    inv_ext.x = gmx[0] > gmn[0] ? 1023.999f / (gmx[0] - gmn[0]) : 0.f;
+    inv_ext.y = gmx[1] > gmn[1] ? 1023.999f / (gmx[1] - gmn[1]) : 0.f;
+    inv_ext.z = gmx[2] > gmn[2] ? 1023.999f / (gmx[2] - gmn[2]) : 0.f;
     ProfScope ps(ctx, "tuple_keys");
-    k_tuple_keys<<<div_up(n, 256), 256, 0, st>>>(h->vidx_knn.p, n, keys.p, vals.p);
+    k_tuple_keys<<<div_up(n, 256), 256, 0, st>>>(h->vidx_knn.p, h->g.p, bmin, inv_ext, n, keys.p,
+                                                 vals.p);
   }
   {
     size_t tmp_bytes = 0;
