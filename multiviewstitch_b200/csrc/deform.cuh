@@ -121,7 +121,7 @@ struct mvs_deform {
 
 namespace mvs {
 
-constexpr int kGrpRuns = 8;             // runs per assembly group
+constexpr int kGrpRuns = 4;             // runs per assembly group
 constexpr int kGrpMax = 14 * kGrpRuns;  // 10 upper-triangle block tiles + 4 gradient tiles per run
 
 // scal[] slots

@@ -632,7 +632,7 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
   }
   // 6. solver buffers
   MVS_TRY(h->sys.reserve(h->sys_floats()));
-  MVS_TRY(h->sys64.reserve(h->sys64_count()));
+  MVS_TRY(h->sys64.reserve(h->sys64_count() + 2));  // + the assembly group counter
   MVS_TRY(h->Minv.reserve((size_t)m * 144));
   MVS_TRY(h->x.reserve((size_t)m * 12));
   MVS_TRY(h->pcg.reserve((size_t)m * 12 * 6));

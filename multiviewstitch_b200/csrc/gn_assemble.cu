@@ -219,13 +219,11 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 5)
                    const unsigned char* __restrict__ run_local, const int* __restrict__ run_start,
                    const int* __restrict__ grp_n, const int* __restrict__ grp_dst,
                    long long* __restrict__ sys64, int nup16, int nruns, int64_t begin, int64_t end,
-                   float w_fit, float fx_scale) {
+                   float w_fit, float fx_scale, unsigned* __restrict__ next_group) {
   __shared__ __align__(16) float rec[kAsmWarps][32][kRecStride];
   __shared__ __align__(16) float accs[kAsmWarps][kGrpMax][16];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = gridDim.x * kAsmWarps;
-  const int wg = blockIdx.x * kAsmWarps + warp;
   const int half = lane >> 4, t = lane & 15;
   int ta, tb;
   switch (t) {
@@ -252,7 +250,13 @@ __global__ void __launch_bounds__(kAsmWarps * 32, 5)
     r.w = __ldg(vw + i);
     return r;
   };
-  for (int q = run_lo / kGrpRuns + wg; q <= run_hi / kGrpRuns; q += nwarps) {
+  // groups are handed out dynamically (run lengths vary); the sums are integer, so the order in
+  // which groups finish cannot change the result
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = (int)atomicAdd(next_group, 1u);
+    q = __shfl_sync(full, q, 0) + run_lo / kGrpRuns;
+    if (q > run_hi / kGrpRuns) break;
     const int r_base = q * kGrpRuns;
     const int r_first = max(r_base, run_lo), r_last = min(r_base + kGrpRuns - 1, run_hi);
     // lane l <= kGrpRuns: first vertex of run r_base + l
@@ -621,7 +625,8 @@ int gn_assemble(mvs_deform* h) {
   frexp(bound, &ex);  // bound < 2^ex
   h->fx_scale = ldexp(1.0, std::max(0, std::min(40, 62 - ex)));
   float fxs = (float)h->fx_scale;
-  MVS_CUDA(cudaMemsetAsync(h->sys64.p, 0, sizeof(long long) * h->sys64_count(), st));
+  // the word after the system is the assembly's group counter: cleared by the same memset
+  MVS_CUDA(cudaMemsetAsync(h->sys64.p, 0, sizeof(long long) * (h->sys64_count() + 1), st));
   int64_t b = h->shard_begin(), e = h->shard_end();
   if (e > b) {
     ProfScope ps(ctx, "gn_assemble_fit");
@@ -630,7 +635,8 @@ int gn_assemble(mvs_deform* h) {
                                       (int64_t)ctx->num_sms * 5);
     k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(
         h->v.p, h->vw.p, h->resid.p, h->run_g.p, h->run_local.p, h->run_start.p, h->grp_n.p,
-        h->grp_dst.p, h->sys64.p, (int)(h->nup * 16), (int)h->nruns, b, e, (float)h->prm.w_fit, fxs);
+        h->grp_dst.p, h->sys64.p, (int)(h->nup * 16), (int)h->nruns, b, e, (float)h->prm.w_fit, fxs,
+        reinterpret_cast<unsigned*>(h->sys64.p + h->sys64_count()));
   }
   MVS_CUDA(cudaGetLastError());
   if (ctx->comm && ctx->nranks > 1) {
