@@ -306,7 +306,7 @@ int mvs_deform_destroy(mvs_deform* h) {
 }
 
 static int set_target_index(mvs_deform* h, int64_t nt) {
-  MVS_TRY(nn_build_pyramid(h->tgt_index, h->tp, nt));
+  MVS_TRY(nn_build_pyramid(h->tgt_index, h->tp, nt, kPyrPpcFar));
   // correspondences of a previous target are no seeds for this one
   if (h->corr_prev.p && h->n > 0)
     MVS_CUDA(cudaMemsetAsync(h->corr_prev.p, 0xff, sizeof(int) * h->n, h->ctx->stream));

@@ -508,7 +508,7 @@ int nn_knn(mvs_nn_index* idx, const float4* q, int64_t nq, int k, int* out_idx, 
   if (k == 1) {
     // 1-NN: sparse occupancy pyramid (built lazily from the cell-sorted copy, .w = original index)
     if (!idx->pyr_built)
-      MVS_TRY(nn_build_pyramid(idx, idx->pts_sorted.p, idx->g.n, 3.0f, true));
+      MVS_TRY(nn_build_pyramid(idx, idx->pts_sorted.p, idx->g.n, kPyrPpcNear, true));
     return nn_nn1_pyramid(idx, q, perm, nq, out_idx, out_d2);
   }
   {

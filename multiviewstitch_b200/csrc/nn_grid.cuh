@@ -163,6 +163,17 @@ struct KnnList {
   }
 };
 
+// First radius, in cells, of an unseeded query's doubling schedule (nn_pyramid.cuh: pyr_search).
+// Measured on B200, 1e7 near-surface queries against 1e7 points (C2): 2.0 -> 5.04 ms, 1.0 -> 2.73,
+// 0.75 -> 2.43, 0.5 -> 2.66, 0.35 -> 3.02; far queries (first GN iteration of C3) do not care.
+constexpr float kPyrFirstRadius = 0.75f;
+// Points per occupied cell wanted by the two users of the pyramid: near-surface 1-NN queries are
+// fastest with ~3 (C2: 2.22 ms at 3, 2.29 at 2, 2.31 at 4.5); the deformation target, whose first
+// iteration queries from up to 5 % of the diagonal away, with ~6 (C3 correspondence passes of one
+// solve: 2.82 ms at 3, 2.60 at 4.5, 2.52 at 6, 2.72 at 8, 2.63 at 12).
+constexpr float kPyrPpcNear = 3.0f;
+constexpr float kPyrPpcFar = 6.0f;
+
 // sparse occupancy pyramid (nn_pyramid.cuh)
 struct PyrParams {
   float bmin[3];
@@ -217,7 +228,8 @@ namespace mvs {
 // Build from device float4 points (w ignored).  target_ppc: wanted points per occupied cell.
 int nn_build(mvs_nn_index* idx, const float4* pts_dev, int64_t n, float target_ppc = 3.0f);
 // Sparse pyramid over device float4 points (w ignored unless w_is_index).
-int nn_build_pyramid(mvs_nn_index* idx, const float4* pts_dev, int64_t n, float target_ppc = 3.0f,
+int nn_build_pyramid(mvs_nn_index* idx, const float4* pts_dev, int64_t n,
+                     float target_ppc = kPyrPpcNear,
                      bool w_is_index = false);
 int nn_nn1_pyramid(mvs_nn_index* idx, const float4* q_dev, const int* perm_dev, int64_t nq,
                    int* out_idx_dev, float* out_d2_dev);

@@ -264,7 +264,9 @@ int nn_build_pyramid(mvs_nn_index* idx, const float4* pts, int64_t n, float targ
 }
 
 // ------------------------------------------------------------------ exact 1-NN over the pyramid
-__global__ void __launch_bounds__(128)
+// 10 CTAs per SM (48 registers, 80 B of spill): 2.22 ms per 1e7 queries against 2.43 at 7 CTAs
+// (72 registers, no spill) and 2.19 at 16 — the walk hides latency with warps, not registers
+__global__ void __launch_bounds__(128, 10)
     k_nn1_pyr(PyrParams P, const float4* __restrict__ q, const int* __restrict__ perm, int64_t nq,
               int* __restrict__ out_idx, float* __restrict__ out_d2) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -182,7 +182,7 @@ __device__ __forceinline__ void pyr_search(const PyrParams& P, float qx, float q
   float gy = fmaxf(fmaxf(P.bmin[1] - qy, qy - (P.bmin[1] + P.dims[1] * P.h)), 0.f);
   float gz = fmaxf(fmaxf(P.bmin[2] - qz, qz - (P.bmin[2] + P.dims[2] * P.h)), 0.f);
   float out = sqrtf(gx * gx + gy * gy + gz * gz);
-  float r = 2.f * P.h + out;
+  float r = kPyrFirstRadius * P.h + out;
   const float rmax = P.h * (float)(P.dims[0] + P.dims[1] + P.dims[2]) + out;
   for (;;) {
     float r2 = r * r;
