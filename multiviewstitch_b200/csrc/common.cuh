@@ -57,6 +57,10 @@ struct mvs_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // forked side stream for work that is independent of the main stream's current kernel
+  // (ctx_side_fork / ctx_side_join); created on first use
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int num_sms = mvs::kNumSMsB200;
   int64_t launch_count = 0;
   bool prof_on = false;
@@ -89,9 +93,15 @@ struct ProfScope {
   const char* name;
   int64_t launches;
   cudaEvent_t start = nullptr, stop = nullptr;
-  ProfScope(mvs_ctx* c, const char* n, int64_t nlaunch = 1);
+  cudaStream_t st = nullptr;  // the stream the family is launched on
+  ProfScope(mvs_ctx* c, const char* n, int64_t nlaunch = 1, cudaStream_t on = nullptr);
   ~ProfScope();
 };
+
+// Fork: the side stream starts after everything queued on the main stream so far.  Join: the main
+// stream waits for everything queued on the side stream so far.
+int ctx_side_fork(mvs_ctx* ctx);
+int ctx_side_join(mvs_ctx* ctx);
 
 // The stream of the context the calling thread last entered (ctx_ensure_device): device buffers
 // are allocated and freed in that stream's order from the cached stream-ordered pool, so the many

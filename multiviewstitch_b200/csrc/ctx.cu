@@ -59,19 +59,19 @@ static cudaEvent_t take_event(mvs_ctx* ctx) {
   return e;
 }
 
-ProfScope::ProfScope(mvs_ctx* c, const char* n, int64_t nlaunch)
-    : ctx(c), name(n), launches(nlaunch) {
+ProfScope::ProfScope(mvs_ctx* c, const char* n, int64_t nlaunch, cudaStream_t on)
+    : ctx(c), name(n), launches(nlaunch), st(on ? on : c->stream) {
   ctx->launch_count += nlaunch;
   if (ctx->prof_on) {
     start = take_event(ctx);
     stop = take_event(ctx);
-    if (start) cudaEventRecord(start, ctx->stream);
+    if (start) cudaEventRecord(start, st);
   }
 }
 
 ProfScope::~ProfScope() {
   if (ctx->prof_on && start && stop) {
-    cudaEventRecord(stop, ctx->stream);
+    cudaEventRecord(stop, st);
     PendingProf p;
     p.name = name;
     p.start = start;
@@ -81,9 +81,27 @@ ProfScope::~ProfScope() {
   }
 }
 
+int ctx_side_fork(mvs_ctx* ctx) {
+  if (!ctx->side) {
+    MVS_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    MVS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    MVS_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  MVS_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  MVS_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  return MVS_OK;
+}
+
+int ctx_side_join(mvs_ctx* ctx) {
+  MVS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  MVS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  return MVS_OK;
+}
+
 int ctx_resolve_prof(mvs_ctx* ctx) {
   if (ctx->pending.empty()) return MVS_OK;
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->side) MVS_CUDA(cudaStreamSynchronize(ctx->side));
   for (auto& p : ctx->pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, p.start, p.stop) == cudaSuccess) {
@@ -139,6 +157,12 @@ static void ctx_free(mvs_ctx* ctx) {
   }
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->side) {
+    cudaStreamSynchronize(ctx->side);
+    cudaStreamDestroy(ctx->side);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -94,6 +94,7 @@ struct mvs_deform {
   mvs::DevBuf<float4> resid;    // (v~ - c, omega)
   mvs::DevBuf<int> corr_prev;   // last correspondence of each vertex (seed of the next search)
   bool corr_seeded = false;     // corr_prev holds valid seeds for the current target
+  bool node_terms_forked = false;  // this iteration's node terms are in flight on the side stream
   mvs::DevBuf<float4> targets;  // (c, omega) for fixed-target modes
   bool have_targets = false;
   mvs::DevBuf<float4> cur0;     // deformed vertices, ORIGINAL order
@@ -136,7 +137,8 @@ int deform_node_targets(mvs_deform* h, double proj_len_err, double proj_dist_err
 // gn_assemble.cu
 int gn_reset_state(mvs_deform* h);
 int gn_deform_and_correspond(mvs_deform* h);   // writes resid (mode 1: NN; else fixed targets)
-int gn_assemble(mvs_deform* h);                 // zero + fit pass (+ allreduce) + node terms + precond
+int gn_node_terms_forked(mvs_deform* h);        // zero + node terms on the side stream (one rank)
+int gn_assemble(mvs_deform* h);                 // [zero +] fit pass [+ allreduce + node terms] + precond
 int gn_apply_update(mvs_deform* h);             // x += delta
 int gn_final_vertices(mvs_deform* h);           // cur0 / curn0 in original order
 int gn_energy(mvs_deform* h, double energy[3]); // at the current state with the current resid

@@ -135,7 +135,13 @@ static int gn_begin_impl(mvs_deform* h, const mvs_gn_params* p) {
 }
 
 static int gn_step_impl(mvs_deform* h) {
-  MVS_TRY(gn_deform_and_correspond(h));
+  MVS_TRY(gn_node_terms_forked(h));  // side stream, overlaps the correspondence pass
+  int rc = gn_deform_and_correspond(h);
+  if (rc != MVS_OK) {  // keep the streams ordered before reporting the error
+    if (h->node_terms_forked) ctx_side_join(h->ctx);
+    h->node_terms_forked = false;
+    return rc;
+  }
   MVS_TRY(gn_assemble(h));
   MVS_TRY(pcg_solve(h));  // also applies x += delta
   return MVS_OK;

@@ -618,19 +618,58 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-int gn_assemble(mvs_deform* h) {
-  mvs_ctx* ctx = h->ctx;
-  cudaStream_t st = ctx->stream;
-  // fixed-point scale: the largest power of two that cannot overflow int64 for this problem
-  // (every entry is bounded by w_fit omega_max n max(1, D^2) plus the node terms)
+// fixed-point scale: the largest power of two that cannot overflow int64 for this problem (every
+// entry is bounded by w_fit omega_max n max(1, D^2) plus the node terms)
+static float gn_fx_scale(mvs_deform* h) {
   double bound = 4.0 * (h->prm.w_fit * (double)h->omega_max * (double)h->n * std::max(1.0, h->diag2) +
                         h->prm.w_reg * 64.0 * std::max(1.0, h->diag2) + h->prm.w_rot * 64.0 + 1.0);
   int ex = 0;
   frexp(bound, &ex);  // bound < 2^ex
   h->fx_scale = ldexp(1.0, std::max(0, std::min(40, 62 - ex)));
-  float fxs = (float)h->fx_scale;
+  return (float)h->fx_scale;
+}
+
+static int gn_zero_system(mvs_deform* h, cudaStream_t st) {
   // the word after the system is the assembly's group counter: cleared by the same memset
   MVS_CUDA(cudaMemsetAsync(h->sys64.p, 0, sizeof(long long) * (h->sys64_count() + 1), st));
+  return MVS_OK;
+}
+
+static int gn_launch_node_terms(mvs_deform* h, float fxs, cudaStream_t st) {
+  ProfScope ps(h->ctx, "gn_node_terms", 1, st);
+  k_node_terms<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(
+      h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m, h->row_ptr.p, h->col.p, h->uidx.p, h->B64(),
+      h->Rot(), h->rhs64(), (float)h->prm.w_rot, (float)h->prm.w_reg, fxs);
+  MVS_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+// The node terms (rotation + smoothness) depend only on the node state, and their fixed-point
+// atomics commute with the fit pass's: on one rank they are zeroed-and-accumulated on the side
+// stream while the main stream runs the correspondence pass, and joined before the fit pass.
+// (Vertex-sharded solves add them once, after the all-reduce, on the main stream.)
+int gn_node_terms_forked(mvs_deform* h) {
+  mvs_ctx* ctx = h->ctx;
+  h->node_terms_forked = false;
+  if (ctx->comm && ctx->nranks > 1) return MVS_OK;
+  float fxs = gn_fx_scale(h);
+  MVS_TRY(ctx_side_fork(ctx));
+  MVS_TRY(gn_zero_system(h, ctx->side));
+  MVS_TRY(gn_launch_node_terms(h, fxs, ctx->side));
+  h->node_terms_forked = true;
+  return MVS_OK;
+}
+
+int gn_assemble(mvs_deform* h) {
+  mvs_ctx* ctx = h->ctx;
+  cudaStream_t st = ctx->stream;
+  float fxs = gn_fx_scale(h);
+  const bool forked = h->node_terms_forked;
+  h->node_terms_forked = false;
+  if (forked)
+    MVS_TRY(ctx_side_join(ctx));
+  else
+    MVS_TRY(gn_zero_system(h, st));
   int64_t b = h->shard_begin(), e = h->shard_end();
   if (e > b) {
     ProfScope ps(ctx, "gn_assemble_fit");
@@ -649,11 +688,9 @@ int gn_assemble(mvs_deform* h) {
     ProfScope ps(ctx, "gn_allreduce", 0);
     MVS_TRY(comm_allreduce_sum_i64(ctx, h->sys64.p, h->sys64_count()));
   }
+  if (!forked) MVS_TRY(gn_launch_node_terms(h, fxs, st));
   {
-    ProfScope ps(ctx, "gn_node_terms", 2);
-    k_node_terms<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(
-        h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m, h->row_ptr.p, h->col.p, h->uidx.p,
-        h->B64(), h->Rot(), h->rhs64(), (float)h->prm.w_rot, (float)h->prm.w_reg, fxs);
+    ProfScope ps(ctx, "gn_sys_convert");
     // sys = [B | rhs | Rot]: B and rhs are contiguous in both buffers
     int64_t nout = h->nnz * 16 + h->m * 12;
     k_sys_convert<<<grid_for(ctx, nout, 256, 4), 256, 0, st>>>(
