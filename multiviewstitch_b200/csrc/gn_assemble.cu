@@ -561,10 +561,13 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
 }
 
+// The diagonal factor is read from the fixed-point system and converted exactly as k_sys_convert
+// does (same float value), so the kernel does not wait for the conversion pass: the two run side by
+// side.
 __global__ void __launch_bounds__(128)
     k_precond(const int* __restrict__ row_ptr, const int* __restrict__ col,
-              const float* __restrict__ B, const float* __restrict__ Rot, int64_t m, double lambda,
-              float* __restrict__ Minv) {
+              const int* __restrict__ uidx, const long long* __restrict__ U, float inv_scale,
+              const float* __restrict__ Rot, int64_t m, double lambda, float* __restrict__ Minv) {
   int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kNodeLanes;
   int lane = threadIdx.x & 31;
   int k = lane & (kNodeLanes - 1);
@@ -576,12 +579,12 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
   for (int q = 0; q < 12; ++q) a[q] = (q == k) ? 1.0 : 0.0;  // identity rows for idle lanes
   if (act) {
-    const float* Bd = B + (size_t)find_slot(row_ptr, col, (int)j, (int)j) * 16;
+    const long long* Bd = U + (size_t)__ldg(uidx + find_slot(row_ptr, col, (int)j, (int)j)) * 16;
     int ka = k / 3, kr = k - 3 * ka;
 #pragma unroll
     for (int q = 0; q < 12; ++q) {
       int qa = q / 3, qr = q - 3 * qa;
-      double v = (qr == kr) ? (double)__ldg(Bd + 4 * ka + qa) : 0.0;
+      double v = (qr == kr) ? (double)(float)((double)__ldg(Bd + 4 * ka + qa) * (double)inv_scale) : 0.0;
       if (k < 9 && q < 9) v += (double)__ldg(Rot + (size_t)j * 81 + 9 * k + q);
       if (q == k) v += lambda;
       a[q] = v;
@@ -689,20 +692,25 @@ int gn_assemble(mvs_deform* h) {
     MVS_TRY(comm_allreduce_sum_i64(ctx, h->sys64.p, h->sys64_count()));
   }
   if (!forked) MVS_TRY(gn_launch_node_terms(h, fxs, st));
+  // conversion (main stream) and block-Jacobi inverses (side stream) both read the finished
+  // fixed-point system
+  const float inv_scale = (float)(1.0 / h->fx_scale);
+  MVS_TRY(ctx_side_fork(ctx));
+  {
+    ProfScope ps(ctx, "gn_precond", 1, ctx->side);
+    k_precond<<<div_up(h->m * kNodeLanes, 128), 128, 0, ctx->side>>>(
+        h->row_ptr.p, h->col.p, h->uidx.p, h->B64(), inv_scale, h->Rot(), h->m, h->prm.lambda,
+        h->Minv.p);
+  }
   {
     ProfScope ps(ctx, "gn_sys_convert");
     // sys = [B | rhs | Rot]: B and rhs are contiguous in both buffers
     int64_t nout = h->nnz * 16 + h->m * 12;
     k_sys_convert<<<grid_for(ctx, nout, 256, 4), 256, 0, st>>>(
-        h->sys64.p, h->sys.p, nout, h->nnz * 16, h->nup * 16, h->tslot.p, h->uidx.p,
-        (float)(1.0 / h->fx_scale));
-  }
-  {
-    ProfScope ps(ctx, "gn_precond");
-    k_precond<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(h->row_ptr.p, h->col.p, h->B(), h->Rot(), h->m,
-                                               h->prm.lambda, h->Minv.p);
+        h->sys64.p, h->sys.p, nout, h->nnz * 16, h->nup * 16, h->tslot.p, h->uidx.p, inv_scale);
   }
   MVS_CUDA(cudaGetLastError());
+  MVS_TRY(ctx_side_join(ctx));
   return MVS_OK;
 }
 
