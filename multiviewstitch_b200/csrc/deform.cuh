@@ -94,6 +94,9 @@ struct mvs_deform {
   mvs::DevBuf<float4> resid;    // (v~ - c, omega)
   mvs::DevBuf<int> corr_prev;   // last correspondence of each vertex (seed of the next search)
   bool corr_seeded = false;     // corr_prev holds valid seeds for the current target
+  mvs::DevBuf<double> pcg_xchg;  // persistent PCG: two halves of [exchange ring | exchange words]
+  size_t pcg_xchg_ring = 0, pcg_xchg_words = 0;
+  unsigned pcg_epoch = 0;
   bool node_terms_forked = false;  // this iteration's node terms are in flight on the side stream
   mvs::DevBuf<float4> targets;  // (c, omega) for fixed-target modes
   bool have_targets = false;

@@ -44,6 +44,11 @@ struct PcgArgs {
   float* delta;   // m x 12 (exported for inspection)
   double* ring;   // kRing x grid x 2 exchange slots, all-ones at launch
   unsigned long long* words;  // (2 iters + 1) x 4 fixed-point exchange words, zero at launch
+  // the other half of the exchange buffer (used by the previous launch): this launch re-arms it for
+  // the next one, so no memset sits between two solves
+  unsigned long long* next_ring;
+  unsigned long long* next_words;
+  int ring_count, word_count;
   double* scal;   // S_* slots
   int64_t m;
   int iters;
@@ -307,6 +312,13 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
   const bool lane_on = k < 12;
   float2* zp = reinterpret_cast<float2*>(a.zbuf);  // 2 x m x 12 float2
   unsigned phase = 0;
+  for (int i = blockIdx.x * kPcgThreads + threadIdx.x; i < a.ring_count + a.word_count;
+       i += gridDim.x * kPcgThreads) {
+    if (i < a.ring_count)
+      a.next_ring[i] = kSlotEmpty;
+    else
+      a.next_words[i - a.ring_count] = 0ull;
+  }
 
   // ---- stage this CTA's matrix slice
   const int nz0 = row0 < m ? __ldg(a.row_ptr + row0) : 0;
@@ -570,13 +582,30 @@ int pcg_solve(mvs_deform* h) {
   a.pbuf = nullptr;
   a.delta = h->pcg.p + 4 * N;
   // exchange slots of the fused barrier + reduction: "empty" = all-ones
+  // two halves [ring | words]: a launch uses one and re-arms the other (the previous launch's)
   size_t ring_doubles = (size_t)kRing * h->pcg_grid * 2;
   size_t nwords = (size_t)(2 * std::max(h->prm.pcg_iters, 0) + 1) * 4;
-  MVS_TRY(h->partials.reserve(ring_doubles + nwords + 16));
-  MVS_CUDA(cudaMemsetAsync(h->partials.p, 0xff, ring_doubles * sizeof(double), ctx->stream));
-  MVS_CUDA(cudaMemsetAsync(h->partials.p + ring_doubles, 0, nwords * sizeof(double), ctx->stream));
-  a.ring = h->partials.p;
-  a.words = reinterpret_cast<unsigned long long*>(h->partials.p + ring_doubles);
+  size_t half = ring_doubles + nwords;
+  if (h->pcg_xchg_ring != ring_doubles || h->pcg_xchg_words != nwords) {
+    MVS_TRY(h->pcg_xchg.reserve(2 * half));
+    for (int k = 0; k < 2; ++k) {
+      MVS_CUDA(cudaMemsetAsync(h->pcg_xchg.p + k * half, 0xff, ring_doubles * sizeof(double), ctx->stream));
+      MVS_CUDA(cudaMemsetAsync(h->pcg_xchg.p + k * half + ring_doubles, 0, nwords * sizeof(double),
+                               ctx->stream));
+    }
+    h->pcg_xchg_ring = ring_doubles;
+    h->pcg_xchg_words = nwords;
+    h->pcg_epoch = 0;
+  }
+  double* cur = h->pcg_xchg.p + (h->pcg_epoch & 1) * half;
+  double* nxt = h->pcg_xchg.p + ((h->pcg_epoch + 1) & 1) * half;
+  ++h->pcg_epoch;
+  a.ring = cur;
+  a.words = reinterpret_cast<unsigned long long*>(cur + ring_doubles);
+  a.next_ring = reinterpret_cast<unsigned long long*>(nxt);
+  a.next_words = reinterpret_cast<unsigned long long*>(nxt + ring_doubles);
+  a.ring_count = (int)ring_doubles;
+  a.word_count = (int)nwords;
   a.scal = h->scal.p;
   a.m = m;
   a.iters = h->prm.pcg_iters;
