@@ -95,10 +95,29 @@ __global__ void __launch_bounds__(kSrtThreads)
   }
 }
 
+// |b| / |a| from the squared norms.  Two IEEE float64 square roots and a division are ~90
+// instructions of software sequences and made the pass compute bound (125 us per 1e7 pairs, 39 % of
+// the HBM roofline); here 1/na2 and 1/sqrt(t) start from float32 hardware seeds and take two Newton
+// steps each in float64 (relative error 6e-8 -> 4e-15 -> rounding level), ~25 instructions.
+// Arguments outside the float32 seed range (zero, subnormal, huge, NaN) take the plain form, which
+// also keeps the reference's behaviour for p_i = centroid (division by zero, SRTSolver.cpp:44).
+__device__ __forceinline__ double norm_ratio(double nb2, double na2) {
+  if (!(na2 > 1e-30 && na2 < 1e30 && nb2 > 1e-30 && nb2 < 1e30)) return sqrt(nb2) / sqrt(na2);
+  double y = (double)__frcp_rn((float)na2);
+  y = y * (2.0 - na2 * y);
+  y = y * (2.0 - na2 * y);
+  const double t = nb2 * y;
+  double r = (double)rsqrtf((float)t);
+  const double h = 0.5 * t;
+  r = r * (1.5 - h * r * r);
+  r = r * (1.5 - h * r * r);
+  return t * r;
+}
+
 // pass 2: sum of |q-c2|/|p-c1| (SRTSolver.cpp:42-45) and raw cross-covariance (p-c1)(q-c2)^T
 // (:75-107, the scale factor is applied once at the end); the last CTA finishes the closed form.
 template <class Acc>
-__global__ void __launch_bounds__(kSrtThreads)
+__global__ void __launch_bounds__(kSrtThreads, 4)
     k_srt_scale_cov(Acc acc, int64_t n, double* partials, unsigned* ticket, double* res) {
   __shared__ double smem[32 * 10];
   double c1[3], c2[3];
@@ -110,29 +129,47 @@ __global__ void __launch_bounds__(kSrtThreads)
   double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    double P[3], Q[3];
-    acc.load(i, P, Q);
+  auto add = [&](const double (&P)[3], const double (&Q)[3]) {
     double a0 = P[0] - c1[0], a1 = P[1] - c1[1], a2 = P[2] - c1[2];
     double b0 = Q[0] - c2[0], b1 = Q[1] - c2[1], b2 = Q[2] - c2[2];
-    double na = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
-    double nb = sqrt(b0 * b0 + b1 * b1 + b2 * b2);
-    v[0] += nb / na;
+    v[0] += norm_ratio(b0 * b0 + b1 * b1 + b2 * b2, a0 * a0 + a1 * a1 + a2 * a2);
     v[1] += a0 * b0; v[2] += a0 * b1; v[3] += a0 * b2;
     v[4] += a1 * b0; v[5] += a1 * b1; v[6] += a1 * b2;
     v[7] += a2 * b0; v[8] += a2 * b1; v[9] += a2 * b2;
+  };
+  // two pairs per trip, both loads issued before the float64 work of either
+  for (; i + stride < n; i += 2 * stride) {
+    double P0[3], Q0[3], P1[3], Q1[3];
+    acc.load(i, P0, Q0);
+    acc.load(i + stride, P1, Q1);
+    add(P0, Q0);
+    add(P1, Q1);
   }
-  if (grid_reduce_sum<10>(v, smem, partials, ticket, res + R_ACC)) {
-    if (threadIdx.x == 0) {
-      double s = res[R_ACC] / (double)n;
-      double S[9], R[9], t[3];
-      for (int k = 0; k < 9; ++k) S[k] = s * res[R_ACC + 1 + k];
-      kabsch_from_cov(S, s, c1, c2, R, t);
-      res[R_SCALE] = s;
-      for (int k = 0; k < 9; ++k) res[R_ROT + k] = R[k];
-      for (int k = 0; k < 3; ++k) res[R_T + k] = t[k];
-    }
+  if (i < n) {
+    double P[3], Q[3];
+    acc.load(i, P, Q);
+    add(P, Q);
   }
+  grid_reduce_sum<10>(v, smem, partials, ticket, res + R_ACC);
+}
+
+// The closed form (3x3 Jacobi SVD in float64) is its own one-thread launch: inlined into the
+// streaming pass it raised that kernel to 128 registers + 168 B of spill, i.e. 2 CTAs per SM instead
+// of 4 and half the loads in flight (125 us per 1e7 pairs; 39 % of the HBM roofline).
+__global__ void k_srt_finish(int64_t n, double* res) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double c1[3], c2[3];
+  for (int a = 0; a < 3; ++a) {
+    c1[a] = res[R_CENT + a];
+    c2[a] = res[R_CENT + 3 + a];
+  }
+  double s = res[R_ACC] / (double)n;
+  double S[9], R[9], t[3];
+  for (int k = 0; k < 9; ++k) S[k] = s * res[R_ACC + 1 + k];
+  kabsch_from_cov(S, s, c1, c2, R, t);
+  res[R_SCALE] = s;
+  for (int k = 0; k < 9; ++k) res[R_ROT + k] = R[k];
+  for (int k = 0; k < 3; ++k) res[R_T + k] = t[k];
 }
 
 // hypothesis record: sR[9], t[3], iR[9] (+3 pad) ; plain R kept separately
@@ -393,9 +430,10 @@ int run_two_pass(mvs_srt* h, Acc acc) {
                                                                 h->ticket.p, h->res.p);
   }
   {
-    ProfScope ps(ctx, "srt_scale_cov");
+    ProfScope ps(ctx, "srt_scale_cov", 2);
     k_srt_scale_cov<Acc><<<grid, kSrtThreads, 0, ctx->stream>>>(acc, h->n, h->partials.p,
                                                                 h->ticket.p, h->res.p);
+    k_srt_finish<<<1, 32, 0, ctx->stream>>>(h->n, h->res.p);
   }
   MVS_CUDA(cudaGetLastError());
   return MVS_OK;
