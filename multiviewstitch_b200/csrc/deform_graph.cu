@@ -3,6 +3,7 @@
 //   node count), per-vertex k-nearest-node weights, vertex reordering by node tuple, node graph
 //   (Deformation.cpp:108-153), block-sparse pattern of the normal equations, and the node
 //   correspondence + smoothing stage (Deformation.cpp:266-381).
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -121,6 +122,132 @@ __global__ void __launch_bounds__(256)
     *cur_io = bi;
     *ticket = 0u;
   }
+}
+
+// Farthest point sampling of a small point set (n <= 8 x kFpsCap: the C1/C4 view meshes) in ONE
+// launch of one thread-block cluster.  The per-step launch above costs ~7 us per node whatever n is;
+// here the 8 CTAs keep their share of the points and of the running minimum distances in shared
+// memory, publish one candidate each (value, index, position) in a double-buffered slot, meet at
+// the cluster barrier, and every warp reads the 8 candidates through distributed shared memory and
+// picks the winner — one cluster barrier per node, no global traffic.  Same result as the oracle
+// (orc_sample_fps): FMA-free float32 distances, farthest point with the lowest index on ties.
+namespace cg = cooperative_groups;
+constexpr int kFpsCluster = 8;
+constexpr int kFpsThreads = 512;
+constexpr int kFpsCap = 12288;  // points per CTA (16 B each in shared memory)
+
+struct FpsCand {
+  float v;
+  int i;
+  float x, y, z;
+};
+
+__global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThreads, 1)
+    k_fps_cluster(const float4* __restrict__ pts, int n, int n_nodes, int first,
+                  int* __restrict__ out_ids) {
+  extern __shared__ float fps_smem[];
+  __shared__ float sv[kFpsThreads / 32];
+  __shared__ int si[kFpsThreads / 32];
+  __shared__ FpsCand cand[2];
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int)cl.block_rank();
+  const int per = (n + kFpsCluster - 1) / kFpsCluster;
+  const int b0 = rank * per;
+  const int cnt = max(0, min(per, n - b0));
+  float* xs = fps_smem;
+  float* ys = xs + per;
+  float* zs = ys + per;
+  float* md = zs + per;
+  for (int k = threadIdx.x; k < cnt; k += kFpsThreads) {
+    float4 p = __ldg(pts + b0 + k);
+    xs[k] = p.x;
+    ys[k] = p.y;
+    zs[k] = p.z;
+    md[k] = INFINITY;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 c = __ldg(pts + first);
+  int cur = first;
+  __syncthreads();
+  for (int s = 0; s < n_nodes; ++s) {
+    if (rank == 0 && threadIdx.x == 0) out_ids[s] = cur;
+    float best = -1.0f;
+    int bi = 0x7fffffff;
+    for (int k = threadIdx.x; k < cnt; k += kFpsThreads) {
+      float d = dist2_rn(xs[k], ys[k], zs[k], c.x, c.y, c.z);
+      float m = md[k];
+      if (d < m) {
+        m = d;
+        md[k] = d;
+      }
+      if (m > best || (m == best && b0 + k < bi)) {
+        best = m;
+        bi = b0 + k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      sv[warp] = best;
+      si[warp] = bi;
+    }
+    __syncthreads();
+    const int slot = s & 1;
+    if (warp == 0) {
+      best = lane < kFpsThreads / 32 ? sv[lane] : -1.0f;
+      bi = lane < kFpsThreads / 32 ? si[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) {
+          best = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        FpsCand cd;
+        cd.v = best;
+        cd.i = bi;
+        const bool has = bi != 0x7fffffff;
+        cd.x = has ? xs[bi - b0] : 0.f;
+        cd.y = has ? ys[bi - b0] : 0.f;
+        cd.z = has ? zs[bi - b0] : 0.f;
+        cand[slot] = cd;
+      }
+    }
+    // candidates of all CTAs are published; a slot is rewritten two steps later, after every CTA has
+    // passed the barrier of the step in between (so nobody still reads it)
+    cl.sync();
+    FpsCand w;
+    w.v = -2.0f;
+    w.i = 0x7fffffff;
+    w.x = w.y = w.z = 0.f;
+    if (lane < kFpsCluster) w = *cl.map_shared_rank(&cand[slot], lane);
+#pragma unroll
+    for (int o = kFpsCluster / 2; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, w.v, o);
+      int oi = __shfl_xor_sync(0xffffffffu, w.i, o);
+      float ox = __shfl_xor_sync(0xffffffffu, w.x, o);
+      float oy = __shfl_xor_sync(0xffffffffu, w.y, o);
+      float oz = __shfl_xor_sync(0xffffffffu, w.z, o);
+      if (ov > w.v || (ov == w.v && oi < w.i)) {
+        w.v = ov; w.i = oi; w.x = ox; w.y = oy; w.z = oz;
+      }
+    }
+    cur = __shfl_sync(0xffffffffu, w.i, 0);
+    c.x = __shfl_sync(0xffffffffu, w.x, 0);
+    c.y = __shfl_sync(0xffffffffu, w.y, 0);
+    c.z = __shfl_sync(0xffffffffu, w.z, 0);
+  }
+  cl.sync();  // no CTA leaves while a peer may still read its candidate slots
 }
 
 // ------------------------------------------------------------------ per-vertex node weights
@@ -946,6 +1073,24 @@ int mvs_deform_sample_fps(mvs_deform* h, int64_t n_nodes, int64_t first_vertex) 
   MVS_TRY(ctx_ensure_device(ctx));
   int64_t n = h->n;
   if (n_nodes > n) n_nodes = n;
+  if (n <= (int64_t)kFpsCluster * kFpsCap) {
+    // small set: the whole sampling in one cluster launch
+    DevBuf<int> out;
+    MVS_TRY(out.reserve((size_t)n_nodes));
+    int per = (int)((n + kFpsCluster - 1) / kFpsCluster);
+    size_t smem = (size_t)per * 16;
+    MVS_CUDA(cudaFuncSetAttribute(k_fps_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kFpsCap * 16)));
+    {
+      ProfScope ps(ctx, "fps_cluster");
+      k_fps_cluster<<<kFpsCluster, kFpsThreads, smem, ctx->stream>>>(h->v0.p, (int)n, (int)n_nodes,
+                                                                      (int)first_vertex, out.p);
+    }
+    MVS_CUDA(cudaGetLastError());
+    std::vector<int32_t> ids((size_t)n_nodes);
+    MVS_TRY(d2h_sync(ctx, ids.data(), out.p, sizeof(int) * n_nodes));
+    return set_nodes_from_host(h, ids);
+  }
   int grid = grid_for(ctx, n, 256, 4);
   DevBuf<float> mind, pval;
   DevBuf<int> pidx, cur, out;

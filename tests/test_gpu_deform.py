@@ -49,6 +49,22 @@ def expand_system(rp, col, B, rot, rhs, lam=0.0):
     return H, rhs.astype(np.float64).ravel()
 
 
+@pytest.mark.parametrize("n,m,first", [(5, 5, 2), (9, 4, 0), (3001, 64, 17), (98304, 48, 5),
+                                       (98305, 48, 5), (150000, 40, 149999)])
+def test_fps_both_paths_match_oracle(ctx, n, m, first):
+    """Farthest point sampling: n <= 98304 runs as one thread-block-cluster launch (some of the 8
+    CTAs are empty at n = 5), larger sets one launch per node; both must give the oracle's ids,
+    including exact distance ties (lattice points) and m == n."""
+    rng = np.random.default_rng(n)
+    pts = rng.integers(-6, 7, size=(n, 3)).astype(np.float32) * 0.25  # many duplicates and ties
+    if n > 1000:
+        pts += rng.normal(size=(n, 3)).astype(np.float32) * (rng.random((n, 1)) < 0.5)
+    d = api.Deformation(pts, None, None, ctx)
+    ids = d.SampleFPS(m, first)
+    assert np.array_equal(ids, oracle.sample_fps(pts, m, first))
+    d.close()
+
+
 def test_sampling_matches_oracle(ctx):
     pts, nrm, faces = mesh()
     d = api.Deformation(pts, nrm, faces, ctx)
