@@ -112,6 +112,35 @@ def test_srt_closed_form_f32_float4(ctx):
     assert abs(s - so) <= SRT_RTOL * so and _rel(R, Ro) <= SRT_RTOL and _rel(t, to) <= SRT_RTOL
 
 
+@pytest.mark.parametrize("unit", [1e-22, 1e-9, 1.0, 1e9, 1e20])
+def test_srt_scale_norm_ratio_ranges(ctx, unit):
+    """The mean of |q-c2|/|p-c1| (SRTSolver.cpp:42-45) is evaluated with float32-seeded Newton
+    steps inside the float32 range of the squared norms and with plain float64 sqrt/div outside it
+    (units of 1e-22 and 1e20 here): both must agree with the oracle to ~1e-12, far inside the bar."""
+    p, q = synth.planted_pairs(20000, noise=1e-3)
+    p, q = p * unit, q * unit
+    solver = api.SRTSolver(10, ctx)
+    solver.SetPrintFlag(False)
+    solver.SetInput(p, q)
+    s, R, t = solver.EstimateTransform()
+    so, Ro, to = oracle.srt_estimate(p, q)
+    assert abs(s - so) <= 1e-12 * so
+    assert _rel(R, Ro) <= SRT_RTOL and _rel(t, to) <= SRT_RTOL
+
+
+def test_srt_point_at_centroid_behaves_like_reference(ctx):
+    """SRTSolver.cpp:44 divides by |p_i - centroid| without a guard: a point that IS the centroid
+    makes the scale non-finite in the reference; the device path keeps that (no silent clamp)."""
+    p = np.array([[-1, 0, 0], [1, 0, 0], [0, -1, 0], [0, 1, 0], [0, 0, -1], [0, 0, 1], [0, 0, 0]], float)
+    q = 2.0 * p + 1.0
+    solver = api.SRTSolver(10, ctx)
+    solver.SetPrintFlag(False)
+    solver.SetInput(p, q)
+    s, R, t = solver.EstimateTransform()
+    so, _, _ = oracle.srt_estimate(p, q)
+    assert not np.isfinite(so) and not np.isfinite(s)
+
+
 def test_srt_planted_recovered_and_reflection(ctx):
     p, q = synth.planted_pairs(4096, noise=0.0)
     solver = api.SRTSolver(10, ctx)
