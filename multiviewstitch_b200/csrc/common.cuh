@@ -70,6 +70,9 @@ struct mvs_ctx {
   // pinned staging for small readbacks (reductions, scalars)
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // two pinned chunks + events for large device -> pageable-host copies (d2h_sync)
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   // NCCL communicator (opaque here; see comm.cu)
   void* comm = nullptr;
   int nranks = 1;
@@ -173,5 +176,8 @@ int pinned_reserve(mvs_ctx* ctx, size_t bytes);
 // Host <-> device helpers on the context stream.
 int h2d(mvs_ctx* ctx, void* dst, const void* src, size_t bytes);
 int d2h_sync(mvs_ctx* ctx, void* dst, const void* src, size_t bytes);
+// device -> host on the context stream; large copies into pageable memory are staged through pinned
+// chunks (and are then complete on return), everything else completes at the next stream sync
+int d2h_async(mvs_ctx* ctx, void* dst, const void* src, size_t bytes);
 
 }  // namespace mvs

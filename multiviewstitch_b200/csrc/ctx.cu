@@ -1,4 +1,5 @@
 // ctx.cu — context lifetime, error string, profiling scopes, launch accounting.
+#include <algorithm>
 #include <stdarg.h>
 
 #include <mutex>
@@ -133,8 +134,54 @@ int h2d(mvs_ctx* ctx, void* dst, const void* src, size_t bytes) {
   return MVS_OK;
 }
 
-int d2h_sync(mvs_ctx* ctx, void* dst, const void* src, size_t bytes) {
+// Large copies into pageable (unpinned) caller memory go through two pinned 1 MiB chunks: the DMA of
+// chunk k+1 runs while the CPU copies chunk k out.  cudaMemcpyAsync straight into pageable memory
+// that was never touched (a fresh result vector, the normal case behind this ABI) pins and faults
+// the destination page by page inside the driver: 2.6-3.2 ms for the 8.6 MB of one 640x480
+// unprojection against 0.6 ms into warm memory.
+constexpr size_t kStageChunk = (size_t)1 << 20;
+constexpr size_t kStageMin = (size_t)1 << 19;
+
+static bool host_is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+int d2h_async(mvs_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes >= kStageMin && host_is_pageable(dst)) {
+    if (!ctx->stage[0]) {
+      for (int k = 0; k < 2; ++k) {
+        MVS_CUDA(cudaMallocHost(&ctx->stage[k], kStageChunk));
+        MVS_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+      }
+    }
+    const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+    auto issue = [&](size_t k) -> cudaError_t {
+      size_t off = k * kStageChunk, len = std::min(kStageChunk, bytes - off);
+      cudaError_t e = cudaMemcpyAsync(ctx->stage[k & 1], (const char*)src + off, len,
+                                      cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) return e;
+      return cudaEventRecord(ctx->stage_ev[k & 1], ctx->stream);
+    };
+    MVS_CUDA(issue(0));
+    for (size_t k = 0; k < nchunks; ++k) {
+      if (k + 1 < nchunks) MVS_CUDA(issue(k + 1));  // its buffer was copied out at step k - 1
+      MVS_CUDA(cudaEventSynchronize(ctx->stage_ev[k & 1]));
+      size_t off = k * kStageChunk, len = std::min(kStageChunk, bytes - off);
+      memcpy((char*)dst + off, ctx->stage[k & 1], len);
+    }
+    return MVS_OK;  // complete on return
+  }
   if (bytes) MVS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return MVS_OK;  // complete after the caller's stream synchronisation
+}
+
+int d2h_sync(mvs_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  MVS_TRY(d2h_async(ctx, dst, src, bytes));
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   return MVS_OK;
 }
@@ -157,6 +204,10 @@ static void ctx_free(mvs_ctx* ctx) {
   }
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int k = 0; k < 2; ++k) {
+    if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+    if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
+  }
   if (ctx->side) {
     cudaStreamSynchronize(ctx->side);
     cudaStreamDestroy(ctx->side);

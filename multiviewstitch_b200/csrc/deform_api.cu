@@ -628,13 +628,9 @@ static int get_f4_as_xyz(mvs_deform* h, const float4* src, int64_t n, double* ou
     else
       k_f4_to_f32xyz<<<div_up(n, 256), 256, 0, ctx->stream>>>(src, (float*)tmp, n);
   }
-  cudaError_t e = cudaMemcpyAsync(out64 ? (void*)out64 : (void*)out32, tmp, bytes,
-                                  cudaMemcpyDeviceToHost, ctx->stream);
+  int rc = d2h_async(ctx, out64 ? (void*)out64 : (void*)out32, tmp, bytes);
   cudaFreeAsync(tmp, ctx->stream);
-  if (e != cudaSuccess) {
-    set_error("get vertices: %s", cudaGetErrorString(e));
-    return MVS_ERR_CUDA;
-  }
+  if (rc != MVS_OK) return rc;
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   return MVS_OK;
 }
@@ -698,15 +694,15 @@ int mvs_deform_get_system(mvs_deform* h, int32_t* row_ptr, int32_t* col, float* 
   if (nnz) *nnz = h->nnz;
   cudaStream_t st = ctx->stream;
   if (row_ptr)
-    MVS_CUDA(cudaMemcpyAsync(row_ptr, h->row_ptr.p, sizeof(int) * (h->m + 1), cudaMemcpyDeviceToHost, st));
+    MVS_TRY(d2h_async(ctx, row_ptr, h->row_ptr.p, sizeof(int) * (h->m + 1)));
   if (col)
-    MVS_CUDA(cudaMemcpyAsync(col, h->col.p, sizeof(int) * h->nnz, cudaMemcpyDeviceToHost, st));
+    MVS_TRY(d2h_async(ctx, col, h->col.p, sizeof(int) * h->nnz));
   if (blocks)
-    MVS_CUDA(cudaMemcpyAsync(blocks, h->B(), sizeof(float) * 16 * h->nnz, cudaMemcpyDeviceToHost, st));
+    MVS_TRY(d2h_async(ctx, blocks, h->B(), sizeof(float) * 16 * h->nnz));
   if (rot)
-    MVS_CUDA(cudaMemcpyAsync(rot, h->Rot(), sizeof(float) * 81 * h->m, cudaMemcpyDeviceToHost, st));
+    MVS_TRY(d2h_async(ctx, rot, h->Rot(), sizeof(float) * 81 * h->m));
   if (rhs)
-    MVS_CUDA(cudaMemcpyAsync(rhs, h->rhs(), sizeof(float) * 12 * h->m, cudaMemcpyDeviceToHost, st));
+    MVS_TRY(d2h_async(ctx, rhs, h->rhs(), sizeof(float) * 12 * h->m));
   MVS_CUDA(cudaStreamSynchronize(st));
   return MVS_OK;
 }

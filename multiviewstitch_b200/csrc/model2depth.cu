@@ -375,8 +375,7 @@ int mvs_unproject_depth(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* 
         dout.p, dv.p);
   }
   MVS_CUDA(cudaGetLastError());
-  MVS_CUDA(cudaMemcpyAsync(out_xyz, dout.p, sizeof(double) * 3 * px, cudaMemcpyDeviceToHost,
-                           ctx->stream));
+  MVS_TRY(d2h_async(ctx, out_xyz, dout.p, sizeof(double) * 3 * px));
   return d2h_sync(ctx, valid, dv.p, sizeof(int) * px);
 }
 

@@ -582,11 +582,9 @@ static int knn_host_common(mvs_nn_index* idx, int64_t nq, int k, int32_t* out_id
   MVS_TRY(idx->o_d2.reserve((size_t)nq * k));
   MVS_TRY(nn_knn(idx, idx->q_in.p, nq, k, idx->o_idx.p, idx->o_d2.p));
   if (out_idx)
-    MVS_CUDA(cudaMemcpyAsync(out_idx, idx->o_idx.p, sizeof(int) * nq * k, cudaMemcpyDeviceToHost,
-                             ctx->stream));
+    MVS_TRY(d2h_async(ctx, out_idx, idx->o_idx.p, sizeof(int) * nq * k));
   if (out_d2)
-    MVS_CUDA(cudaMemcpyAsync(out_d2, idx->o_d2.p, sizeof(float) * nq * k, cudaMemcpyDeviceToHost,
-                             ctx->stream));
+    MVS_TRY(d2h_async(ctx, out_d2, idx->o_d2.p, sizeof(float) * nq * k));
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   return MVS_OK;
 }

@@ -310,9 +310,9 @@ int mvs_depth2model(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam,
                                                      tex_index ? dtex.p : nullptr);
     }
     if (out_xyz)
-      MVS_CUDA(cudaMemcpyAsync(out_xyz, dxyz.p, sizeof(double) * 3 * np, cudaMemcpyDeviceToHost, st));
+      MVS_TRY(d2h_async(ctx, out_xyz, dxyz.p, sizeof(double) * 3 * np));
     if (tex_index)
-      MVS_CUDA(cudaMemcpyAsync(tex_index, dtex.p, sizeof(int) * np, cudaMemcpyDeviceToHost, st));
+      MVS_TRY(d2h_async(ctx, tex_index, dtex.p, sizeof(int) * np));
   }
   if (nf > 0 && facets) {
     MVS_TRY(dfac.reserve((size_t)nf * 3));
@@ -321,7 +321,7 @@ int mvs_depth2model(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam,
       k_d2m_facets<<<div_up(nq, 256), 256, 0, st>>>(d.p, w, h, min_dsp, max_dsp, thr, tab.p, cnt.p,
                                                     dfac.p);
     }
-    MVS_CUDA(cudaMemcpyAsync(facets, dfac.p, sizeof(int) * 3 * nf, cudaMemcpyDeviceToHost, st));
+    MVS_TRY(d2h_async(ctx, facets, dfac.p, sizeof(int) * 3 * nf));
   }
   MVS_CUDA(cudaGetLastError());
   MVS_CUDA(cudaStreamSynchronize(st));

@@ -795,8 +795,7 @@ static int apply_common(mvs_ctx* ctx, double* pts, double* normals, int64_t n, d
   if (normals) MVS_TRY(upload_f64(ctx, normals, 3 * n, dn));
   MVS_TRY(ps_apply(w, dp.p, normals ? dn.p : nullptr, n, kAll, scale, R, t, inverse));
   if (normals)
-    MVS_CUDA(cudaMemcpyAsync(normals, dn.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost,
-                             ctx->stream));
+    MVS_TRY(d2h_async(ctx, normals, dn.p, sizeof(double) * 3 * n));
   return d2h_sync(ctx, pts, dp.p, sizeof(double) * 3 * n);
 }
 
@@ -1055,8 +1054,7 @@ int mvs_align(mvs_ctx* ctx, double* src_xyz, double* src_normals, int64_t n_src,
   }
   if (out_tgt_labels) memcpy(out_tgt_labels, h_tl.data(), sizeof(int32_t) * nt);
   if (src_normals)
-    MVS_CUDA(cudaMemcpyAsync(src_normals, dsn.p, sizeof(double) * 3 * n_src,
-                             cudaMemcpyDeviceToHost, st));
+    MVS_TRY(d2h_async(ctx, src_normals, dsn.p, sizeof(double) * 3 * n_src));
   return d2h_sync(ctx, src_xyz, ds.p, sizeof(double) * 3 * n_src);
 }
 

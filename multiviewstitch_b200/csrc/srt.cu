@@ -646,7 +646,7 @@ int mvs_srt_inliers(mvs_srt* h, double scale, const double R[9], const double t[
   }
   MVS_CUDA(cudaGetLastError());
   double sums[2];
-  MVS_CUDA(cudaMemcpyAsync(flags, dflags.p, (size_t)h->n, cudaMemcpyDeviceToHost, ctx->stream));
+  MVS_TRY(d2h_async(ctx, flags, dflags.p, (size_t)h->n));
   MVS_TRY(d2h_sync(ctx, sums, h->res.p + R_ACC, sizeof(sums)));
   if (err_sum) *err_sum = sums[0];
   if (n_inliers) *n_inliers = (int64_t)sums[1];
