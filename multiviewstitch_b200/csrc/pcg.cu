@@ -527,9 +527,11 @@ static int plan_pcg(mvs_deform* h) {
   if (h->pcg_plan_valid) return MVS_OK;
   mvs_ctx* ctx = h->ctx;
   int64_t m = h->m;
-  const int rs_opts[4] = {1, 2, 4, 8};
+  // the smallest row-slot count whose grid is co-resident: a CTA walks its RS slots one after the
+  // other in every phase, so 20,000 rows run 5 slots on 250 CTAs instead of 8 slots on 157
+  const int rs_opts[7] = {1, 2, 3, 4, 5, 6, 8};
   for (int stage = 1; stage >= 0; --stage) {
-    for (int oi = 0; oi < 4; ++oi) {
+    for (int oi = 0; oi < 7; ++oi) {
       int RS = rs_opts[oi];
       int rpc = RS * kGroups;
       int grid = (int)((m + rpc - 1) / rpc);
@@ -547,7 +549,10 @@ static int plan_pcg(mvs_deform* h) {
       switch (RS) {
         case 1: MVS_TRY(max_coresident<1>(smem, ctx->num_sms, &cap)); break;
         case 2: MVS_TRY(max_coresident<2>(smem, ctx->num_sms, &cap)); break;
+        case 3: MVS_TRY(max_coresident<3>(smem, ctx->num_sms, &cap)); break;
         case 4: MVS_TRY(max_coresident<4>(smem, ctx->num_sms, &cap)); break;
+        case 5: MVS_TRY(max_coresident<5>(smem, ctx->num_sms, &cap)); break;
+        case 6: MVS_TRY(max_coresident<6>(smem, ctx->num_sms, &cap)); break;
         default: MVS_TRY(max_coresident<8>(smem, ctx->num_sms, &cap)); break;
       }
       if (grid <= cap) {
@@ -617,7 +622,10 @@ int pcg_solve(mvs_deform* h) {
   switch (h->pcg_rs) {
     case 1: MVS_TRY(launch_pcg<1>(h, a, h->pcg_grid, h->pcg_smem)); break;
     case 2: MVS_TRY(launch_pcg<2>(h, a, h->pcg_grid, h->pcg_smem)); break;
+    case 3: MVS_TRY(launch_pcg<3>(h, a, h->pcg_grid, h->pcg_smem)); break;
     case 4: MVS_TRY(launch_pcg<4>(h, a, h->pcg_grid, h->pcg_smem)); break;
+    case 5: MVS_TRY(launch_pcg<5>(h, a, h->pcg_grid, h->pcg_smem)); break;
+    case 6: MVS_TRY(launch_pcg<6>(h, a, h->pcg_grid, h->pcg_smem)); break;
     default: MVS_TRY(launch_pcg<8>(h, a, h->pcg_grid, h->pcg_smem)); break;
   }
   MVS_CUDA(cudaGetLastError());
