@@ -253,6 +253,12 @@ int mvs_deform_set_target(mvs_deform* h, const double* tpts_xyz, const double* t
                           int64_t n_target);
 int mvs_deform_set_target_f32(mvs_deform* h, const float* tpts_xyz, const float* tnormals_xyz,
                               int64_t n_target);
+/* Target = the valid pixels of an inverse-depth image, unprojected and compacted in pixel order on
+ * the device: mvs_unproject_depth [ref: Image3D/Image3D.cpp:92-106] + "keep the valid points"
+ * [ref: Processor/Processor.cpp:1122-1137] + mvs_deform_set_target without the trip through host
+ * vectors (same points, same order, same float32 rounding).  n_target (optional): valid count. */
+int mvs_deform_set_target_depth(mvs_deform* h, const float* inv_depth, const mvs_camera* cam,
+                                double min_dsp, double max_dsp, int64_t* n_target);
 int mvs_deform_set_target_dev_f32(mvs_deform* h, const float* tpts_xyzw_dev,
                                   const float* tnormals_xyzw_dev, int64_t n_target);
 /* corr_mode 2 targets: per-vertex xyz + weight (0 = unconstrained). */
@@ -351,6 +357,12 @@ int mvs_check_consistency(mvs_ctx* ctx, float* depth, const mvs_camera* cam, con
  * valid iff min_dsp <= d <= max_dsp. out_xyz: w*h*3 doubles, valid: w*h flags. */
 int mvs_unproject_depth(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam,
                         double min_dsp, double max_dsp, double* out_xyz, int32_t* valid);
+/* The same unprojection [ref: Camera/Camera.cpp:40-44,61-67 GetWorldCoordFromImg] for a list of
+ * pixels uv (n x 2: column u, row v) — the matched pixels Processor feeds to SRTSolver
+ * [ref: Processor/Processor.cpp:806-811] — bit-identical to the rows of mvs_unproject_depth. */
+int mvs_unproject_pixels(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam, double min_dsp,
+                         double max_dsp, const int32_t* uv, int64_t n, double* out_xyz,
+                         int32_t* valid);
 
 /* ---------------------------------------------------------------- multi-GPU ---------------- */
 /* One process per GPU. id: 128-byte NCCL unique id produced on rank 0 and broadcast by the

@@ -441,6 +441,17 @@ class Deformation:
             check(lib().mvs_deform_set_target(self._h, _ptr(p, C.c_double), _ptr(nr, C.c_double),
                                               C.c_int64(len(p))))
 
+    def SetTargetDepth(self, inv_depth, cam: "Camera", min_dsp: float, max_dsp: float) -> int:
+        """Target = the valid pixels of an inverse-depth image, unprojected and compacted in pixel
+        order on the device (unproject_depth + boolean compaction + SetTarget without the host
+        round trip; identical points and order).  Returns the number of target points."""
+        a = _f32(inv_depth).reshape(cam.h, cam.w)
+        nt = C.c_int64(0)
+        check(lib().mvs_deform_set_target_depth(self._h, _ptr(a, C.c_float), C.byref(cam),
+                                                C.c_double(min_dsp), C.c_double(max_dsp),
+                                                C.byref(nt)))
+        return int(nt.value)
+
     def SetTargetDev(self, tpts_ptr: int, tnormals_ptr: int | None, nt: int):
         check(lib().mvs_deform_set_target_dev_f32(self._h, _dev(tpts_ptr),
                                                   _dev(tnormals_ptr) if tnormals_ptr else None,
@@ -783,6 +794,21 @@ def check_consistency(depth, cam: Camera, ref_depths, ref_cams, min_dsp, max_dsp
                                       _ptr(rd, C.c_float), arr, C.c_int(len(ref_cams)),
                                       C.c_double(min_dsp), C.c_double(max_dsp), C.c_double(reproj_err)))
     return d
+
+
+def unproject_pixels(inv_depth, cam: Camera, uv, min_dsp: float, max_dsp: float,
+                     ctx: Context | None = None):
+    """[ref: Camera/Camera.cpp:40-44,61-67] world points of the pixels uv (n x 2: column, row) ->
+    (points n x 3, valid n); bit-identical to the matching rows of unproject_depth."""
+    a = _f32(inv_depth).reshape(cam.h, cam.w)
+    px = np.ascontiguousarray(uv, np.int32).reshape(-1, 2)
+    out = np.empty((len(px), 3), np.float64)
+    valid = np.empty(len(px), np.int32)
+    check(lib().mvs_unproject_pixels(_ctxh(ctx), _ptr(a, C.c_float), C.byref(cam),
+                                     C.c_double(min_dsp), C.c_double(max_dsp),
+                                     _ptr(px, C.c_int32), C.c_int64(len(px)),
+                                     _ptr(out, C.c_double), _ptr(valid, C.c_int32)))
+    return out, valid
 
 
 def unproject_depth(inv_depth, cam: Camera, min_dsp: float, max_dsp: float,

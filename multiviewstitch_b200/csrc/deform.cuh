@@ -153,5 +153,8 @@ int arap_solve(mvs_deform* h, const double* ctrl_xyz_host, const int32_t* ctrl_i
 
 // pcg.cu
 int pcg_solve(mvs_deform* h);
+// model2depth.cu: inverse-depth image (host) -> valid world points compacted in pixel order (device)
+int unproject_compact_f4(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam, double min_dsp,
+                         double max_dsp, DevBuf<float4>& out, DevBuf<int>& scan_tmp, int64_t* count);
 
 }  // namespace mvs

@@ -358,6 +358,20 @@ int mvs_deform_set_target_f32(mvs_deform* h, const float* tpts, const float* tno
   return set_target_index(h, nt);
 }
 
+int mvs_deform_set_target_depth(mvs_deform* h, const float* inv_depth, const mvs_camera* cam,
+                                double min_dsp, double max_dsp, int64_t* n_target) {
+  MVS_REQUIRE(h && inv_depth && cam && cam->w > 0 && cam->h > 0, "bad argument");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  int64_t nt = 0;
+  DevBuf<int> scan_tmp;
+  MVS_TRY(unproject_compact_f4(h->ctx, inv_depth, cam, min_dsp, max_dsp, h->tp_own, scan_tmp, &nt));
+  if (n_target) *n_target = nt;
+  MVS_TRY(target_common(h, nt));
+  h->tp = h->tp_own.p;
+  h->tn = nullptr;
+  return set_target_index(h, nt);
+}
+
 int mvs_deform_set_target_dev_f32(mvs_deform* h, const float* tpts_dev, const float* tnormals_dev,
                                   int64_t nt) {
   MVS_REQUIRE(h && tpts_dev, "null argument");

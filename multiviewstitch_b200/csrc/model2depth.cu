@@ -271,11 +271,134 @@ __global__ void k_unproject(const float* __restrict__ dsp, int w, int h, double 
                                __dmul_rn(Rt[6 + a], c2));
 }
 
+// the same arithmetic for a list of pixels (u, v): out n x 3, valid n
+__global__ void k_unproject_pixels(const float* __restrict__ dsp_at, const int* __restrict__ uv,
+                                   int64_t n, double fx, double cx, double fy, double cy,
+                                   const double* __restrict__ Rt, double min_dsp, double max_dsp,
+                                   double* __restrict__ out, int* __restrict__ valid) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int i = uv[2 * k], j = uv[2 * k + 1];
+  double d = (double)dsp_at[k];
+  if (d < min_dsp || d > max_dsp) {
+    valid[k] = 0;
+    out[3 * k] = out[3 * k + 1] = out[3 * k + 2] = 0.0;
+    return;
+  }
+  valid[k] = 1;
+  double z = __ddiv_rn(1.0, d);
+  double c0 = __dsub_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)i, cx), z), fx), Rt[9]);
+  double c1 = __dsub_rn(__ddiv_rn(__dmul_rn(__dsub_rn((double)j, cy), z), fy), Rt[10]);
+  double c2 = __dsub_rn(z, Rt[11]);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    out[3 * k + a] = __dadd_rn(__dadd_rn(__dmul_rn(Rt[a], c0), __dmul_rn(Rt[3 + a], c1)),
+                               __dmul_rn(Rt[6 + a], c2));
+}
+
+// valid points in pixel order -> float4 (the rounding of k_xyz_f64_to_f4); prefix = exclusive scan of
+// the valid flags with the total at prefix[n]
+__global__ void k_compact_valid_f4(const double* __restrict__ xyz, const int* __restrict__ prefix,
+                                   int64_t n, float4* __restrict__ out) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int at = prefix[k];
+  if (prefix[k + 1] == at) return;
+  out[at] = make_float4((float)xyz[3 * k], (float)xyz[3 * k + 1], (float)xyz[3 * k + 2], 0.f);
+}
+
+// Inverse-depth image (host) -> the valid world points, compacted in pixel order, as float4 on the
+// device: the unprojection of mvs_unproject_depth followed by what a caller does with its result
+// before Deformation::Deform (keep the valid points, Processor.cpp:1122-1137) without the trip
+// through host vectors.  *count = number of valid points.
+int unproject_compact_f4(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam, double min_dsp,
+                         double max_dsp, DevBuf<float4>& out, DevBuf<int>& scan_tmp, int64_t* count) {
+  size_t px = (size_t)cam->w * cam->h;
+  DevBuf<float> din;
+  DevBuf<double> dout, drt;
+  DevBuf<int> dv;
+  MVS_TRY(din.reserve(px));
+  MVS_TRY(dout.reserve(px * 3));
+  MVS_TRY(dv.reserve(px + 2));
+  MVS_TRY(drt.reserve(12));
+  MVS_TRY(out.reserve(px));
+  double rt[12];
+  for (int i = 0; i < 9; ++i) rt[i] = cam->R[i];
+  for (int i = 0; i < 3; ++i) rt[9 + i] = cam->t[i];
+  MVS_TRY(h2d(ctx, din.p, inv_depth, sizeof(float) * px));
+  MVS_TRY(h2d(ctx, drt.p, rt, sizeof(rt)));
+  {
+    ProfScope ps(ctx, "unproject_depth");
+    k_unproject<<<div_up((int64_t)px, 256), 256, 0, ctx->stream>>>(
+        din.p, cam->w, cam->h, cam->K[0], cam->K[2], cam->K[4], cam->K[5], drt.p, min_dsp, max_dsp,
+        dout.p, dv.p);
+  }
+  MVS_CUDA(cudaMemsetAsync(dv.p + px, 0, sizeof(int) * 2, ctx->stream));
+  MVS_TRY(exclusive_scan_inplace(ctx, dv.p, (int64_t)px, scan_tmp));
+  {
+    ProfScope ps(ctx, "compact_valid");
+    k_compact_valid_f4<<<div_up((int64_t)px, 256), 256, 0, ctx->stream>>>(dout.p, dv.p, (int64_t)px,
+                                                                           out.p);
+  }
+  MVS_CUDA(cudaGetLastError());
+  int total = 0;
+  MVS_TRY(d2h_sync(ctx, &total, dv.p + px, sizeof(int)));  // rt[] and the temporaries stay alive
+  *count = total;
+  return MVS_OK;
+}
+
 }  // namespace mvs
 
 using namespace mvs;
 
 extern "C" {
+
+int mvs_unproject_pixels(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam, double min_dsp,
+                         double max_dsp, const int32_t* uv, int64_t n, double* out_xyz,
+                         int32_t* valid) {
+  if (!ctx) ctx = default_ctx();
+  if (!ctx) return MVS_ERR_NO_DEVICE;
+  MVS_TRY(ctx_ensure_device(ctx));
+  if (!inv_depth || !cam || !out_xyz || !valid || (n > 0 && !uv) || n < 0 || cam->w <= 0 ||
+      cam->h <= 0) {
+    set_error("unproject_pixels: bad argument");
+    return MVS_ERR_INVALID_ARG;
+  }
+  if (n == 0) return MVS_OK;
+  std::vector<float> at((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    int u = uv[2 * k], v = uv[2 * k + 1];
+    if (u < 0 || v < 0 || u >= cam->w || v >= cam->h) {
+      set_error("unproject_pixels: pixel %lld = (%d, %d) outside the %d x %d image", (long long)k, u,
+                v, cam->w, cam->h);
+      return MVS_ERR_INVALID_ARG;
+    }
+    at[(size_t)k] = inv_depth[(size_t)v * cam->w + u];
+  }
+  DevBuf<float> dat;
+  DevBuf<int> duv, dv;
+  DevBuf<double> dout, drt;
+  MVS_TRY(dat.reserve((size_t)n));
+  MVS_TRY(duv.reserve((size_t)n * 2));
+  MVS_TRY(dv.reserve((size_t)n));
+  MVS_TRY(dout.reserve((size_t)n * 3));
+  MVS_TRY(drt.reserve(12));
+  double rt[12];
+  for (int i = 0; i < 9; ++i) rt[i] = cam->R[i];
+  for (int i = 0; i < 3; ++i) rt[9 + i] = cam->t[i];
+  MVS_TRY(h2d(ctx, dat.p, at.data(), sizeof(float) * n));
+  MVS_TRY(h2d(ctx, duv.p, uv, sizeof(int) * 2 * n));
+  MVS_TRY(h2d(ctx, drt.p, rt, sizeof(rt)));
+  {
+    ProfScope ps(ctx, "unproject_pixels");
+    k_unproject_pixels<<<div_up(n, 128), 128, 0, ctx->stream>>>(
+        dat.p, duv.p, n, cam->K[0], cam->K[2], cam->K[4], cam->K[5], drt.p, min_dsp, max_dsp, dout.p,
+        dv.p);
+  }
+  MVS_CUDA(cudaGetLastError());
+  MVS_TRY(d2h_async(ctx, out_xyz, dout.p, sizeof(double) * 3 * n));
+  return d2h_sync(ctx, valid, dv.p, sizeof(int) * n);
+}
 
 int mvs_model2depth(mvs_ctx* ctx, const float* pts_xyz, int64_t n, const int32_t* facets,
                     int64_t n_facets, const mvs_camera* cams, int ncams, float znear, float zfar,

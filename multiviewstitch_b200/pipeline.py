@@ -74,15 +74,28 @@ def lattice_matches(points_a, valid_a, cam_b_tuple, valid_b, planted, w, h, step
 
 
 def stitch_pair(depth_a, cam_a, depth_b, cam_b, matches, ctx=None, n_nodes=512, gn_iters=4,
-                pcg_iters=20, seed=0, iter_num=200, pixel_err=60.0, adapt_ratio=0.75):
+                pcg_iters=20, seed=0, iter_num=200, pixel_err=60.0, adapt_ratio=0.75,
+                host_vectors=False):
     """One view pair through the hot path.  cam_a / cam_b: api.Camera.  matches: (n, 4) int pixel
-    pairs (u1, v1, u2, v2).  Returns a dict with every intermediate the tests compare."""
+    pairs (u1, v1, u2, v2).  Returns a dict with every intermediate the tests compare.
+
+    host_vectors=True follows the reference call for call — both views are unprojected into full
+    h*w host vectors (Image3D::SolveUnProjectionD), the matches and the valid target points are
+    picked out of them on the host and the target goes back to the device through SetTarget.  The
+    default keeps those intermediates on the device: only the matched pixels are unprojected
+    (unproject_pixels) and the target is unprojected + compacted where it is used
+    (Deformation.SetTargetDepth).  Both give bit-identical results (tests/test_gpu_pipeline.py);
+    the host-vector form moves 17 MB per pair through pageable memory."""
     w, h = cam_a.w, cam_a.h
-    pts_a, val_a = api.unproject_depth(depth_a, cam_a, MIN_DSP, MAX_DSP, ctx)
-    pts_b, val_b = api.unproject_depth(depth_b, cam_b, MIN_DSP, MAX_DSP, ctx)
-    ka = matches[:, 1] * w + matches[:, 0]
-    kb = matches[:, 3] * w + matches[:, 2]
-    p, q = pts_a[ka], pts_b[kb]
+    if host_vectors:
+        pts_a, val_a = api.unproject_depth(depth_a, cam_a, MIN_DSP, MAX_DSP, ctx)
+        pts_b, val_b = api.unproject_depth(depth_b, cam_b, MIN_DSP, MAX_DSP, ctx)
+        ka = matches[:, 1] * w + matches[:, 0]
+        kb = matches[:, 3] * w + matches[:, 2]
+        p, q = pts_a[ka], pts_b[kb]
+    else:
+        p, _ = api.unproject_pixels(depth_a, cam_a, matches[:, 0:2], MIN_DSP, MAX_DSP, ctx)
+        q, _ = api.unproject_pixels(depth_b, cam_b, matches[:, 2:4], MIN_DSP, MAX_DSP, ctx)
     keep, err, _ = api.remove_outliers(p, q, cam_a, cam_b, 3, iter_num, pixel_err, adapt_ratio, seed, ctx)
     solver = api.SRTSolver(iter_num, ctx)
     solver.SetPrintFlag(False)
@@ -93,10 +106,14 @@ def stitch_pair(depth_a, cam_a, depth_b, cam_b, matches, ctx=None, n_nodes=512, 
     # template = view-1 mesh in the frame of view 2
     va, tex_a, fa = api.depth2model(depth_a, cam_a, MIN_DSP, MAX_DSP, SMOOTH_THRES, ctx)
     va_b, _ = api.apply_srt(va, None, scale, R, t, ctx=ctx)
-    tgt = pts_b[np.flatnonzero(val_b)]  # (integer take: 3x faster than a boolean mask here)
     d = api.Deformation(va_b, None, fa, ctx)
     d.SampleFPS(min(n_nodes, len(va_b)), 0)
-    d.SetTarget(tgt)
+    if host_vectors:
+        tgt = pts_b[np.flatnonzero(val_b)]  # (integer take: 3x faster than a boolean mask here)
+        d.SetTarget(tgt)
+    else:
+        tgt = None
+        d.SetTargetDepth(depth_b, cam_b, MIN_DSP, MAX_DSP)
     d.GNBegin(api.gn_params(gn_iters=gn_iters, pcg_iters=pcg_iters, corr_mode=1))
     for _ in range(gn_iters):
         d.GNStep()

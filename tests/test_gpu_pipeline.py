@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from multiviewstitch_b200 import api, pipeline
+from multiviewstitch_b200 import _capi, api, pipeline
 from tests import synth
 
 pytestmark = pytest.mark.gpu
@@ -90,7 +90,28 @@ def test_two_view_pair_end_to_end(ctx):
     pb, vb = api.unproject_depth(db, cb, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
     matches = pipeline.lattice_matches(pa, va, sc["cam_b"], vb, sc["planted"], w, h, seed=0)
     assert len(matches) > 60
-    out = pipeline.stitch_pair(da, ca, db, cb, matches, ctx, n_nodes=256, gn_iters=3, seed=3)
+    out = pipeline.stitch_pair(da, ca, db, cb, matches, ctx, n_nodes=256, gn_iters=3, seed=3,
+                               host_vectors=True)
+    # ---- the device-resident form of the same pair (matched pixels unprojected on their own, target
+    # unprojected + compacted where it is used) gives the same bits at every stage
+    dev = pipeline.stitch_pair(da, ca, db, cb, matches, ctx, n_nodes=256, gn_iters=3, seed=3)
+    assert dev["scale"] == out["scale"] and np.array_equal(dev["R"], out["R"])
+    assert np.array_equal(dev["t"], out["t"]) and np.array_equal(dev["kept"], out["kept"])
+    assert dev["err"] == out["err"] and dev["residual"] == out["residual"]
+    assert np.array_equal(dev["template"], out["template"])
+    assert np.array_equal(dev["deformed"], out["deformed"])
+    assert np.array_equal(dev["render"], out["render"])
+    uv = np.concatenate([matches[:, 0:2], [[0, 0], [w - 1, h - 1]]]).astype(np.int32)
+    pp, pv = api.unproject_pixels(da, ca, uv, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
+    rows = uv[:, 1] * w + uv[:, 0]
+    assert np.array_equal(pp, pa[rows]) and np.array_equal(pv, va[rows])
+    with pytest.raises(_capi.MvsError):
+        api.unproject_pixels(da, ca, [[w, 0]], pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
+    dd = api.Deformation(out["template"], None, out["facets"], ctx)
+    assert dd.SetTargetDepth(db, cb, pipeline.MIN_DSP, pipeline.MAX_DSP) == int(vb.sum())
+    with pytest.raises(_capi.MvsError):  # no valid pixel: an error code, not an empty index
+        dd.SetTargetDepth(np.zeros_like(db), cb, pipeline.MIN_DSP, pipeline.MAX_DSP)
+    dd.close()
     # ---- oracle pipeline, stage by stage
     opa, ova = oracle.unproject_depth(da, oa, pipeline.MIN_DSP, pipeline.MAX_DSP)
     opb, ovb = oracle.unproject_depth(db, ob, pipeline.MIN_DSP, pipeline.MAX_DSP)
