@@ -319,10 +319,11 @@ def test_export_obj_format(ctx, tmp_path):
     assert fl[0] == f"f {a[0]}//{a[0]} {a[1]}//{a[1]} {a[2]}//{a[2]}"
 
 
-@pytest.mark.parametrize("m", [6000, 12000])
+@pytest.mark.parametrize("m", [6000, 12000, 20000])
 def test_many_nodes_multi_slot_pcg_parity(ctx, m):
     """More node rows than one co-resident wave of 16-lane row groups (148 SMs x 2 CTAs x 16):
-    the persistent PCG kernel runs 2 (m = 6000) / 4 (m = 12000) row slots per lane group."""
+    the persistent PCG kernel runs 2 (m = 6000) / 3 (m = 12000) / 5 (m = 20000, the C5 node count)
+    row slots per lane group."""
     verts, faces = synth.cube_sphere(64)  # 24,578 vertices
     pts = verts.astype(np.float32)
     d = api.Deformation(pts, None, faces, ctx)
@@ -357,6 +358,54 @@ def test_solve_is_bitwise_reproducible(ctx):
         d.GNEnd()
         outs.append((d.Vertices(), d.NodeState()))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_handles_interleaved_and_reused_stay_bitwise_identical(ctx):
+    """Two deformation handles stepped alternately on one context (each step forks its node terms
+    and preconditioner to the context's side stream), and one handle reused for solves with
+    different PCG iteration counts (the persistent solver re-arms its exchange buffers for the next
+    launch): every solve must equal the same solve run alone on a fresh handle, bit for bit."""
+    verts, faces = synth.cube_sphere(40)
+    pts = verts.astype(np.float32)
+    tv = synth.bend_twist(synth.cube_sphere(44, rot=synth.axis_angle([1, 2, 3], 0.7))[0], 0.04).astype(np.float32)
+    tw = synth.bend_twist(synth.cube_sphere(46, rot=synth.axis_angle([3, 1, 2], 0.3))[0], 0.03).astype(np.float32)
+
+    def fresh(target, gn, pcg):
+        d = api.Deformation(pts, None, faces, ctx)
+        d.SampleFPS(200, 0)
+        d.SetTarget(target)
+        d.GNBegin(api.gn_params(gn_iters=gn, pcg_iters=pcg, corr_mode=1))
+        for _ in range(gn):
+            d.GNStep()
+        d.GNEnd()
+        out = d.Vertices()
+        d.close()
+        return out
+
+    ref_a, ref_b = fresh(tv, 4, 20), fresh(tw, 4, 7)
+    a = api.Deformation(pts, None, faces, ctx)
+    b = api.Deformation(pts, None, faces, ctx)
+    for d, t in ((a, tv), (b, tw)):
+        d.SampleFPS(200, 0)
+        d.SetTarget(t)
+    a.GNBegin(api.gn_params(gn_iters=4, pcg_iters=20, corr_mode=1))
+    b.GNBegin(api.gn_params(gn_iters=4, pcg_iters=7, corr_mode=1))
+    for _ in range(4):
+        a.GNStep()
+        b.GNStep()
+    a.GNEnd()
+    b.GNEnd()
+    assert np.array_equal(a.Vertices(), ref_a) and np.array_equal(b.Vertices(), ref_b)
+    # the same handle again: other target, other PCG iteration count, then the first setting again
+    for target, pcg, ref in ((tw, 7, ref_b), (tv, 20, ref_a), (tv, 20, ref_a)):
+        a.SetTarget(target)
+        a.GNBegin(api.gn_params(gn_iters=4, pcg_iters=pcg, corr_mode=1))
+        for _ in range(4):
+            a.GNStep()
+        a.GNEnd()
+        assert np.array_equal(a.Vertices(), ref)
+    a.close()
+    b.close()
 
 
 def test_weighted_targets_and_large_coordinates(ctx):
