@@ -204,7 +204,10 @@ __device__ __forceinline__ long long fx_limb(double v, const FxUnit& u, int limb
   return (long long)l;
 }
 
-template <int N>
+// FENCE = false: a pure all-reduce.  The p.q exchange needs no memory ordering — the search
+// directions a CTA stored before it are read by other CTAs only after the NEXT (fenced) exchange —
+// so it skips the release/acquire fences (each waits for the CTA's outstanding stores).
+template <int N, bool FENCE = true>
 __device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
                                                  unsigned long long* words, unsigned& wi, int ncta,
                                                  const FxUnit (&unit)[N], double (&out)[N]) {
@@ -227,7 +230,7 @@ __device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
     if (N > 1 && j == 1) u = unit[N - 1];
     long long fxv = fx_limb(s, u, limb);
     unsigned long long enc = (unsigned long long)(fxv + kLimbBias) + (1ull << kCountShift);
-    if (threadIdx.x == 0) fence_acq_rel();  // publish what this CTA wrote before the call
+    if (FENCE && threadIdx.x == 0) fence_acq_rel();  // publish what this CTA wrote before the call
     __syncwarp((1u << (2 * N)) - 1u);
     unsigned long long* wd = words + wi + threadIdx.x;
     atomicAdd(wd, enc);
@@ -235,7 +238,7 @@ __device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
     unsigned spins = 0;
     while (((b = ld_word(wd)) >> kCountShift) < (unsigned long long)ncta)
       if (++spins > (1u << 26)) __trap();  // a lost CTA becomes an error, not a hang
-    if (threadIdx.x == 0) fence_acq_rel();
+    if (FENCE && threadIdx.x == 0) fence_acq_rel();
     long long sum = (long long)(b & ((1ull << kCountShift) - 1ull)) - (long long)ncta * kLimbBias;
     red2[threadIdx.x] = (double)sum;
   }
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
       grid_exchange<1>(pq, red, a.ring, phase, ncta, pqa);
       unit_a[0] = fx_unit_for(fabs(pqa[0]));
     } else {
-      grid_exchange_fx<1>(pq, red, a.words, wi, ncta, unit_a, pqa);
+      grid_exchange_fx<1, false>(pq, red, a.words, wi, ncta, unit_a, pqa);
     }
     // ---- phase B: alpha ; delta += alpha p ; r -= alpha q ; z = M^-1 r ; r.z, |r|^2
     double pqt = pqa[0];
