@@ -292,6 +292,44 @@ def secondary_c2(args, api, ctx, stream, peak):
                                   "max_abs_error_vs_planted": err,
                                   "note": "includes the D2H read of (s,R,t); noise 1e-3 on 1e7 pairs"}
         index.close(); srt.close()
+        # configs[1] is a sweep: the same two measurements on the first n points of the set
+        sweep = []
+        for ns in (10_000, 100_000, 1_000_000):
+            if ns >= n:
+                continue
+            tq = q4s[:ns].contiguous()
+            qq = query[:ns].contiguous()
+            ix = api.NNIndex(ctx)
+            ix.build_dev(tq.data_ptr(), ns)
+            ix.knn_dev(qq.data_ptr(), ns, 1, idx_out.data_ptr(), d2_out.data_ptr())
+            best_nn = None
+            for rep in range(3):
+                ev[0].record(stream)
+                ix.knn_dev(qq.data_ptr(), ns, 1, idx_out.data_ptr(), d2_out.data_ptr())
+                ev[1].record(stream)
+                stream.synchronize()
+                ms = ev[0].elapsed_time(ev[1])
+                best_nn = ms if best_nn is None else min(best_nn, ms)
+            ix.close()
+            sr = api.SRTSolver(10, ctx)
+            sr.SetPrintFlag(False)
+            sr.SetInputDev(p4.data_ptr(), q4.data_ptr(), ns)
+            sr.EstimateTransform()
+            best_srt = None
+            for rep in range(3):
+                ev[2].record(stream)
+                sr.EstimateTransform()
+                ev[3].record(stream)
+                stream.synchronize()
+                ms = ev[2].elapsed_time(ev[3])
+                best_srt = ms if best_srt is None else min(best_srt, ms)
+            sr.close()
+            sweep.append({"points": ns, "nn_ms": best_nn, "nn_corr_per_s": ns / (best_nn * 1e-3),
+                          "srt_ms": best_srt, "srt_pairs_per_s": ns / (best_srt * 1e-3)})
+        sweep.append({"points": n, "nn_ms": out["nn_corr"]["ms"], "nn_corr_per_s": out["nn_corr"]["value"],
+                      "srt_ms": out["srt_closed_form"]["ms"],
+                      "srt_pairs_per_s": out["srt_closed_form"]["value"]})
+        out["c2_sweep"] = sweep
     return out
 
 
