@@ -252,6 +252,21 @@ class Deformation {
     else
       check(mvs_deform_run(h_, projLenErr, projDistErr, &gn));
   }
+  // Device-side shortcut (not in the reference): the target is the set of valid pixels of an
+  // inverse-depth image — Image3D::SolveUnProjectionD (Image3D.cpp:92-106) + "keep the valid points"
+  // + Deform's target upload, without the host vectors.  Then run with DeformCurrentTarget().
+  int64_t SetTargetDepth(const std::vector<float>& inv_depth, const Camera& cam, double minDsp,
+                         double maxDsp) {
+    int64_t nt = 0;
+    check(mvs_deform_set_target_depth(h_, inv_depth.data(), &cam.c(), minDsp, maxDsp, &nt));
+    return nt;
+  }
+  void DeformCurrentTarget(double projLenErr, double projDistErr) {
+    if (solver == ARAP)
+      check(mvs_deform_run_arap(h_, projLenErr, projDistErr, &arap));
+    else
+      check(mvs_deform_run(h_, projLenErr, projDistErr, &gn));
+  }
   // replace CGAL's Polyhedron() accessor (Deformation.h:233)
   std::vector<Vector3d> Vertices() const {
     std::vector<Vector3d> out(count());
