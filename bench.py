@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="objects", choices=["objects", "shard", "pairs"])
     ap.add_argument("--pairs", type=int, default=28, help="view pairs of --mode pairs (C(8,2) = 28)")
+    ap.add_argument("--pair-workers", type=int, default=0,
+                    help="--mode pairs: host threads per rank, each with its own context/stream, "
+                         "working through the rank's pairs concurrently (independent units); "
+                         "0 = min(4, host cores / ranks)")
     ap.add_argument("--side", type=int, default=408, help="cube-sphere grid side (verts = 6*side^2+2)")
     ap.add_argument("--nodes", type=int, default=4096)
     ap.add_argument("--gn-iters", type=int, default=10)
@@ -416,9 +420,34 @@ def run_pairs(args):
             mt = pipeline.lattice_matches(pa, va, sc["cam_b"], vb, sc["planted"], 640, 480, seed=u)
             work.append((da, ca, db, cb, mt, sc["planted"], u))
 
-        def step():
-            return [pipeline.stitch_pair(da, ca, db, cb, mt, ctx, n_nodes=512, gn_iters=4, seed=u)
-                    for da, ca, db, cb, mt, _, u in work]
+        want = args.pair_workers if args.pair_workers > 0 else min(4, max(1, (os.cpu_count() or 1) // world))
+        nw = max(1, min(want, len(work)))
+        if nw == 1:
+            def step():
+                return [pipeline.stitch_pair(da, ca, db, cb, mt, ctx, n_nodes=512, gn_iters=4, seed=u)
+                        for da, ca, db, cb, mt, _, u in work]
+        else:
+            # independent pairs: nw host threads, each with its own context (own stream, own side
+            # stream); a pair's launches and host glue overlap with the other workers' — the ctypes
+            # calls release the GIL.  Every worker synchronises its context before the step returns,
+            # so the CUDA events that bracket the step on `stream` span all of the work.
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(nw)
+            wctx = [api.Context(local) for _ in range(nw)]
+
+            def run_share(k):
+                res = [(i, pipeline.stitch_pair(*work[i][:5], wctx[k], n_nodes=512, gn_iters=4,
+                                                seed=work[i][6]))
+                       for i in range(k, len(work), nw)]
+                wctx[k].sync()
+                return res
+
+            def step():
+                res = [None] * len(work)
+                for part in pool.map(run_share, range(nw)):
+                    for i, o in part:
+                        res[i] = o
+                return res
 
         def barrier():
             if world > 1:
@@ -428,6 +457,9 @@ def run_pairs(args):
         for _ in range(max(3, args.warmup)):
             outs = step()
         ctx.launch_count_reset()
+        if nw > 1:
+            for c in wctx:
+                c.launch_count_reset()
         clocks = Clocks(local)
         if rank == 0:
             clocks.start()
@@ -440,7 +472,7 @@ def run_pairs(args):
             ev[s][1].record(stream)
         barrier()
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-        launches = ctx.launch_count()
+        launches = ctx.launch_count() if nw == 1 else sum(c.launch_count() for c in wctx)
         clk = clocks.stop() if rank == 0 else None
     # every pair must recover its planted similarity
     worst = 0.0
@@ -458,7 +490,8 @@ def run_pairs(args):
                 "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
                 "config": {"workload": f"C4: {args.pairs} view pairs (two 640x480 depth maps each) sharded "
                                        "pair -> rank u % N, SRT + deformation + Model2Depth per pair",
-                           "pairs_on_busiest_rank": -(-args.pairs // world), "l2": "host buffers per pair"},
+                           "pairs_on_busiest_rank": -(-args.pairs // world), "l2": "host buffers per pair",
+                           "host_workers_per_rank": nw},
                 "max_srt_error_vs_planted": worst, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line), flush=True)
     if world > 1:
