@@ -185,3 +185,66 @@ def test_vertex_normals_sphere():
     radial = verts / np.linalg.norm(verts, axis=1, keepdims=True)
     assert np.all(np.sum(n * radial, 1) > 0.99)
     assert np.allclose(n, synth.vertex_normals(verts, faces), atol=1e-12)
+
+
+def test_pipelined_pcg_recurrences_track_standard_pcg():
+    """Pins the plan of DESIGN.md §8 (one exchange per PCG iteration): the pipelined recurrences of
+    Ghysels & Vanroose reproduce the oracle's standard PCG iterates in float64; with float32 vectors
+    they drift far more than standard float32 PCG does; with float64 recurrences and a float64 halo
+    (float32 matrix and preconditioner) they are at least as close to the oracle as the float32
+    standard kernel.  Real normal equations of the embedded-deformation solve, 20 iterations."""
+    verts, faces = synth.cube_sphere(24)
+    pts = verts.astype(np.float32)
+    m = 200
+    ids = oracle.sample_fps(pts, m, 0)
+    widx, w = oracle.node_weights(pts, pts[ids], 4)
+    graph = oracle.node_graph(pts[ids], 8)
+    prm = oracle.gn_params(gn_iters=1, pcg_iters=20)
+    x0 = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float64), (m, 1))
+    H, g = oracle.gn_assemble_dense(pts, ids, widx, w, graph, synth.bend_twist(verts, 0.05), None, prm, x0)
+    H = H + prm.lam * np.eye(len(g)) if hasattr(prm, "lam") else H
+    b = (-g).astype(np.float32).astype(np.float64)  # the device holds the gradient in float32
+    N = len(b)
+    Minv = np.zeros_like(H)
+    for j in range(N // 12):
+        sl = slice(12 * j, 12 * j + 12)
+        Minv[sl, sl] = np.linalg.inv(H[sl, sl])
+    d64 = lambda a, c: float(np.dot(a.astype(np.float64), c.astype(np.float64)))
+
+    def standard(dt):
+        A, Mi = H.astype(dt), Minv.astype(dt)
+        x = np.zeros(N, dt); r = b.astype(dt); z = Mi @ r; p = z.copy(); rz = d64(r, z)
+        for _ in range(20):
+            q = A @ p
+            a = dt(rz / d64(p, q))
+            x = x + a * p; r = r - a * q; z = Mi @ r
+            rzn = d64(r, z); p = z + dt(rzn / rz) * p; rz = rzn
+        return x.astype(np.float64)
+
+    def pipelined(vec, mat, halo):
+        A, Mi = H.astype(mat).astype(vec), Minv.astype(mat).astype(vec)
+        x = np.zeros(N, vec); r = b.astype(vec); u = Mi @ r
+        wv = A @ u.astype(halo).astype(vec)
+        z = np.zeros(N, vec); q = z.copy(); s = z.copy(); p = z.copy()
+        go = ao = 1.0
+        for it in range(20):
+            gam, dl = d64(r, u), d64(wv, u)
+            mm = Mi @ wv
+            nn = A @ mm.astype(halo).astype(vec)
+            be = gam / go if it else 0.0
+            al = gam / (dl - be * gam / ao) if it else gam / dl
+            be_, al_ = vec(be), vec(al)
+            z = nn + be_ * z; q = mm + be_ * q; s = wv + be_ * s; p = u + be_ * p
+            x = x + al_ * p; r = r - al_ * s; u = u - al_ * q; wv = wv - al_ * z
+            go, ao = gam, al
+        return x.astype(np.float64)
+
+    ref = standard(np.float64)
+    rel = lambda x: np.linalg.norm(x - ref) / np.linalg.norm(ref)
+    e_std32 = rel(standard(np.float32))
+    e_p64 = rel(pipelined(np.float64, np.float64, np.float64))
+    e_p32 = rel(pipelined(np.float32, np.float32, np.float32))
+    e_mixed = rel(pipelined(np.float64, np.float32, np.float64))
+    assert e_p64 < 1e-10                       # same iterates in exact arithmetic
+    assert e_p32 > 5 * e_std32                 # float32 recurrences drift
+    assert e_mixed < 5e-6 and e_mixed < 5 * max(e_std32, 1e-7)   # float64 recurrences + halo do not
