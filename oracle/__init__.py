@@ -28,6 +28,22 @@ def build(force: bool = False) -> Path:
     return _LIB_PATH
 
 
+_LIB_MT_PATH = _LIB_PATH.parent / "liboracle_mt.so"
+
+
+def build_mt() -> Path | None:
+    """The OpenMP courtesy build (same sources, -fopenmp).  Optional: None when the toolchain has no
+    libgomp.  Only bench.py's courtesy multi-thread timing uses it; tests and parity never do."""
+    build()
+    srcs = list(_HERE.glob("*.cpp")) + list(_HERE.glob("*.h")) + [_HERE / "Makefile"]
+    stale = (not _LIB_MT_PATH.exists()) or any(s.stat().st_mtime > _LIB_MT_PATH.stat().st_mtime for s in srcs)
+    if stale:
+        r = subprocess.run(["make", "-C", str(_HERE), "-j8", "mt"], capture_output=True, text=True)
+        if r.returncode != 0:
+            return None
+    return _LIB_MT_PATH
+
+
 class Camera(C.Structure):
     _fields_ = [("K", C.c_double * 9), ("R", C.c_double * 9), ("t", C.c_double * 3),
                 ("w", C.c_int32), ("h", C.c_int32)]
@@ -246,8 +262,22 @@ def gn_assemble_dense(pts, node_ids, widx, w, graph, targets, tweights, prm, x):
     return H, g
 
 
+_lib_mt = None
+
+
+def lib_mt():
+    """liboracle_mt.so or None (see build_mt)."""
+    global _lib_mt
+    if _lib_mt is None:
+        path = build_mt()
+        if path is None:
+            return None
+        _lib_mt = C.CDLL(str(path))
+    return _lib_mt
+
+
 def gn_solve(pts, normals, node_ids, widx, w, graph, prm, x0=None, targets=None, tweights=None,
-             tpts=None, tnormals=None):
+             tpts=None, tnormals=None, mt=False):
     pts = _f32(pts).reshape(-1, 3)
     normals = _f32(normals).reshape(-1, 3) if normals is not None else None
     node_ids, widx, w, graph = _i32(node_ids), _i32(widx), _f32(w), _i32(graph)
@@ -262,13 +292,18 @@ def gn_solve(pts, normals, node_ids, widx, w, graph, prm, x0=None, targets=None,
     tnormals = _f32(tnormals).reshape(-1, 3) if tnormals is not None else None
     out = np.empty((n, 3), np.float64)
     energy = np.zeros(3, np.float64)
-    lib().orc_gn_solve(_p(pts, C.c_float), _p(normals, C.c_float), C.c_int64(n),
-                       _p(node_ids, C.c_int32), C.c_int64(m), _p(widx, C.c_int32),
-                       _p(w, C.c_float), _p(graph, C.c_int32), C.c_int(graph.shape[1]),
-                       _p(targets, C.c_double), _p(tweights, C.c_float), _p(tpts, C.c_float),
-                       _p(tnormals, C.c_float), C.c_int64(len(tpts) if tpts is not None else 0),
-                       C.byref(prm), _p(x, C.c_double), _p(out, C.c_double),
-                       _p(energy, C.c_double))
+    L = lib()
+    if mt:
+        L = lib_mt()
+        if L is None:
+            raise RuntimeError("oracle: the OpenMP courtesy build is not available (no libgomp)")
+    L.orc_gn_solve(_p(pts, C.c_float), _p(normals, C.c_float), C.c_int64(n),
+                   _p(node_ids, C.c_int32), C.c_int64(m), _p(widx, C.c_int32),
+                   _p(w, C.c_float), _p(graph, C.c_int32), C.c_int(graph.shape[1]),
+                   _p(targets, C.c_double), _p(tweights, C.c_float), _p(tpts, C.c_float),
+                   _p(tnormals, C.c_float), C.c_int64(len(tpts) if tpts is not None else 0),
+                   C.byref(prm), _p(x, C.c_double), _p(out, C.c_double),
+                   _p(energy, C.c_double))
     return x, out, energy
 
 

@@ -6,6 +6,9 @@
 // Gauss-Newton solve whose formulation is fixed in SURVEY.md §8(a) D7-D9 and DESIGN.md; there are no
 // reference lines for it ("parity unpinned" against CGAL), so it is pinned by the finite-difference
 // and scipy checks in tests/test_oracle_deform.py.
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -148,14 +151,14 @@ void assemble(const Problem& P, const double* targets, const float* tw, const or
   S.lambda = prm.lambda;
   double e_fit = 0, e_rot = 0, e_reg = 0;
   // ---- fit term
-  for (int64_t i = 0; i < P.n; ++i) {
+  auto fit_vertex = [&](int64_t i, double* SB, double* Sg, double& ef) {
     double om = tw ? (double)tw[i] : 1.0;
-    if (!(om > 0)) continue;
+    if (!(om > 0)) return;
     double vt[3];
     deform_vertex(P, x, i, vt);
     double r[3] = {vt[0] - targets[3 * i], vt[1] - targets[3 * i + 1], vt[2] - targets[3 * i + 2]};
     double wf = prm.w_fit * om;
-    e_fit += wf * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    ef += wf * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
     double b[4][4];
     int js[4];
     for (int a = 0; a < 4; ++a) {
@@ -172,16 +175,42 @@ void assemble(const Problem& P, const double* targets, const float* tw, const or
     for (int a = 0; a < 4; ++a) {
       if (js[a] < 0) continue;
       for (int c = 0; c < 4; ++c)
-        for (int rr = 0; rr < 3; ++rr) S.g[12 * (size_t)js[a] + 3 * c + rr] += wf * b[a][c] * r[rr];
+        for (int rr = 0; rr < 3; ++rr) Sg[12 * (size_t)js[a] + 3 * c + rr] += wf * b[a][c] * r[rr];
       for (int bb = 0; bb < 4; ++bb) {
         if (js[bb] < 0) continue;
         int slot = S.find(js[a], js[bb]);
-        double* B = &S.B[16 * (size_t)slot];
+        double* B = &SB[16 * (size_t)slot];
         for (int c = 0; c < 4; ++c)
           for (int d = 0; d < 4; ++d) B[4 * c + d] += wf * b[a][c] * b[bb][d];
       }
     }
+  };
+#ifdef _OPENMP
+  {  // courtesy multi-thread build: per-thread partial systems, summed afterwards
+    const int T = omp_get_max_threads();
+    std::vector<std::vector<double>> Bt((size_t)T), gt((size_t)T);
+    std::vector<double> et((size_t)T, 0.0);
+#pragma omp parallel
+    {
+      const int t = omp_get_thread_num();
+      Bt[t].assign(S.B.size(), 0.0);
+      gt[t].assign(S.g.size(), 0.0);
+#pragma omp for schedule(static)
+      for (int64_t i = 0; i < P.n; ++i) fit_vertex(i, Bt[t].data(), gt[t].data(), et[t]);
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)S.B.size(); ++k) {
+      double acc = 0;
+      for (int t = 0; t < T; ++t) acc += Bt[t][k];
+      S.B[k] += acc;
+    }
+    for (size_t k = 0; k < S.g.size(); ++k)
+      for (int t = 0; t < T; ++t) S.g[k] += gt[t][k];
+    for (int t = 0; t < T; ++t) e_fit += et[t];
   }
+#else
+  for (int64_t i = 0; i < P.n; ++i) fit_vertex(i, S.B.data(), S.g.data(), e_fit);
+#endif
   // ---- rotation term (6 residuals on the columns of A_j)
   for (int64_t j = 0; j < P.m; ++j) {
     const double* X = x + 12 * (size_t)j;
@@ -255,6 +284,7 @@ void assemble(const Problem& P, const double* targets, const float* tw, const or
 
 // y = H v
 void spmv(const System& S, const double* v, double* y) {
+#pragma omp parallel for schedule(static)
   for (int64_t j = 0; j < S.m; ++j) {
     double acc[12];
     for (int k = 0; k < 12; ++k) acc[k] = S.lambda * v[12 * j + k];
@@ -292,6 +322,7 @@ void diag_block(const System& S, int64_t j, double D[144]) {
 void pcg(const System& S, int iters, double tol, std::vector<double>& delta) {
   size_t N = (size_t)S.m * 12;
   std::vector<double> Minv((size_t)S.m * 144);
+#pragma omp parallel for schedule(static)
   for (int64_t j = 0; j < S.m; ++j) {
     double D[144];
     diag_block(S, j, D);
@@ -302,6 +333,7 @@ void pcg(const System& S, int iters, double tol, std::vector<double>& delta) {
     }
   }
   auto precond = [&](const std::vector<double>& r, std::vector<double>& z) {
+#pragma omp parallel for schedule(static)
     for (int64_t j = 0; j < S.m; ++j)
       for (int a = 0; a < 12; ++a) {
         double s = 0;
@@ -592,6 +624,7 @@ void orc_gn_solve(const float* pts, const float* normals, int64_t n, const int32
   std::vector<int32_t> nn;
   std::vector<float> nd2;
   std::vector<double> delta;
+  void* tree = (prm->corr_mode == 1) ? orc_kdtree_build(tpts, nt) : nullptr;  // once per solve
   for (int it = 0; it < prm->gn_iters; ++it) {
     const double* T = targets;
     const float* W = tweights;
@@ -602,12 +635,14 @@ void orc_gn_solve(const float* pts, const float* normals, int64_t n, const int32
       qf.resize((size_t)n * 3);
       nn.resize((size_t)n);
       nd2.resize((size_t)n);
+#pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < n; ++i) {
         double v[3];
         deform_vertex(P, x, i, v);
         for (int a = 0; a < 3; ++a) qf[3 * i + a] = (float)v[a];
       }
-      orc_knn_kdtree(qf.data(), n, tpts, nt, 1, nn.data(), nd2.data());
+      orc_kdtree_query(tree, qf.data(), n, 1, nn.data(), nd2.data());
+#pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < n; ++i) {
         int32_t c = nn[i];
         float om = 1.0f;
@@ -628,6 +663,7 @@ void orc_gn_solve(const float* pts, const float* normals, int64_t n, const int32
     pcg(S, prm->pcg_iters, prm->pcg_tol, delta);
     for (size_t i = 0; i < (size_t)m * 12; ++i) x[i] += delta[i];
   }
+  if (tree) orc_kdtree_free(tree);
   if (out_pts)
     for (int64_t i = 0; i < n; ++i) deform_vertex(P, x, i, out_pts + 3 * i);
 }

@@ -151,25 +151,48 @@ void orc_knn_brute(const float* q, int64_t nq, const float* t, int64_t nt, int k
   }
 }
 
-void orc_knn_kdtree(const float* q, int64_t nq, const float* t, int64_t nt, int k,
-                    int32_t* out_idx, float* out_d2) {
-  KdTree tree;
-  tree.pts = t;
-  tree.order.resize((size_t)nt);
-  for (int64_t i = 0; i < nt; ++i) tree.order[i] = (int32_t)i;
-  tree.nodes.reserve((size_t)(nt / 4 + 16));
-  if (nt > 0) tree.build(0, (int32_t)nt);
-  std::vector<float> tmpd((size_t)k);
-  std::vector<int32_t> tmpi((size_t)k);
-  for (int64_t i = 0; i < nq; ++i) {
-    Best b;
-    b.init(k, tmpd.data(), tmpi.data());
-    if (nt > 0) tree.search(0, q + 3 * i, b);
-    for (int j = 0; j < k; ++j) {
-      if (out_idx) out_idx[i * k + j] = tmpi[j];
-      if (out_d2) out_d2[i * k + j] = tmpd[j];
+// A tree that outlives one query batch: the Gauss-Newton loop searches the same target set every
+// iteration (the reference builds its FLANN index once per Deform call, Deformation.cpp:245-252).
+void* orc_kdtree_build(const float* t, int64_t nt) {
+  KdTree* tree = new KdTree;
+  tree->pts = t;
+  tree->order.resize((size_t)nt);
+  for (int64_t i = 0; i < nt; ++i) tree->order[i] = (int32_t)i;
+  tree->nodes.reserve((size_t)(nt / 4 + 16));
+  if (nt > 0) tree->build(0, (int32_t)nt);
+  return tree;
+}
+
+void orc_kdtree_free(void* handle) { delete static_cast<KdTree*>(handle); }
+
+void orc_kdtree_query(const void* handle, const float* q, int64_t nq, int k, int32_t* out_idx,
+                      float* out_d2) {
+  const KdTree& tree = *static_cast<const KdTree*>(handle);
+  const bool any = !tree.order.empty();
+  // queries are independent; the OpenMP courtesy build (liboracle_mt.so) spreads them over threads,
+  // the default single-thread build ignores the pragmas
+#pragma omp parallel
+  {
+    std::vector<float> tmpd((size_t)k);
+    std::vector<int32_t> tmpi((size_t)k);
+#pragma omp for schedule(dynamic, 2048)
+    for (int64_t i = 0; i < nq; ++i) {
+      Best b;
+      b.init(k, tmpd.data(), tmpi.data());
+      if (any) tree.search(0, q + 3 * i, b);
+      for (int j = 0; j < k; ++j) {
+        if (out_idx) out_idx[i * k + j] = tmpi[j];
+        if (out_d2) out_d2[i * k + j] = tmpd[j];
+      }
     }
   }
+}
+
+void orc_knn_kdtree(const float* q, int64_t nq, const float* t, int64_t nt, int k,
+                    int32_t* out_idx, float* out_d2) {
+  void* tree = orc_kdtree_build(t, nt);
+  orc_kdtree_query(tree, q, nq, k, out_idx, out_d2);
+  orc_kdtree_free(tree);
 }
 
 // PartRecognition/PartRecognition.cpp:50-77: template -> float32 (:54-60), query cast to float

@@ -248,3 +248,20 @@ def test_pipelined_pcg_recurrences_track_standard_pcg():
     assert e_p64 < 1e-10                       # same iterates in exact arithmetic
     assert e_p32 > 5 * e_std32                 # float32 recurrences drift
     assert e_mixed < 5e-6 and e_mixed < 5 * max(e_std32, 1e-7)   # float64 recurrences + halo do not
+
+
+def test_openmp_courtesy_build_matches_single_thread():
+    """bench.py reports a courtesy multi-thread CPU number from the same oracle sources compiled with
+    -fopenmp; its results must agree with the single-thread oracle (summation order only)."""
+    if oracle.lib_mt() is None:
+        pytest.skip("no libgomp in this toolchain")
+    verts, faces = synth.cube_sphere(20)
+    pts = verts.astype(np.float32)
+    ids = oracle.sample_fps(pts, 60, 0)
+    widx, w = oracle.node_weights(pts, pts[ids], 4)
+    graph = oracle.node_graph(pts[ids], 8)
+    tv = synth.bend_twist(synth.cube_sphere(22, rot=synth.axis_angle([1, 2, 3], 0.7))[0], 0.04).astype(np.float32)
+    prm = oracle.gn_params(gn_iters=3, pcg_iters=15, corr_mode=1)
+    x1, o1, e1 = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, tpts=tv)
+    x2, o2, e2 = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, tpts=tv, mt=True)
+    assert np.abs(o1 - o2).max() < 1e-10 and np.abs(x1 - x2).max() < 1e-10
