@@ -213,6 +213,11 @@ def run_reference(args):
                                      "built here, so this is the oracle port"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_cores": os.cpu_count()}
+    try:  # courtesy number on every host core; `value` stays the single-thread reference arm
+        line["cpu_baseline"]["openmp_courtesy"] = cpu_solve_openmp(
+            args, pts, tgt, args.ref_gn_iters, (ids, widx, w, graph))
+    except Exception as exc:
+        line["cpu_baseline"]["openmp_courtesy"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
 
 
