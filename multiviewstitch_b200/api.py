@@ -288,6 +288,19 @@ class SRTSolver:
             return s.value, R.reshape(3, 3), t, be.value, bi.value
         return s.value, R.reshape(3, 3), t
 
+    def EstimateTransformArray(self, triples=None, seed: int = 0):
+        """[ref: Solver/SRTSolver.cpp:256-270 EstimateTransform(double&, double[3][3], double[3])]
+        the deprecated array overload: RANSAC path, outputs copied into plain arrays."""
+        s = C.c_double()
+        R = ((C.c_double * 3) * 3)()
+        t = (C.c_double * 3)()
+        tr = _i32(triples).reshape(-1, 3) if triples is not None else None
+        if tr is not None:
+            self.SetIterationNum(len(tr))
+        check(lib().mvs_srt_estimate_array(self._h, _ptr(tr, C.c_int32), C.c_uint64(seed),
+                                           C.byref(s), R, t))
+        return s.value, np.array([[R[i][j] for j in range(3)] for i in range(3)]), np.array(t[:])
+
     def Inliers(self, scale, R, t, pixel_thr):
         """[ref: Processor/Processor.cpp:210-239] -> (flags uint8, err_all sum, n_inliers)"""
         R, t = _f64(R).reshape(9), _f64(t).reshape(3)

@@ -1,0 +1,166 @@
+"""oracle.ref — TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of oracle/_ref/libmvsref.so: the reference's own first-party sources
+(Solver/SRTSolver.cpp, Camera/Camera.cpp, SetUtils/PointSetUtils.cpp, SetUtils/UnionSetUtils.cpp,
+Depth2Model/Depth2Model.cpp, Common/Utils.h) compiled UNMODIFIED from /root/reference by
+`make -C oracle ref` against the stand-in headers in oracle/compat/ (see oracle/ref_shim.cpp).
+Used to pin the restatement in oracle/*.cpp (tests/test_ref_parity.py), to generate the committed
+vectors tests/golden/ref_*.npz (tests/golden/make_ref_golden.py) and as the `kind: "reference"` CPU
+leg of bench.py's SRT line.  The product never loads it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from . import Camera, _f32, _f64, _i32, _p
+
+_HERE = Path(__file__).resolve().parent
+REF_ROOT = Path("/root/reference/MultiViewStitch")
+_LIB_PATH = _HERE / "_ref" / "libmvsref.so"
+_lib = None
+
+
+def build() -> Path | None:
+    """Compile the reference sources where they lie (only possible where /root/reference exists —
+    this container; the GPU box uses the prebuilt oracle/_ref/libmvsref.so that travels with the
+    snapshot)."""
+    if not REF_ROOT.exists():
+        return _LIB_PATH if _LIB_PATH.exists() else None
+    r = subprocess.run(["make", "-C", str(_HERE), "-j8", "ref"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref build failed:\n" + r.stdout + r.stderr)
+    return _LIB_PATH
+
+
+def available() -> bool:
+    return _LIB_PATH.exists() or REF_ROOT.exists()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if build() is None:
+            raise RuntimeError("oracle/_ref/libmvsref.so is not built and /root/reference is absent")
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.ref_srt_residual.restype = C.c_double
+        _lib.ref_connected_keep.restype = C.c_int
+    return _lib
+
+
+def _cam(c):
+    return C.byref(c) if c is not None else None
+
+
+def srt_estimate(p, q, cam1: Camera | None = None, cam2: Camera | None = None):
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    s = C.c_double()
+    R, t = np.empty(9), np.empty(3)
+    lib().ref_srt_estimate(_p(p, C.c_double), _p(q, C.c_double), C.c_int64(len(p)), _cam(cam1),
+                           _cam(cam2), C.byref(s), _p(R, C.c_double), _p(t, C.c_double))
+    return s.value, R.reshape(3, 3), t
+
+
+def srt_residual(p, q, cam1: Camera, cam2: Camera, scale, R, t):
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    R, t = _f64(R).reshape(9), _f64(t).reshape(3)
+    return lib().ref_srt_residual(_p(p, C.c_double), _p(q, C.c_double), C.c_int64(len(p)),
+                                  _cam(cam1), _cam(cam2), C.c_double(scale), _p(R, C.c_double),
+                                  _p(t, C.c_double))
+
+
+def srt_triples(n: int, iter_num: int, seed: int):
+    tr = np.empty((iter_num, 3), np.int32)
+    lib().ref_srt_triples(C.c_int64(n), C.c_int(iter_num), C.c_uint(seed), _p(tr, C.c_int32))
+    return tr
+
+
+def srt_ransac(p, q, cam1: Camera, cam2: Camera, iter_num: int, seed: int, array: bool = False):
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    s = C.c_double()
+    R, t = np.empty(9), np.empty(3)
+    lib().ref_srt_ransac(_p(p, C.c_double), _p(q, C.c_double), C.c_int64(len(p)), _cam(cam1),
+                         _cam(cam2), C.c_int(iter_num), C.c_uint(seed), C.c_int(int(array)),
+                         C.byref(s), _p(R, C.c_double), _p(t, C.c_double))
+    return s.value, R.reshape(3, 3), t
+
+
+def project(cam: Camera, pts):
+    pts = _f64(pts).reshape(-1, 3)
+    uv = np.empty((len(pts), 2), np.int32)
+    lib().ref_project(_cam(cam), _p(pts, C.c_double), C.c_int64(len(pts)), _p(uv, C.c_int32))
+    return uv
+
+
+def unproject(cam: Camera, uv, depth):
+    uv = _i32(uv).reshape(-1, 2)
+    depth = _f64(depth).reshape(-1)
+    out = np.empty((len(uv), 3))
+    lib().ref_unproject(_cam(cam), _p(uv, C.c_int32), _p(depth, C.c_double), C.c_int64(len(uv)),
+                        _p(out, C.c_double))
+    return out
+
+
+def gl_matrices(cam: Camera, znear: float, zfar: float):
+    mv, fr, pr = np.empty(16, np.float32), np.empty(4, np.float32), np.empty(16, np.float32)
+    lib().ref_gl_matrices(_cam(cam), C.c_float(znear), C.c_float(zfar), _p(mv, C.c_float),
+                          _p(fr, C.c_float), _p(pr, C.c_float))
+    return mv.reshape(4, 4), fr, pr.reshape(4, 4)
+
+
+def pointset(pts):
+    pts = _f64(pts).reshape(-1, 3)
+    b, c, P = np.empty(3), np.empty(3), np.empty(9)
+    lib().ref_pointset(_p(pts, C.c_double), C.c_int64(len(pts)), _p(b, C.c_double),
+                       _p(c, C.c_double), _p(P, C.c_double))
+    return b, c, P.reshape(3, 3)
+
+
+def connected_keep(n: int, facets):
+    facets = _i32(facets).reshape(-1)
+    keep = np.empty(n, np.uint8)
+    ncomp = lib().ref_connected_keep(C.c_int64(n), _p(facets, C.c_int32), C.c_int64(len(facets) // 3),
+                                     _p(keep, C.c_uint8))
+    return keep.astype(bool), int(ncomp)
+
+
+def depth2model(inv_depth, cam: Camera, min_dsp, max_dsp, smooth):
+    d = _f32(inv_depth).reshape(-1)
+    n = cam.w * cam.h
+    xyz = np.empty((n, 3))
+    tex = np.empty(n, np.int32)
+    fac = np.empty((2 * (cam.w - 1) * (cam.h - 1), 3), np.int32)
+    npts, nf = C.c_int64(), C.c_int64()
+    lib().ref_depth2model(_p(d, C.c_float), _cam(cam), C.c_double(min_dsp), C.c_double(max_dsp),
+                          C.c_double(smooth), _p(xyz, C.c_double), _p(tex, C.c_int32),
+                          _p(fac, C.c_int32), C.byref(npts), C.byref(nf))
+    return xyz[:npts.value].copy(), tex[:npts.value].copy(), fac[:nf.value].copy()
+
+
+def calc_rotation(a, b):
+    a, b = _f64(a).reshape(3), _f64(b).reshape(3)
+    R = np.empty(9)
+    lib().ref_calc_rotation(_p(a, C.c_double), _p(b, C.c_double), _p(R, C.c_double))
+    return R.reshape(3, 3)
+
+
+def axis_angle(axis, angle_deg, pb):
+    axis, pb = _f64(axis).reshape(3), _f64(pb).reshape(3)
+    out = np.empty(3)
+    lib().ref_axis_angle(_p(axis, C.c_double), C.c_double(angle_deg), _p(pb, C.c_double),
+                         _p(out, C.c_double))
+    return out
+
+
+def save_depth(filename: str, depth):
+    d = _f64(depth).reshape(-1)
+    lib().ref_save_depth(str(filename).encode(), _p(d, C.c_double), C.c_int64(len(d)))
+
+
+def load_depth(filename: str, w: int, h: int):
+    d = np.empty(w * h)
+    lib().ref_load_depth(str(filename).encode(), _p(d, C.c_double), C.c_int(w), C.c_int(h))
+    return d

@@ -1,0 +1,138 @@
+"""Seeded inputs of the reference-parity cases, shared by tests/golden/make_ref_golden.py (which runs
+them through oracle/_ref — the reference's own code compiled unmodified) and by
+tests/test_ref_parity.py / tests/test_gpu_ref_parity.py (which run the oracle restatement and the
+CUDA path on the same inputs).  `run(mod)` evaluates every case with either back end: `mod` is
+`oracle.ref` (the reference) or an adapter with the same function names."""
+from __future__ import annotations
+
+import numpy as np
+
+from multiviewstitch_b200 import synth
+
+MIN_DSP, MAX_DSP, SMOOTH = 0.0025, 0.3, 0.12  # config.txt:23-24,38
+
+
+def cams(make_camera, w=640, h=480):
+    (K, R1, t1, _, _), (_, R2, t2, _, _) = synth.camera_pair()
+    return make_camera(K, R1, t1, w, h), make_camera(K, R2, t2, w, h)
+
+
+def srt_inputs():
+    """name -> (p, q): planted similarity with noise / with outliers / an exact reflection (forces
+    the det(R) = -1 branch, SRTSolver.cpp:115-119) / the three-pair minimum."""
+    rng = np.random.default_rng(4242)
+    out = {}
+    p, q = synth.planted_pairs(2000, seed=5, noise=1e-3)
+    out["noisy"] = (p, q)
+    p2, q2 = synth.planted_pairs(500, seed=6, noise=2e-3)
+    bad = rng.random(500) < 0.1
+    q2 = q2.copy()
+    q2[bad] += rng.normal(scale=0.3, size=(int(bad.sum()), 3))
+    out["outliers"] = (p2, q2)
+    p3 = synth.sphere_points(300, 7, center=(0, 0, 5.0))
+    M = synth.PLANTED_R @ np.diag([1.0, 1.0, -1.0])      # improper: a mirrored copy
+    q3 = synth.PLANTED_S * p3 @ M.T + synth.PLANTED_T
+    out["mirror"] = (p3, q3)
+    p4, q4 = synth.planted_pairs(3, seed=8, noise=1e-3)
+    out["three"] = (p4, q4)
+    return out
+
+
+def project_points():
+    """world points around both cameras, including ones that land at negative pixel coordinates
+    (the (int)(x + 0.5) truncation toward zero, Camera.cpp:46-47) and behind the camera"""
+    rng = np.random.default_rng(99)
+    a = rng.normal(size=(4000, 3)) * np.array([3.0, 3.0, 2.0]) + np.array([0, 0, 5.0])
+    b = rng.normal(size=(500, 3)) * 6.0
+    return np.concatenate([a, b], 0)
+
+
+def unproject_inputs(w=640, h=480):
+    """distinct pixels with an inverse depth ("dsp", float32 as in the .raw files) inside the valid
+    window; depth = 1 / dsp as Image3D.cpp:98-103 / Depth2Model.cpp:37 hand it to the camera"""
+    rng = np.random.default_rng(100)
+    pix = rng.choice(w * h, 3000, replace=False)
+    uv = np.stack([pix % w, pix // w], 1).astype(np.int32)
+    dsp = rng.uniform(MIN_DSP * 1.01, MAX_DSP * 0.99, 3000).astype(np.float32)
+    return uv, dsp, 1.0 / dsp.astype(np.float64)
+
+
+def pointsets():
+    rng = np.random.default_rng(17)
+    body, _ = synth.humanoid(300, seed=3)
+    ell = rng.normal(size=(5000, 3)) * np.array([3.0, 1.0, 0.3]) @ synth.axis_angle([1, 1, 0], 0.7).T + 2.0
+    return {"humanoid": body, "ellipsoid": ell}
+
+
+def facet_sets():
+    """name -> (n, facets): two components of different size; two of EQUAL size (ProminentRepresent
+    keeps the first root with the largest rank, UnionSetUtils.cpp:33-43); isolated vertices"""
+    v1, f1 = synth.uv_sphere(12, 8)
+    v2, f2 = synth.uv_sphere(8, 6)
+    big_small = (len(v1) + len(v2), np.concatenate([f1, f2 + len(v1)], 0))
+    small_big = (len(v1) + len(v2), np.concatenate([f2, f1 + len(v2)], 0))
+    equal = (2 * len(v2) + 5, np.concatenate([f2 + 5, f2 + 5 + len(v2)], 0))
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(v1) + len(v2))
+    shuffled = (len(v1) + len(v2), perm[big_small[1]])
+    return {"big_small": big_small, "small_big": small_big, "equal": equal, "shuffled": shuffled}
+
+
+def depth_map(w, h, seed=0):
+    """Synthetic inverse-depth image (float32, the `.raw` format): a bumpy sphere in front of a flat
+    wall, with a disparity discontinuity at the silhouette (exercises the three-edge smoothness test,
+    Depth2Model.cpp:52-75), out-of-range and zero pixels."""
+    rng = np.random.default_rng(seed)
+    fx = 525.0 * w / 640.0
+    u, v = np.meshgrid(np.arange(w), np.arange(h))
+    x, y = (u - (w - 1) / 2) / fx, (v - (h - 1) / 2) / fx
+    # ray/sphere: centre (0,0,5), radius 1 (+ bumps)
+    rad = 1.0 + 0.05 * np.sin(9 * x) * np.cos(7 * y)
+    a = x * x + y * y + 1.0
+    disc = 25.0 - a * (25.0 - rad * rad)
+    z = np.full((h, w), 9.0 + 0.5 * x)                    # wall
+    hit = disc > 0
+    z[hit] = ((5.0 - np.sqrt(disc[hit])) / a[hit])
+    d = (1.0 / z).astype(np.float32)
+    d[rng.random((h, w)) < 0.02] = 0.0                   # holes
+    d[:3, :] = 0.5                                        # > MaxDsp
+    d[-2:, :] = 0.001                                     # < MinDsp
+    return d
+
+
+def run(mod, make_camera, d2m_size=(160, 120)):
+    """Every case through `mod`; returns {key: ndarray}."""
+    out = {}
+    c1, c2 = cams(make_camera)
+    for name, (p, q) in srt_inputs().items():
+        s, R, t = mod.srt_estimate(p, q, c1, c2)
+        out[f"srt_{name}_s"], out[f"srt_{name}_R"], out[f"srt_{name}_t"] = np.float64(s), R, t
+        out[f"srt_{name}_res"] = np.float64(mod.srt_residual(p, q, c1, c2, s, R, t))
+        out[f"srt_{name}_res_planted"] = np.float64(
+            mod.srt_residual(p, q, c1, c2, synth.PLANTED_S, synth.PLANTED_R, synth.PLANTED_T))
+    for name, seed, iters in (("noisy", 1, 40), ("outliers", 2, 200)):
+        p, q = srt_inputs()[name]
+        tr = mod.srt_triples(len(p), iters, seed)
+        s, R, t = mod.srt_ransac(p, q, c1, c2, iters, seed, False, tr)
+        out[f"ransac_{name}_triples"] = tr
+        out[f"ransac_{name}_s"], out[f"ransac_{name}_R"], out[f"ransac_{name}_t"] = np.float64(s), R, t
+        s2, R2, t2 = mod.srt_ransac(p, q, c1, c2, iters, seed, True, tr)
+        out[f"ransac_{name}_array_R"], out[f"ransac_{name}_array_t"] = R2, t2
+    pts = project_points()
+    out["project_uv1"] = mod.project(c1, pts)
+    out["project_uv2"] = mod.project(c2, pts)
+    uv, _, depth = unproject_inputs()
+    out["unproject_1"] = mod.unproject(c1, uv, depth)
+    out["unproject_2"] = mod.unproject(c2, uv, depth)
+    for name, ps in pointsets().items():
+        b, c, P = mod.pointset(ps)
+        out[f"ps_{name}_bary"], out[f"ps_{name}_bbc"], out[f"ps_{name}_pivots"] = b, c, P
+    for name, (n, f) in facet_sets().items():
+        keep, ncomp = mod.connected_keep(n, f)
+        out[f"cc_{name}_keep"] = np.asarray(keep, bool)
+        out[f"cc_{name}_ncomp"] = np.int64(ncomp)
+    w, h = d2m_size
+    cd = cams(make_camera, w, h)[1]
+    xyz, tex, fac = mod.depth2model(depth_map(w, h), cd, MIN_DSP, MAX_DSP, SMOOTH)
+    out["d2m_xyz"], out["d2m_tex"], out["d2m_facets"] = xyz, tex, fac
+    return out
