@@ -636,6 +636,23 @@ def run_b200(args):
             dg = float(np.linalg.norm(pts.max(0) - pts.min(0)))
             e2e_diff = float(np.abs(out_h - out_dev).max() / dg)
 
+    # ---- vertex-sharded mode: the all-reduced solve must carry the bits of the unsharded one
+    shard_equal = None
+    if shard:
+        if rank == 0:
+            with torch.cuda.stream(stream):
+                ctx1 = api.Context(local, stream.cuda_stream)  # no communicator: plain one-rank solve
+                d1 = api.Deformation(pts, nrm, faces, ctx1)
+                d1.SampleFPS(args.nodes, 0)
+                d1.BuildGraph(4, 8)
+                d1.SetTargetDev(tgt4.data_ptr(), None, nt)
+                d1.Solve(prm)
+                shard_equal = bool(np.array_equal(d1.Vertices(), out_dev)
+                                   and np.array_equal(d1.NodeState(), d.NodeState()))
+                d1.close()
+        if world > 1:
+            dist.barrier()
+
     # ---- max over ranks
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
@@ -724,6 +741,7 @@ def run_b200(args):
                     "max_abs_diff_vs_resident_over_bbox_diag": e2e_diff},
                 "gpu_launches": int(launches), "clocks": clk,
                 "wall_s_timed_region": t_wall, "secondary": secondary, "families": families,
+                "shard_bitwise_equal": shard_equal,
                 "e2e_families_ms_per_step": None if e2e_ms is None else {
                     k: round(v[0] / args.steps, 4) for k, v in
                     sorted(prof_e2e.items(), key=lambda kv: -kv[1][0])}}

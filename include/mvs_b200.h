@@ -275,6 +275,11 @@ int mvs_deform_run(mvs_deform* h, double proj_len_err, double proj_dist_err,
                    const mvs_gn_params* params);
 /* [ref: Deformation/Deformation.h:237-240 Deform(tpts,tnormals,threshold)] */
 int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_params* params);
+/* The correspondence stage of that variant alone [ref: Deformation/Deformation.cpp:186-203]: per
+ * node the 1-NN target point, valid iff d2 <= threshold and cos(dir, node normal) >= 0.5; invalid
+ * nodes keep their own position.  controls_xyz m x 3, valid m (either may be NULL). */
+int mvs_deform_node_targets_threshold(mvs_deform* h, double threshold, double* controls_xyz,
+                                      int32_t* valid);
 /* As-rigid-as-possible mode of Deform(): the solver the reference actually runs, CGAL 4.6
  * Surface_mesh_deformation [ref: Deformation/Deformation.cpp:256-260 insert_roi_vertices(all),
  * :383-392 every sampled node a control vertex, :393 preprocess(), :398 deform(5, 1e-4), :400
@@ -301,6 +306,16 @@ int mvs_deform_run_arap(mvs_deform* h, double proj_len_err, double proj_dist_err
 int mvs_deform_gn_begin(mvs_deform* h, const mvs_gn_params* params);
 int mvs_deform_gn_step(mvs_deform* h);
 int mvs_deform_gn_end(mvs_deform* h);
+/* The whole fixed-iteration solve in ONE call: gn_begin + params->gn_iters x gn_step + gn_end, every
+ * launch enqueued from C++ with no host synchronisation in between (the loop Deformation::Deform
+ * runs inside `deformMesh.deform(...)`, Deformation/Deformation.cpp:398); one stream synchronise
+ * at the end.  Result readable with mvs_deform_get_vertices*. */
+int mvs_deform_solve(mvs_deform* h, const mvs_gn_params* params);
+/* Correspondences of the LAST Gauss-Newton step (corr_mode 1): out_idx[i] = index of the target
+ * point that vertex i (original vertex order) was matched to — the exact nearest neighbour, lowest
+ * index on ties, of the vertex deformed by the node state the step started from. -1 before the first
+ * step or outside this rank's vertex shard. */
+int mvs_deform_get_correspondences(mvs_deform* h, int32_t* out_idx /* n */);
 /* energy terms after the last step: fit, rot, reg (weighted sums of squares) */
 int mvs_deform_get_energy(mvs_deform* h, double energy[3]);
 int mvs_deform_get_node_state(mvs_deform* h, float* A_t /* m x 12: a1,a2,a3 (columns), t */);
@@ -370,9 +385,17 @@ int mvs_unproject_pixels(mvs_ctx* ctx, const float* inv_depth, const mvs_camera*
 int mvs_comm_unique_id(char id[128]);
 int mvs_comm_init(mvs_ctx* ctx, int nranks, int rank, const char id[128]);
 int mvs_comm_destroy(mvs_ctx* ctx);
-/* Vertex-sharded GN: this rank owns vertices [v_begin, v_end) of the mesh for the fit term; node
- * state is replicated; J^T J / J^T r partial blocks and PCG scalars are all-reduced over NCCL. */
+/* Vertex-sharded GN: this rank owns vertices [v_begin, v_end) of the mesh (positions in the solver's
+ * sorted vertex order) for the fit term; node state is replicated; the partial J^T J / J^T r blocks
+ * are all-reduced over NCCL as 64-bit fixed-point integers.  Each boundary is moved down to the start
+ * of the assembly group (4 runs of equal node tuples) that contains it, so ranks that split [0, n) at
+ * common points tile it exactly and the all-reduced system is BITWISE the unsharded one. */
 int mvs_deform_set_shard(mvs_deform* h, int64_t v_begin, int64_t v_end);
+/* Work through this rank's vertex range as `parts` consecutive sub-ranges, one launch each: the
+ * partial sums `parts` ranks would produce, added by the same commutative integer additions the
+ * all-reduce performs — the sharded arithmetic checked on ONE GPU (result bitwise equal to
+ * parts = 1).  Default 1. */
+int mvs_deform_set_shard_parts(mvs_deform* h, int parts);
 /* Static partition of `n_units` independent units (view pairs) over ranks: unit u -> u % nranks.
  * [ref: Processor/Processor.cpp:629-826 independent `for k` pair loop] */
 int mvs_partition_units(int64_t n_units, int nranks, int rank, int64_t* begin_stride_count /*3*/);

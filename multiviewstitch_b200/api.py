@@ -485,6 +485,15 @@ class Deformation:
                                             _ptr(v, C.c_int32)))
         return c, v
 
+    def NodeTargetsThreshold(self, threshold: float):
+        """Correspondence stage of Deform(tpts, tnormals, threshold) [ref: Deformation.cpp:186-203]."""
+        m = len(self.Nodes())
+        c = np.empty((m, 3), np.float64)
+        v = np.empty(m, np.int32)
+        check(lib().mvs_deform_node_targets_threshold(self._h, C.c_double(threshold),
+                                                      _ptr(c, C.c_double), _ptr(v, C.c_int32)))
+        return c, v
+
     # ---- Deform
     def Deform(self, tpts, tnormals, *args, params: GNParams | None = None):
         """Deform(tpts, tnormals, threshold) [ref: Deformation.cpp:155-230] or
@@ -530,6 +539,16 @@ class Deformation:
     def GNEnd(self):
         check(lib().mvs_deform_gn_end(self._h))
 
+    def Solve(self, params: GNParams):
+        """gn_begin + gn_iters x gn_step + gn_end in one library call (no host round trips)."""
+        check(lib().mvs_deform_solve(self._h, C.byref(params)))
+
+    def Correspondences(self):
+        """Target index matched to every vertex (original order) by the last GN step."""
+        out = np.empty(self.n, np.int32)
+        check(lib().mvs_deform_get_correspondences(self._h, _ptr(out, C.c_int32)))
+        return out
+
     def Energy(self):
         e = np.zeros(3, np.float64)
         check(lib().mvs_deform_get_energy(self._h, _ptr(e, C.c_double)))
@@ -563,6 +582,9 @@ class Deformation:
         check(lib().mvs_deform_get_stats(self._h, out))
         return dict(zip(("vertices", "nodes", "pattern_blocks", "tuple_runs", "facets",
                          "target_points"), [int(v) for v in out]))
+
+    def SetShardParts(self, parts: int):
+        check(lib().mvs_deform_set_shard_parts(self._h, C.c_int(parts)))
 
     def SetShard(self, v_begin: int, v_end: int):
         check(lib().mvs_deform_set_shard(self._h, C.c_int64(v_begin), C.c_int64(v_end)))

@@ -65,7 +65,11 @@ static int load_nccl() {
   } while (0)
 
 int comm_allreduce_sum_f32(mvs_ctx* ctx, float* buf_dev, size_t count) {
-  if (!ctx->comm || ctx->nranks <= 1 || count == 0) return MVS_OK;
+  if (ctx->nranks <= 1 || count == 0) return MVS_OK;
+  if (!ctx->comm) {
+    set_error("all-reduce on %d ranks without a communicator (mvs_comm_init failed?)", ctx->nranks);
+    return MVS_ERR_COMM;
+  }
   ctx->launch_count += 1;
   MVS_NCCL(g_nccl.AllReduce(buf_dev, buf_dev, count, ncclFloat32, ncclSum, (ncclComm_t)ctx->comm,
                             ctx->stream));
@@ -73,7 +77,11 @@ int comm_allreduce_sum_f32(mvs_ctx* ctx, float* buf_dev, size_t count) {
 }
 
 int comm_allreduce_sum_f64(mvs_ctx* ctx, double* buf_dev, size_t count) {
-  if (!ctx->comm || ctx->nranks <= 1 || count == 0) return MVS_OK;
+  if (ctx->nranks <= 1 || count == 0) return MVS_OK;
+  if (!ctx->comm) {
+    set_error("all-reduce on %d ranks without a communicator (mvs_comm_init failed?)", ctx->nranks);
+    return MVS_ERR_COMM;
+  }
   ctx->launch_count += 1;
   MVS_NCCL(g_nccl.AllReduce(buf_dev, buf_dev, count, ncclFloat64, ncclSum, (ncclComm_t)ctx->comm,
                             ctx->stream));
@@ -81,7 +89,11 @@ int comm_allreduce_sum_f64(mvs_ctx* ctx, double* buf_dev, size_t count) {
 }
 
 int comm_allreduce_sum_i64(mvs_ctx* ctx, long long* buf_dev, size_t count) {
-  if (!ctx->comm || ctx->nranks <= 1 || count == 0) return MVS_OK;
+  if (ctx->nranks <= 1 || count == 0) return MVS_OK;
+  if (!ctx->comm) {
+    set_error("all-reduce on %d ranks without a communicator (mvs_comm_init failed?)", ctx->nranks);
+    return MVS_ERR_COMM;
+  }
   ctx->launch_count += 1;
   MVS_NCCL(g_nccl.AllReduce(buf_dev, buf_dev, count, ncclInt64, ncclSum, (ncclComm_t)ctx->comm,
                             ctx->stream));
@@ -108,15 +120,16 @@ int mvs_comm_init(mvs_ctx* ctx, int nranks, int rank, const char id[128]) {
   MVS_REQUIRE(ctx && id && nranks >= 1 && rank >= 0 && rank < nranks, "bad argument");
   MVS_TRY(ctx_ensure_device(ctx));
   MVS_TRY(mvs_comm_destroy(ctx));
-  ctx->nranks = nranks;
-  ctx->rank = rank;
-  if (nranks == 1) return MVS_OK;
+  if (nranks == 1) return MVS_OK;  // mvs_comm_destroy left nranks = 1, rank = 0
   MVS_TRY(load_nccl());
   ncclUniqueId u;
   memcpy(&u, id, 128);
   ncclComm_t comm = nullptr;
   MVS_NCCL(g_nccl.CommInitRank(&comm, nranks, u, rank));
+  // the context becomes a member of the job only once the communicator exists
   ctx->comm = (void*)comm;
+  ctx->nranks = nranks;
+  ctx->rank = rank;
   return MVS_OK;
 }
 

@@ -16,6 +16,7 @@
 //       sys = [ B: nnz x 16 | rhs: m x 12 | Rot: m x 81 ]
 //   block-CSR pattern row_ptr[m+1], col[nnz] (ascending, diagonal included)
 #pragma once
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -52,6 +53,7 @@ struct mvs_deform {
   mvs::DevBuf<int> row_ptr, col;
   int64_t nnz = 0;
   std::vector<int> h_row_ptr;  // host copy of row_ptr (solver launch planning)
+  std::vector<int> h_grp_start;  // first sorted vertex of every assembly group, then n
   bool pcg_plan_valid = false;
   int pcg_rs = 1, pcg_grid = 0, pcg_stage = 0;
   size_t pcg_smem = 0;
@@ -107,6 +109,10 @@ struct mvs_deform {
   mvs_gn_params prm{};
   bool gn_active = false;
   int64_t v_begin = 0, v_end = -1;  // shard of sorted positions owned by this rank
+  // the rank's range is worked through as `shard_parts` consecutive sub-ranges, one launch each — the
+  // partial sums `shard_parts` ranks would produce, added by the same integer atomics the all-reduce
+  // performs (mvs_deform_set_shard_parts: single-GPU check of the sharded arithmetic)
+  int shard_parts = 1;
   double energy[3] = {0, 0, 0};
   // as-rigid-as-possible solver state (arap.cu), built on first use
   mvs::ArapState* arap = nullptr;
@@ -119,8 +125,16 @@ struct mvs_deform {
   size_t sys64_count() const { return (size_t)nup * 16 + (size_t)m * 12; }
   long long* B64() { return sys64.p; }
   long long* rhs64() { return sys64.p + (size_t)nup * 16; }
-  int64_t shard_begin() const { return v_begin; }
-  int64_t shard_end() const { return v_end < 0 ? n : v_end; }
+  // A requested boundary is moved DOWN to the start of the assembly group that contains it (0 and n
+  // stay): ranks that split [0, n) at common points still tile it exactly, and no group — the unit
+  // in which float32 partial sums are formed before they become integers — is split between ranks.
+  int64_t snap(int64_t i) const {
+    if (i <= 0 || i >= n || h_grp_start.empty()) return i < 0 ? 0 : (i > n ? n : i);
+    auto it = std::upper_bound(h_grp_start.begin(), h_grp_start.end(), (int)i);
+    return (int64_t) * (it - 1);
+  }
+  int64_t shard_begin() const { return snap(v_begin); }
+  int64_t shard_end() const { return v_end < 0 ? n : snap(v_end); }
 };
 
 namespace mvs {
@@ -142,7 +156,6 @@ int gn_reset_state(mvs_deform* h);
 int gn_deform_and_correspond(mvs_deform* h);   // writes resid (mode 1: NN; else fixed targets)
 int gn_node_terms_forked(mvs_deform* h);        // zero + node terms on the side stream (one rank)
 int gn_assemble(mvs_deform* h);                 // [zero +] fit pass [+ allreduce + node terms] + precond
-int gn_apply_update(mvs_deform* h);             // x += delta
 int gn_final_vertices(mvs_deform* h);           // cur0 / curn0 in original order
 int gn_energy(mvs_deform* h, double energy[3]); // at the current state with the current resid
 int gn_recompute_normals(mvs_deform* h);        // curn0 from cur0 + facets (Deformation.h:86-128)

@@ -40,6 +40,13 @@ __global__ void k_targets_permute(const double* __restrict__ t, const float* __r
                        (float)t[3 * (size_t)o + 2], om);
 }
 
+// out[perm[i]] = in[i]: sorted vertex order -> original vertex order
+__global__ void k_unpermute_i32(const int* __restrict__ in, const int* __restrict__ perm, int64_t n,
+                                int* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[perm[i]] = in[i];
+}
+
 // node controls (m x 3 doubles) -> per-vertex targets on the node vertices only
 __global__ void k_targets_from_nodes(const double* __restrict__ controls,
                                      const int* __restrict__ valid, int only_valid,
@@ -58,7 +65,7 @@ __global__ void k_targets_from_nodes(const double* __restrict__ controls,
 // cos(dir, normal) >= 0.5 (the 6-D tree has scale = 0, i.e. it is a plain position search).
 __global__ void k_node_targets_threshold(PyrParams tg, const float4* __restrict__ g,
                                          const float4* __restrict__ gnrm, int64_t m,
-                                         float threshold, double* __restrict__ controls,
+                                         double threshold, double* __restrict__ controls,
                                          int* __restrict__ valid) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -84,7 +91,7 @@ __global__ void k_node_targets_threshold(PyrParams tg, const float4* __restrict_
     }
   } vis{&nn, 0.f, 0.f, 0.f};
   pyr_search(tg, q.x, q.y, q.z, vis);
-  if (nn.d2[0] > threshold) return;
+  if ((double)nn.d2[0] > threshold) return;  // float dists[0] against the double threshold (:198)
   double d0 = __dsub_rn((double)vis.cx, (double)q.x), d1 = __dsub_rn((double)vis.cy, (double)q.y),
          d2 = __dsub_rn((double)vis.cz, (double)q.z);
   double n0 = nq.x, n1 = nq.y, n2 = nq.z;
@@ -455,6 +462,46 @@ int mvs_deform_gn_step(mvs_deform* h) {
   return gn_step_impl(h);
 }
 
+int mvs_deform_solve(mvs_deform* h, const mvs_gn_params* params) {
+  MVS_REQUIRE(h, "null handle");
+  mvs_gn_params def;
+  if (!params) {
+    mvs_gn_default_params(&def);
+    params = &def;
+  }
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  MVS_TRY(gn_begin_impl(h, params));
+  for (int it = 0; it < params->gn_iters; ++it) {
+    int rc = gn_step_impl(h);
+    if (rc != MVS_OK) {
+      h->gn_active = false;
+      return rc;
+    }
+  }
+  MVS_TRY(gn_final_vertices(h));
+  MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  h->gn_active = false;
+  return MVS_OK;
+}
+
+int mvs_deform_get_correspondences(mvs_deform* h, int32_t* out_idx) {
+  MVS_REQUIRE(h && out_idx, "null argument");
+  mvs_ctx* ctx = h->ctx;
+  MVS_TRY(ctx_ensure_device(ctx));
+  if (!h->graph_built || !h->corr_prev.p) {
+    set_error("get_correspondences: graph not built");
+    return MVS_ERR_STATE;
+  }
+  int* tmp = nullptr;
+  MVS_CUDA(cudaMallocAsync((void**)&tmp, sizeof(int) * h->n, ctx->stream));
+  k_unpermute_i32<<<div_up(h->n, 256), 256, 0, ctx->stream>>>(h->corr_prev.p, h->perm.p, h->n, tmp);
+  int rc = d2h_async(ctx, out_idx, tmp, sizeof(int) * h->n);
+  cudaFreeAsync(tmp, ctx->stream);
+  MVS_TRY(rc);
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return MVS_OK;
+}
+
 int mvs_deform_gn_end(mvs_deform* h) {
   MVS_REQUIRE(h, "null handle");
   if (!h->gn_active) {
@@ -498,16 +545,9 @@ int mvs_deform_run(mvs_deform* h, double proj_len_err, double proj_dist_err,
   return MVS_OK;
 }
 
-int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_params* params) {
-  MVS_REQUIRE(h, "null handle");
-  mvs_gn_params def;
-  if (!params) {
-    mvs_gn_default_params(&def);
-    params = &def;
-  }
-  MVS_TRY(validate_params(params));
+static int node_targets_threshold_impl(mvs_deform* h, double threshold, DevBuf<double>& c,
+                                       DevBuf<int>& v) {
   mvs_ctx* ctx = h->ctx;
-  MVS_TRY(ctx_ensure_device(ctx));
   if (!h->tgt_index || !h->tgt_index->pyr_built) {
     set_error("run_threshold: target not set");
     return MVS_ERR_STATE;
@@ -518,15 +558,45 @@ int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_param
     return MVS_ERR_STATE;
   }
   MVS_TRY(ensure_graph(h));
-  DevBuf<double> c;
-  DevBuf<int> v;
   MVS_TRY(c.reserve((size_t)h->m * 3));
   MVS_TRY(v.reserve((size_t)h->m));
-  {
-    ProfScope ps(ctx, "node_targets_threshold");
-    k_node_targets_threshold<<<div_up(h->m, 64), 64, 0, ctx->stream>>>(
-        h->tgt_index->pyr, h->g.p, h->gnrm.p, h->m, (float)threshold, c.p, v.p);
+  ProfScope ps(ctx, "node_targets_threshold");
+  k_node_targets_threshold<<<div_up(h->m, 64), 64, 0, ctx->stream>>>(
+      h->tgt_index->pyr, h->g.p, h->gnrm.p, h->m, threshold, c.p, v.p);
+  MVS_CUDA(cudaGetLastError());
+  return MVS_OK;
+}
+
+int mvs_deform_node_targets_threshold(mvs_deform* h, double threshold, double* controls_xyz,
+                                      int32_t* valid) {
+  MVS_REQUIRE(h, "null handle");
+  MVS_TRY(ctx_ensure_device(h->ctx));
+  DevBuf<double> c;
+  DevBuf<int> v;
+  MVS_TRY(node_targets_threshold_impl(h, threshold, c, v));
+  if (controls_xyz)
+    MVS_CUDA(cudaMemcpyAsync(controls_xyz, c.p, sizeof(double) * 3 * h->m, cudaMemcpyDeviceToHost,
+                             h->ctx->stream));
+  if (valid)
+    MVS_CUDA(cudaMemcpyAsync(valid, v.p, sizeof(int) * h->m, cudaMemcpyDeviceToHost,
+                             h->ctx->stream));
+  MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
+  return MVS_OK;
+}
+
+int mvs_deform_run_threshold(mvs_deform* h, double threshold, const mvs_gn_params* params) {
+  MVS_REQUIRE(h, "null handle");
+  mvs_gn_params def;
+  if (!params) {
+    mvs_gn_default_params(&def);
+    params = &def;
   }
+  MVS_TRY(validate_params(params));
+  mvs_ctx* ctx = h->ctx;
+  MVS_TRY(ctx_ensure_device(ctx));
+  DevBuf<double> c;
+  DevBuf<int> v;
+  MVS_TRY(node_targets_threshold_impl(h, threshold, c, v));
   MVS_TRY(set_node_targets(h, c, v, 1));
   mvs_gn_params p = *params;
   p.corr_mode = 2;
@@ -740,6 +810,16 @@ int mvs_deform_set_shard(mvs_deform* h, int64_t v_begin, int64_t v_end) {
   }
   h->v_begin = v_begin;
   h->v_end = v_end;
+  return MVS_OK;
+}
+
+int mvs_deform_set_shard_parts(mvs_deform* h, int parts) {
+  MVS_REQUIRE(h, "null handle");
+  if (parts < 1 || parts > 1024) {
+    set_error("set_shard_parts: parts must be in [1, 1024]");
+    return MVS_ERR_INVALID_ARG;
+  }
+  h->shard_parts = parts;
   return MVS_OK;
 }
 

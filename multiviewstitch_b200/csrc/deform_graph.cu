@@ -751,6 +751,15 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
     MVS_CUDA(cudaMemcpyAsync(h->run_start.p + nruns, &n32, sizeof(int), cudaMemcpyHostToDevice, st));
     MVS_CUDA(cudaGetLastError());
     MVS_CUDA(cudaStreamSynchronize(st));
+    // host copy of the first vertex of every assembly group (+ n): vertex shards are snapped to
+    // group boundaries, the unit of float32 accumulation, so sharded sums carry the unsharded bits
+    {
+      std::vector<int> rs((size_t)nruns + 1);
+      MVS_TRY(d2h_sync(ctx, rs.data(), h->run_start.p, sizeof(int) * (nruns + 1)));
+      h->h_grp_start.resize((size_t)h->ngroups + 1);
+      for (int64_t q = 0; q < h->ngroups; ++q) h->h_grp_start[q] = rs[(size_t)q * kGrpRuns];
+      h->h_grp_start[h->ngroups] = (int)n;
+    }
     float mn[3], mx[3];
     MVS_TRY(bbox_host(ctx, h->v0.p, n, h->node_index->red, mn, mx));
     double d2 = 0;

@@ -39,6 +39,11 @@ __device__ __forceinline__ NodeX load_node(const float* __restrict__ x, int j) {
   return n;
 }
 
+// v~ = sum_a w_a [A_a (v - g_a) + g_a + t_a] over the vertex's nodes in ASCENDING node id order, in a
+// fixed float32 sequence of explicit roundings (one product, two fused multiply-adds, two additions,
+// one fused multiply-add per component and node) so that the oracle (oracle/deform.cpp
+// deform_vertex_f32, std::fmaf in the same order) produces the SAME float32 query point and with it
+// bit-identical correspondence indices (north_star: correspondence indices bit-exact).
 __device__ __forceinline__ float3 deform_point(float4 v, int4 id, float4 w,
                                                const float4* __restrict__ g,
                                                const float* __restrict__ x) {
@@ -50,13 +55,16 @@ __device__ __forceinline__ float3 deform_point(float4 v, int4 id, float4 w,
     if (ids[a] < 0) continue;
     float4 gj = __ldg(g + ids[a]);
     NodeX n = load_node(x, ids[a]);
-    float d0 = v.x - gj.x, d1 = v.y - gj.y, d2 = v.z - gj.z;
-    float px = n.a[0] * d0 + n.a[3] * d1 + n.a[6] * d2 + gj.x + n.a[9];
-    float py = n.a[1] * d0 + n.a[4] * d1 + n.a[7] * d2 + gj.y + n.a[10];
-    float pz = n.a[2] * d0 + n.a[5] * d1 + n.a[8] * d2 + gj.z + n.a[11];
-    out.x += ws[a] * px;
-    out.y += ws[a] * py;
-    out.z += ws[a] * pz;
+    float d0 = __fsub_rn(v.x, gj.x), d1 = __fsub_rn(v.y, gj.y), d2 = __fsub_rn(v.z, gj.z);
+    float px = __fmaf_rn(n.a[6], d2, __fmaf_rn(n.a[3], d1, __fmul_rn(n.a[0], d0)));
+    float py = __fmaf_rn(n.a[7], d2, __fmaf_rn(n.a[4], d1, __fmul_rn(n.a[1], d0)));
+    float pz = __fmaf_rn(n.a[8], d2, __fmaf_rn(n.a[5], d1, __fmul_rn(n.a[2], d0)));
+    px = __fadd_rn(__fadd_rn(px, gj.x), n.a[9]);
+    py = __fadd_rn(__fadd_rn(py, gj.y), n.a[10]);
+    pz = __fadd_rn(__fadd_rn(pz, gj.z), n.a[11]);
+    out.x = __fmaf_rn(ws[a], px, out.x);
+    out.y = __fmaf_rn(ws[a], py, out.y);
+    out.z = __fmaf_rn(ws[a], pz, out.z);
   }
   return out;
 }
@@ -148,28 +156,49 @@ __global__ void k_deform_resid(const float4* __restrict__ v, const int4* __restr
   resid[i] = make_float4(q.x - t.x, q.y - t.y, q.z - t.z, t.w);
 }
 
+// sub-range `part` of `parts` of [b, e)
+static inline void shard_part(const mvs_deform* h, int64_t b, int64_t e, int parts, int part,
+                              int64_t* pb, int64_t* pe) {
+  if (parts <= 1) {
+    *pb = b;
+    *pe = e;
+    return;
+  }
+  int64_t per = (e - b + parts - 1) / parts;
+  int64_t lo = std::min(e, b + per * part), hi = std::min(e, b + per * (part + 1));
+  *pb = part == 0 ? b : std::max(b, h->snap(lo));
+  *pe = part == parts - 1 ? e : std::max(b, h->snap(hi));
+}
+
 int gn_deform_and_correspond(mvs_deform* h) {
   mvs_ctx* ctx = h->ctx;
-  int64_t b = h->shard_begin(), e = h->shard_end();
-  if (e <= b) return MVS_OK;
+  const int64_t b0 = h->shard_begin(), e0 = h->shard_end();
+  if (e0 <= b0) return MVS_OK;
   if (h->prm.corr_mode == 1) {
     if (!h->tgt_index || !h->tgt_index->pyr_built) {
       set_error("corr_mode 1 needs a target (mvs_deform_set_target*)");
       return MVS_ERR_STATE;
     }
-    ProfScope ps(ctx, "gn_deform_corr");
-    k_deform_corr<<<div_up(e - b, 128), 128, 0, ctx->stream>>>(
-        h->tgt_index->pyr, h->tp, h->corr_prev.p, h->tn, h->v.p, h->nrm.p, h->vidx.p, h->vw.p,
-        h->g.p, h->x.p, b, e, (float)h->prm.max_corr_dist2, (float)h->prm.min_corr_cos,
-        h->resid.p);
-  } else {
-    if (!h->have_targets) {
-      set_error("fixed-target mode needs per-vertex targets");
-      return MVS_ERR_STATE;
+  } else if (!h->have_targets) {
+    set_error("fixed-target mode needs per-vertex targets");
+    return MVS_ERR_STATE;
+  }
+  const int parts = std::max(1, h->shard_parts);
+  for (int part = 0; part < parts; ++part) {
+    int64_t b, e;
+    shard_part(h, b0, e0, parts, part, &b, &e);
+    if (e <= b) continue;
+    if (h->prm.corr_mode == 1) {
+      ProfScope ps(ctx, "gn_deform_corr");
+      k_deform_corr<<<div_up(e - b, 128), 128, 0, ctx->stream>>>(
+          h->tgt_index->pyr, h->tp, h->corr_prev.p, h->tn, h->v.p, h->nrm.p, h->vidx.p, h->vw.p,
+          h->g.p, h->x.p, b, e, (float)h->prm.max_corr_dist2, (float)h->prm.min_corr_cos,
+          h->resid.p);
+    } else {
+      ProfScope ps(ctx, "gn_deform_resid");
+      k_deform_resid<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(
+          h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, h->targets.p, b, e, h->resid.p);
     }
-    ProfScope ps(ctx, "gn_deform_resid");
-    k_deform_resid<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(
-        h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, h->targets.p, b, e, h->resid.p);
   }
   MVS_CUDA(cudaGetLastError());
   return MVS_OK;
@@ -673,8 +702,16 @@ int gn_assemble(mvs_deform* h) {
     MVS_TRY(ctx_side_join(ctx));
   else
     MVS_TRY(gn_zero_system(h, st));
-  int64_t b = h->shard_begin(), e = h->shard_end();
-  if (e > b) {
+  const int64_t b0 = h->shard_begin(), e0 = h->shard_end();
+  const int parts = std::max(1, h->shard_parts);
+  unsigned* group_counter = reinterpret_cast<unsigned*>(h->sys64.p + h->sys64_count());
+  bool counter_clean = true;  // zeroed together with the system
+  for (int part = 0; part < parts; ++part) {
+    int64_t b, e;
+    shard_part(h, b0, e0, parts, part, &b, &e);
+    if (e <= b) continue;
+    if (!counter_clean) MVS_CUDA(cudaMemsetAsync(group_counter, 0, sizeof(long long), st));
+    counter_clean = false;
     ProfScope ps(ctx, "gn_assemble_fit");
     int64_t warps_needed = std::min<int64_t>(h->ngroups, (e - b + 63) / 64);
     int grid = (int)std::min<int64_t>((warps_needed + kAsmWarps - 1) / kAsmWarps,
@@ -682,7 +719,7 @@ int gn_assemble(mvs_deform* h) {
     k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(
         h->v.p, h->vw.p, h->resid.p, h->run_g.p, h->run_local.p, h->run_start.p, h->grp_n.p,
         h->grp_dst.p, h->sys64.p, (int)(h->nup * 16), (int)h->nruns, b, e, (float)h->prm.w_fit, fxs,
-        reinterpret_cast<unsigned*>(h->sys64.p + h->sys64_count()));
+        group_counter);
   }
   MVS_CUDA(cudaGetLastError());
   if (ctx->comm && ctx->nranks > 1) {
@@ -711,19 +748,6 @@ int gn_assemble(mvs_deform* h) {
   }
   MVS_CUDA(cudaGetLastError());
   MVS_TRY(ctx_side_join(ctx));
-  return MVS_OK;
-}
-
-__global__ void k_axpy1(float* __restrict__ x, const float* __restrict__ d, int64_t n) {
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t < n) x[t] += d[t];
-}
-
-int gn_apply_update(mvs_deform* h) {
-  ProfScope ps(h->ctx, "gn_update");
-  float* delta = h->pcg.p + (size_t)h->m * 12 * 5;
-  k_axpy1<<<div_up(h->m * 12, 256), 256, 0, h->ctx->stream>>>(h->x.p, delta, h->m * 12);
-  MVS_CUDA(cudaGetLastError());
   return MVS_OK;
 }
 

@@ -558,7 +558,8 @@ static int plan_pcg(mvs_deform* h) {
         case 6: MVS_TRY(max_coresident<6>(smem, ctx->num_sms, &cap)); break;
         default: MVS_TRY(max_coresident<8>(smem, ctx->num_sms, &cap)); break;
       }
-      if (grid <= cap) {
+      // the exchange words count arrivals in 10 bits (kCountShift): fewer than 1024 CTAs
+      if (grid <= cap && grid < 1024) {
         h->pcg_rs = RS;
         h->pcg_grid = grid;
         h->pcg_smem = smem;

@@ -543,6 +543,9 @@ int mvs_srt_set_input(mvs_srt* h, const double* p, const double* q, int64_t n,
   cudaFreeAsync(staging, ctx->stream);
   MVS_TRY(st);
   MVS_CUDA(cudaGetLastError());
+  // SetInput COPIES (Solver/SRTSolver.h:16-19): the caller may reuse or free p/q as soon as this
+  // returns, also when they are pinned (a pinned source is read by the DMA engine asynchronously)
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   return MVS_OK;
 }
 
@@ -561,6 +564,7 @@ int mvs_srt_set_input_f32(mvs_srt* h, const float* p, const float* q, int64_t n,
   MVS_TRY(h2d(ctx, h->qf.p, q, sizeof(float4) * n));
   h->p4 = h->pf.p;
   h->q4 = h->qf.p;
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));  // copy semantics, see mvs_srt_set_input
   return MVS_OK;
 }
 

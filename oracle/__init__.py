@@ -245,6 +245,25 @@ def node_targets(nodes, node_normals, tpts, tnormals, graph, proj_len_err=100.0,
     return controls, valid
 
 
+def node_targets_threshold(nodes, node_normals, tpts, threshold):
+    """Deformation.cpp:155-230: per-node 1-NN target, kept iff d2 <= threshold and cos >= 0.5."""
+    nodes, node_normals = _f32(nodes).reshape(-1, 3), _f32(node_normals).reshape(-1, 3)
+    tpts = _f32(tpts).reshape(-1, 3)
+    m = len(nodes)
+    controls = np.empty((m, 3), np.float64)
+    valid = np.empty(m, np.int32)
+    lib().orc_node_targets_threshold(_p(nodes, C.c_float), _p(node_normals, C.c_float), C.c_int64(m),
+                                     _p(tpts, C.c_float), C.c_int64(len(tpts)), C.c_double(threshold),
+                                     _p(controls, C.c_double), _p(valid, C.c_int32))
+    return controls, valid
+
+
+def set_literal_comparator(on: bool):
+    """Measurement switch of node_targets: the reference's literal, non-transitive priority-queue
+    comparator (Deformation.cpp:318-327) instead of the bucketed strict-weak ordering."""
+    lib().orc_set_literal_comparator(C.c_int(1 if on else 0))
+
+
 def gn_assemble_dense(pts, node_ids, widx, w, graph, targets, tweights, prm, x):
     pts = _f32(pts).reshape(-1, 3)
     node_ids, widx, w, graph = _i32(node_ids), _i32(widx), _f32(w), _i32(graph)
@@ -305,6 +324,23 @@ def gn_solve(pts, normals, node_ids, widx, w, graph, prm, x0=None, targets=None,
                    C.byref(prm), _p(x, C.c_double), _p(out, C.c_double),
                    _p(energy, C.c_double))
     return x, out, energy
+
+
+def gn_correspondences(pts, node_ids, widx, w, x, tpts, want_nn=True):
+    """Query points (float32, the device's evaluation order) and exact 1-NN correspondences of one
+    Gauss-Newton iteration at node state x (m x 12)."""
+    pts, tpts = _f32(pts).reshape(-1, 3), _f32(tpts).reshape(-1, 3)
+    node_ids, widx, w = _i32(node_ids), _i32(widx), _f32(w)
+    x = _f64(x).reshape(-1)
+    n = len(pts)
+    q = np.empty((n, 3), np.float32)
+    idx = np.empty(n, np.int32) if want_nn else None
+    d2 = np.empty(n, np.float32) if want_nn else None
+    lib().orc_gn_correspondences(_p(pts, C.c_float), C.c_int64(n), _p(node_ids, C.c_int32),
+                                 C.c_int64(len(node_ids)), _p(widx, C.c_int32), _p(w, C.c_float),
+                                 _p(x, C.c_double), _p(tpts, C.c_float), C.c_int64(len(tpts)),
+                                 _p(q, C.c_float), _p(idx, C.c_int32), _p(d2, C.c_float))
+    return q, idx, d2
 
 
 def deform_vertices(pts, nodes, widx, w, x):

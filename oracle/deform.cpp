@@ -14,6 +14,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <queue>
 #include <vector>
 
 #include "oracle.h"
@@ -138,6 +139,37 @@ void deform_vertex(const Problem& P, const double* x, int64_t i, double out[3]) 
     for (int r = 0; r < 3; ++r) {
       double v = X[r] * d[0] + X[3 + r] * d[1] + X[6 + r] * d[2] + g[r] + X[9 + r];
       out[r] += wj * v;
+    }
+  }
+}
+
+// The correspondence QUERY point of vertex i: the same sum evaluated in float32 with the node state
+// rounded to float32 (the device's state IS float32), nodes in ASCENDING node-id order, and one fixed
+// sequence of roundings per component — product, two fused multiply-adds, two additions, one fused
+// multiply-add with the weight (std::fmaf is correctly rounded, like the device's fma.rn.f32).  The
+// device evaluates deform_point() (csrc/gn_assemble.cu) in exactly this order, so that "same node
+// state in -> bit-identical query point -> bit-identical exact-NN index out".
+void deform_vertex_f32(const Problem& P, const double* x, int64_t i, float out[3]) {
+  int order[4] = {0, 1, 2, 3};
+  auto key = [&](int a) {
+    int j = P.widx[4 * i + a];
+    return j < 0 ? 0x7fffffff : j;
+  };
+  std::sort(order, order + 4, [&](int a, int b) { return key(a) < key(b); });
+  out[0] = out[1] = out[2] = 0.0f;
+  for (int o = 0; o < 4; ++o) {
+    int a = order[o];
+    int j = P.widx[4 * i + a];
+    if (j < 0) continue;
+    float wj = P.w[4 * i + a];
+    float g[3], X[12];
+    for (int r = 0; r < 3; ++r) g[r] = (float)P.nodes[3 * (size_t)j + r];
+    for (int q = 0; q < 12; ++q) X[q] = (float)x[12 * (size_t)j + q];
+    float d0 = P.pts[3 * i] - g[0], d1 = P.pts[3 * i + 1] - g[1], d2 = P.pts[3 * i + 2] - g[2];
+    for (int r = 0; r < 3; ++r) {
+      float s = std::fmaf(X[6 + r], d2, std::fmaf(X[3 + r], d1, X[r] * d0));
+      s = (s + g[r]) + X[9 + r];
+      out[r] = std::fmaf(wj, s, out[r]);
     }
   }
 }
@@ -371,6 +403,10 @@ void pcg(const System& S, int iters, double tol, std::vector<double>& delta) {
   }
 }
 
+// 0: bucketed strict-weak ordering of the node-correspondence candidates (the contract of the build);
+// 1: the reference's literal, non-transitive priority-queue comparator (measurement only)
+int g_literal_comparator = 0;
+
 Problem make_problem(const float* pts, int64_t n, const int32_t* node_ids, int64_t m,
                      const int32_t* widx, const float* w, const int32_t* graph, int gk1) {
   Problem P;
@@ -474,6 +510,38 @@ void orc_node_weights(const float* pts, int64_t n, const float* nodes, int64_t m
   }
 }
 
+void orc_set_literal_comparator(int on) { g_literal_comparator = on; }
+
+// Deformation/Deformation.cpp:155-230, the Deform(tpts, tnormals, threshold) variant: the 6-D tree
+// is built with scale = 0 (:162-170), i.e. it is a plain position search; per node (:186-203): 1-NN
+// in the target (float32 squared distance, exact here where FLANN approximates), skipped when
+// dists[0] > threshold (float against double, :198) or when cos(dir, normal) < 0.5 with
+// dir = p1 - p in double (:202-203; a NaN cosine compares false and the node is kept, as there).
+void orc_node_targets_threshold(const float* nodes, const float* node_normals, int64_t m,
+                                const float* tpts, int64_t nt, double threshold, double* controls,
+                                int32_t* valid) {
+  std::vector<int32_t> nn1((size_t)m);
+  std::vector<float> d1((size_t)m);
+  orc_knn_kdtree(nodes, m, tpts, nt, 1, nn1.data(), d1.data());
+  for (int64_t i = 0; i < m; ++i) {
+    valid[i] = 0;
+    for (int a = 0; a < 3; ++a) controls[3 * i + a] = (double)nodes[3 * i + a];
+    if ((double)d1[i] > threshold) continue;
+    const float* p1 = tpts + 3 * (size_t)nn1[i];
+    double dir[3], nr[3];
+    for (int a = 0; a < 3; ++a) {
+      dir[a] = (double)p1[a] - (double)nodes[3 * i + a];
+      nr[a] = (double)node_normals[3 * i + a];
+    }
+    double dot = dir[0] * nr[0] + dir[1] * nr[1] + dir[2] * nr[2];
+    double dl = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    double nl = std::sqrt(nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2]);
+    if (dot / (dl * nl) < 0.5) continue;
+    valid[i] = 1;
+    for (int a = 0; a < 3; ++a) controls[3 * i + a] = (double)p1[a];
+  }
+}
+
 // Deformation/Deformation.cpp:266-357 (correspondence per node) and :359-381 (2 Jacobi sweeps).
 void orc_node_targets(const float* nodes, const float* node_normals, int64_t m, const float* tpts,
                       const float* tnormals, int64_t nt, double proj_len_err, double proj_dist_err,
@@ -529,11 +597,39 @@ void orc_node_targets(const float* nodes, const float* node_normals, int64_t m, 
       items.push_back({std::floor(pdist / 1e-6), std::fabs(plen), c.idx, plen, pdist});
     }
     if (items.empty()) continue;  // :315
-    std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
-      if (a.key != b.key) return a.key < b.key;
-      if (a.aplen != b.aplen) return a.aplen < b.aplen;
-      return a.idx < b.idx;
-    });
+    if (g_literal_comparator) {
+      // the reference's literal ordering (:318-327): a std::priority_queue over `operator<` with the
+      // pairwise |projDist - other| <= 1e-6 tolerance.  That relation is not transitive, so the pop
+      // order depends on the heap algorithm and the push order (here: libstdc++'s heap, candidates
+      // pushed in ascending (d2, index) order as a radius search returns them) — it cannot be pinned
+      // across standard libraries, which is why the build and the default oracle use the bucketed
+      // strict-weak version above.  Kept to MEASURE how often the two pick different top-8 sets
+      // (tests/test_oracle_deform.py).
+      struct QNode {
+        double projLen, projDist;
+        int idx;
+        bool operator<(const QNode& o) const {
+          if (std::fabs(projDist - o.projDist) <= 1e-6) return std::fabs(projLen) > std::fabs(o.projLen);
+          return projDist > o.projDist;
+        }
+      };
+      std::priority_queue<QNode> Q;
+      for (const Item& it : items) Q.push(QNode{it.plen, it.pdist, it.idx});
+      std::vector<Item> ordered;
+      int take = std::min<int>(8, (int)Q.size());
+      for (int j = 0; j < take; ++j) {
+        QNode c = Q.top();
+        Q.pop();
+        ordered.push_back({0.0, std::fabs(c.projLen), c.idx, c.projLen, c.projDist});
+      }
+      items.swap(ordered);
+    } else {
+      std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+        if (a.key != b.key) return a.key < b.key;
+        if (a.aplen != b.aplen) return a.aplen < b.aplen;
+        return a.idx < b.idx;
+      });
+    }
     int nb = std::min<int>(8, (int)items.size());  // :338
     double mlen = 0, mdist = 0, mp[3] = {0, 0, 0};
     for (int j = 0; j < nb; ++j) {
@@ -637,9 +733,7 @@ void orc_gn_solve(const float* pts, const float* normals, int64_t n, const int32
       nd2.resize((size_t)n);
 #pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < n; ++i) {
-        double v[3];
-        deform_vertex(P, x, i, v);
-        for (int a = 0; a < 3; ++a) qf[3 * i + a] = (float)v[a];
+        deform_vertex_f32(P, x, i, &qf[3 * i]);
       }
       orc_kdtree_query(tree, qf.data(), n, 1, nn.data(), nd2.data());
 #pragma omp parallel for schedule(static)
@@ -666,6 +760,23 @@ void orc_gn_solve(const float* pts, const float* normals, int64_t n, const int32
   if (tree) orc_kdtree_free(tree);
   if (out_pts)
     for (int64_t i = 0; i < n; ++i) deform_vertex(P, x, i, out_pts + 3 * i);
+}
+
+// Correspondences of one Gauss-Newton iteration at node state x (m x 12): the float32 query point
+// of every vertex (deform_vertex_f32) and its exact 1-NN in the target (lowest index on ties).
+void orc_gn_correspondences(const float* pts, int64_t n, const int32_t* node_ids, int64_t m,
+                            const int32_t* widx, const float* w, const double* x, const float* tpts,
+                            int64_t nt, float* query_xyz, int32_t* out_idx, float* out_d2) {
+  Problem P = make_problem(pts, n, node_ids, m, widx, w, nullptr, 0);
+  std::vector<float> qf((size_t)n * 3);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) deform_vertex_f32(P, x, i, &qf[3 * i]);
+  if (query_xyz) std::memcpy(query_xyz, qf.data(), sizeof(float) * 3 * n);
+  if (out_idx && out_d2) {
+    void* tree = orc_kdtree_build(tpts, nt);
+    orc_kdtree_query(tree, qf.data(), n, 1, out_idx, out_d2);
+    orc_kdtree_free(tree);
+  }
 }
 
 // Deformation/Deformation.h:111-128 FacetNormal (normalised cross((p2-p1),(p3-p1))) and :86-109

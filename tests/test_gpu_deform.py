@@ -199,11 +199,15 @@ def test_rigid_motion_recovered(ctx):
     d = api.Deformation(pts, nrm, faces, ctx)
     d.SampleFPS(60, 0)
     d.SetTargets(targets)
-    d.GNBegin(api.gn_params(gn_iters=8, pcg_iters=200, corr_mode=2))
+    d.GNBegin(api.gn_params(gn_iters=8, pcg_iters=50, corr_mode=2))
     for _ in range(8):
         d.GNStep()
     d.GNEnd()
-    assert np.abs(d.Vertices() - targets).max() < 2e-4
+    # 50 PCG iterations: 2e-7 after every GN iteration from the 4th on.  (200 float32 PCG iterations
+    # on an already converged system resolve the rounding noise of J^T r along the weakly constrained
+    # modes, lambda = 1e-6: 2e-7 after 4 and 12 GN iterations but 2e-4 after 8, scratch/rigid_probe.py
+    # — still inside the 1e-4 x diagonal bar.)
+    assert np.abs(d.Vertices() - targets).max() < 5e-6
     A = d.NodeState()[:, :9].reshape(-1, 3, 3).transpose(0, 2, 1)
     assert np.allclose(A, R[None], atol=2e-3)
     # identity targets: zero update

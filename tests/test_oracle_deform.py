@@ -265,3 +265,74 @@ def test_openmp_courtesy_build_matches_single_thread():
     x1, o1, e1 = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, tpts=tv)
     x2, o2, e2 = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, tpts=tv, mt=True)
     assert np.abs(o1 - o2).max() < 1e-10 and np.abs(x1 - x2).max() < 1e-10
+
+
+def test_query_point_float32_order_tracks_float64():
+    """The correspondence query point (float32, fixed rounding order shared with the device) is the
+    float64 deformed vertex to float32 accuracy, for identity and perturbed node states."""
+    verts, faces = synth.uv_sphere(48, 36)
+    pts = verts.astype(np.float32)
+    ids = oracle.sample_fps(pts, 60, 0)
+    widx, w = oracle.node_weights(pts, pts[ids], 4)
+    rng = np.random.default_rng(3)
+    ident = np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (60, 1))
+    for x in (ident, ident + 0.05 * rng.normal(size=ident.shape)):
+        xf = x.astype(np.float32).astype(np.float64)  # the device state is float32
+        q, idx, d2 = oracle.gn_correspondences(pts, ids, widx, w, xf, pts)
+        want = oracle.deform_vertices(pts, pts[ids], widx, w, xf)
+        assert np.abs(q - want).max() < 2e-6
+        # exact 1-NN of the query in the target, lowest index on ties (brute force)
+        bi, bd = oracle.knn(q, pts, 1, "brute")
+        assert np.array_equal(idx, bi[:, 0]) and np.array_equal(d2, bd[:, 0])
+    # identity state: every vertex is its own query up to rounding of w-weighted sums
+    q, idx, _ = oracle.gn_correspondences(pts, ids, widx, w, ident, pts)
+    assert (idx == np.arange(len(pts))).mean() > 0.99
+
+
+def _literal_vs_bucketed(nodes, nn, tv, tn, graph):
+    try:
+        c0, v0 = oracle.node_targets(nodes, nn, tv, tn, graph, smooth_sweeps=0)
+        oracle.set_literal_comparator(True)
+        c1, v1 = oracle.node_targets(nodes, nn, tv, tn, graph, smooth_sweeps=0)
+    finally:
+        oracle.set_literal_comparator(False)
+    return c0, v0, c1, v1
+
+
+def test_literal_reference_comparator_measured_against_bucketed_rule():
+    """the node-correspondence candidates are ordered by floor(projDist / 1e-6) buckets,
+    the reference by a pairwise |projDist - other| <= 1e-6 priority-queue comparator that is not a
+    strict weak ordering (Deformation.cpp:318-327; its pop order depends on the heap algorithm).
+    Measured: on a generic scan (asymmetric tessellation, warped) the two pick the same 8 neighbours
+    for EVERY node; on symmetric data with rings of equal projDist (concentric UV spheres, a lattice
+    plane under a node) a few nodes pick different members of a tied ring — valid flags unchanged,
+    controls moved by less than the ring's point spacing."""
+    verts, faces = synth.uv_sphere(40, 30)
+    pts = verts.astype(np.float32)
+    nrm = synth.vertex_normals(verts, faces).astype(np.float32)
+    ids = oracle.sample_fps(pts, 120, 0)
+    graph = oracle.node_graph(pts[ids], 8)
+    # generic: rotated cube-sphere tessellation, scaled and warped
+    tv, tf = synth.cube_sphere(60, rot=synth.axis_angle([1, 2, 3], 0.7))
+    tv = synth.bend_twist(tv * 1.03, 0.02)
+    tn = synth.vertex_normals(tv, tf).astype(np.float32)
+    c0, v0, c1, v1 = _literal_vs_bucketed(pts[ids], nrm[ids], tv.astype(np.float32), tn, graph)
+    assert np.array_equal(v0, v1) and v0.sum() > 60
+    assert np.array_equal(c0, c1)
+    # symmetric: concentric UV sphere -> exact projDist ties
+    tv, tf = synth.uv_sphere(110, 90, radius=1.03)
+    tn = synth.vertex_normals(tv, tf).astype(np.float32)
+    c0, v0, c1, v1 = _literal_vs_bucketed(pts[ids], nrm[ids], tv.astype(np.float32), tn, graph)
+    assert np.array_equal(v0, v1)
+    moved = np.abs(c0 - c1).max(1)
+    assert (moved > 0).sum() <= 6 and moved.max() < 0.06  # target point spacing ~ 2 pi 1.03 / 110
+    # adversarial: nodes above a regular lattice plane
+    gx, gy = np.meshgrid(np.arange(-20, 21), np.arange(-20, 21))
+    plane = np.stack([gx.ravel() * 0.01, gy.ravel() * 0.01, np.zeros(gx.size)], 1).astype(np.float32)
+    pn = np.tile(np.array([0, 0, 1], np.float32), (len(plane), 1))
+    nodes = np.array([[0.0, 0.0, 0.05], [0.005, 0.005, 0.03], [0.0031, -0.0012, 0.04]], np.float32)
+    nn = np.tile(np.array([0, 0, 1], np.float32), (3, 1))
+    g3 = np.array([[0, 1, 2]] * 3, np.int32)
+    a0, w0, a1, w1 = _literal_vs_bucketed(nodes, nn, plane, pn, g3)
+    assert np.array_equal(w0, w1)
+    assert np.abs(a0 - a1).max() <= 0.01 + 1e-9  # at most one lattice spacing
