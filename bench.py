@@ -1,23 +1,30 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the non-rigid alignment hot path (BASELINE.json metric).
 
-Workload (BASELINE.json configs[2], "C3"): one closed 1,000,002-vertex mesh (UV sphere with
-bumps), a 4096-node deformation graph (farthest-point sampling, k = 4 node weights, 8-neighbour
-node graph), target = the mesh warped by a smooth bend+twist (5 % of the bbox diagonal), exact-NN
-correspondences re-derived in every Gauss-Newton iteration, 10 GN iterations x 20 block-Jacobi PCG
-iterations, then the vertex update (deformed vertices + recomputed normals).
+Workload (BASELINE.json configs[2], "C3"): one closed 1,003,688-vertex cube-sphere mesh with bumps
+(near-uniform density), a 4096-node deformation graph (farthest-point sampling, k = 4 node weights,
+8-neighbour node graph), target "scan" = the same shape re-tessellated (turned, 2.7 % finer) and warped
+by a smooth bend+twist of 5 % of the bbox diagonal, exact-NN correspondences re-derived in every
+Gauss-Newton iteration, 10 GN iterations x 20 block-Jacobi PCG iterations, then the vertex update
+(deformed vertices + recomputed normals).
 
 A "step" is one such 10-iteration solve starting from the identity node state.
-  value  = GN iterations / s with every input resident in HBM (K steps, device-timed)
+  value  = GN iterations / s with every input resident in HBM: K steps, each ONE library call
+           (mvs_deform_solve), device-timed, per-family profiling OFF; `families` and `roofline` come
+           from a second, separately profiled pass over the same K steps
   e2e    = the same metric through the host-buffer C ABI a reference caller would use:
-           mvs_deform_set_target_f32(host) -> gn_begin -> 10 x gn_step -> gn_end ->
-           mvs_deform_get_vertices_f32(host), H2D/D2H inside the timed region
-  --gpus N: one process per GPU, every rank solves its own mesh (independent objects, as the
-           reference's independent view pairs — no data-path collective), scaling "weak".
-  --mode shard: ONE mesh vertex-sharded over the ranks with an NCCL all-reduce of the J^T J / J^T r
-           node blocks (configs[4] layout), scaling "strong".
+           mvs_deform_set_target_f32(host) -> mvs_deform_solve -> mvs_deform_get_vertices_f32(host),
+           H2D/D2H inside the timed region
+  --gpus N: one process per GPU.  The headline line is N independent C3 meshes (the reference's
+           independent objects, no data-path collective, scaling "weak"); at EVERY N the line also
+           carries north_star's two partitions: secondary.c4_pairs (configs[3]: 28 view pairs sharded
+           pair -> rank, one mvs_stitch_pairs call per rank) and secondary.c5_shard (configs[4]: ONE
+           5M-vertex / 20K-node graph vertex-sharded over the ranks with an NCCL all-reduce of the
+           fixed-point J^T J / J^T r blocks, checked bitwise against the unsharded solve).
+  --mode shard / --mode pairs: those two partitions as the headline line of their own run.
   --impl reference: the CPU oracle (oracle/, single thread like the reference) on the same
-           workload, bounded to --steps solves of --ref-gn-iters iterations.
+           workload; a step = one full solve, and `steps` reports the solves actually timed
+           inside --ref-budget-s.
 """
 from __future__ import annotations
 
@@ -51,12 +58,21 @@ def parse():
                     help="--mode pairs: host threads per rank, each with its own context/stream, "
                          "working through the rank's pairs concurrently (independent units); "
                          "0 = min(4, host cores / ranks)")
-    ap.add_argument("--side", type=int, default=408, help="cube-sphere grid side (verts = 6*side^2+2)")
+    ap.add_argument("--side", type=int, default=409, help="cube-sphere grid side (verts = 6*side^2+2)")
     ap.add_argument("--nodes", type=int, default=4096)
     ap.add_argument("--gn-iters", type=int, default=10)
     ap.add_argument("--pcg-iters", type=int, default=20)
-    ap.add_argument("--ref-gn-iters", type=int, default=10)
-    ap.add_argument("--ref-budget-s", type=float, default=120.0)
+    ap.add_argument("--ref-gn-iters", type=int, default=0,
+                    help="GN iterations of the in-line cpu_baseline solve (0 = --gn-iters)")
+    ap.add_argument("--ref-budget-s", type=float, default=100.0)
+    ap.add_argument("--c5-side", type=int, default=913, help="secondary.c5_shard mesh (5,001,416 verts)")
+    ap.add_argument("--c5-nodes", type=int, default=20000)
+    ap.add_argument("--c5-steps", type=int, default=3)
+    ap.add_argument("--c5-cpu", action="store_true",
+                    help="also run the CPU oracle on the C5 workload (about two minutes) and report "
+                         "the distance of the GPU result to it")
+    ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
@@ -174,7 +190,21 @@ def cpu_solve_openmp(args, pts, tgt, gn_iters, graph_parts):
                     "products in parallel, kd-tree build serial); the reference is single-threaded"}
 
 
+def base_config(args, n, nt):
+    """The `config` object — identical on both arms (the reference arm runs the same workload)."""
+    return {"workload": workload_name(args, n), "verts": int(n), "target_points": int(nt),
+            "nodes": int(args.nodes), "gn_iters": int(args.gn_iters), "pcg_iters": int(args.pcg_iters),
+            "mode": args.mode,
+            "step": f"one {args.gn_iters}-iteration solve from the identity node state + vertex update",
+            "l2": "per-iteration working set ~100 MB (> L2 with the target); the GPU arm also writes a "
+                  "512 MiB flush buffer between timed steps"}
+
+
 def run_reference(args):
+    """The reference's CPU path (the oracle port: the reference's Deformation stage needs CGAL and
+    FLANN and cannot be compiled here) on the SAME workload with all the host threads it can use —
+    one, like the reference.  A step = one full 10-iteration solve (about 7 s); the run is bounded
+    by --ref-budget-s and `steps` reports the solves actually timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -184,38 +214,42 @@ def run_reference(args):
     nodes = pts[ids]
     widx, w = oracle.node_weights(pts, nodes, 4)
     graph = oracle.node_graph(nodes, 8)
-    prm = oracle.gn_params(gn_iters=args.ref_gn_iters, pcg_iters=args.pcg_iters, corr_mode=1)
+    prm = oracle.gn_params(gn_iters=args.gn_iters, pcg_iters=args.pcg_iters, corr_mode=1)
     times = []
     t_begin = time.perf_counter()
-    for s in range(args.warmup + args.steps):
-        if s < args.warmup and s > 0:
-            continue  # one warm-up pass is enough to page the arrays in; the CPU has no JIT
+    warm = 1 if args.warmup > 0 else 0  # one pass pages the arrays in; the CPU has no JIT to warm
+    for s in range(warm + args.steps):
         if times and time.perf_counter() - t_begin > args.ref_budget_s:
-            break  # bounded sample: keep the whole run within a few minutes
+            break  # bounded sample: the whole run stays within a few minutes
         t0 = time.perf_counter()
-        oracle.gn_solve(pts, None, ids, widx, w, graph, prm, tpts=tgt)
+        x, out, _ = oracle.gn_solve(pts, None, ids, widx, w, graph, prm, tpts=tgt)  # incl. vertex update
         dt = time.perf_counter() - t0
-        if s >= args.warmup:
+        if s >= warm:
             times.append(dt)
     tot = sum(times)
-    val = args.ref_gn_iters * len(times) / tot
-    sample = (f"{len(times)} solve(s) of {args.ref_gn_iters} GN x {args.pcg_iters} PCG iterations on the "
-              f"full {len(pts)}-vertex / {args.nodes}-node workload (kd-tree NN, no vertex update)")
+    val = args.gn_iters * len(times) / tot
+    sample = (f"{len(times)} full solve(s) of {args.gn_iters} GN x {args.pcg_iters} PCG iterations on the "
+              f"whole {len(pts)}-vertex / {args.nodes}-node workload (kd-tree built once per solve, exact "
+              f"NN per iteration, deformed vertices evaluated at the end), 1 warm-up solve, "
+              f"{args.steps} requested, bounded by {args.ref_budget_s:.0f} s")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+            "steps": len(times), "steps_requested": args.steps, "warmup": warm,
+            "ms_per_step": 1e3 * tot / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, len(pts)), "l2": "inputs larger than L2"},
+            "config": base_config(args, len(pts), len(tgt)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": sample,
-                             "note": "single thread because the reference is single-threaded; "
-                                     "the reference itself (MSVC + CGAL/OpenCV/Eigen) cannot be "
-                                     "built here, so this is the oracle port"},
+                             "note": "single thread because the reference is single-threaded; the "
+                                     "reference's Deformation stage (CGAL + FLANN, MSVC) cannot be built "
+                                     "here, so this leg is the oracle port; oracle/_ref (the reference's "
+                                     "own SRT/Camera/PointSet/Depth2Model sources) pins the port"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "host_cores": os.cpu_count()}
+            "gpu_launches": 0, "host_cores": os.cpu_count(),
+            "wall_s": time.perf_counter() - t_begin}
     try:  # courtesy number on every host core; `value` stays the single-thread reference arm
         line["cpu_baseline"]["openmp_courtesy"] = cpu_solve_openmp(
-            args, pts, tgt, args.ref_gn_iters, (ids, widx, w, graph))
+            args, pts, tgt, args.gn_iters, (ids, widx, w, graph))
     except Exception as exc:
         line["cpu_baseline"]["openmp_courtesy"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
@@ -291,11 +325,30 @@ def secondary_c2(args, api, ctx, stream, peak):
         par = q4s[inv, :3] - query[:, :3]
         d_par = (par[:, 0] * par[:, 0] + par[:, 1] * par[:, 1]) + par[:, 2] * par[:, 2]
         ok = bool(torch.equal(d_got, d2_out)) and bool((d2_out <= d_par).all())
+        # exactness spot check at full size: brute force over ALL n targets for 4096 random queries
+        # (same FMA-free float32 distance, lowest index on ties)
+        sel = torch.randint(0, n, (4096,), device="cuda", generator=g)
+        bf_idx = torch.empty(4096, dtype=torch.int64, device="cuda")
+        bf_d2 = torch.empty(4096, dtype=torch.float32, device="cuda")
+        tx, ty, tz = q4s[:, 0].contiguous(), q4s[:, 1].contiguous(), q4s[:, 2].contiguous()
+        for c0 in range(0, 4096, 64):
+            qs = query[sel[c0:c0 + 64], :3]
+            dx = tx[None, :] - qs[:, 0:1]
+            dy = ty[None, :] - qs[:, 1:2]
+            dz = tz[None, :] - qs[:, 2:3]
+            dd = (dx * dx + dy * dy) + dz * dz
+            mn = dd.min(dim=1, keepdim=True).values
+            first = torch.where(dd == mn, torch.arange(n, device="cuda")[None, :],
+                                torch.full((1, 1), n, device="cuda")).min(dim=1).values
+            bf_idx[c0:c0 + 64] = first
+            bf_d2[c0:c0 + 64] = mn[:, 0]
+            del dx, dy, dz, dd
+        brute_ok = bool(torch.equal(bf_idx, idx_out[sel].long())) and bool(torch.equal(bf_d2, d2_out[sel]))
         out["nn_corr"] = {"value": n / (best * 1e-3), "unit": "NN-corr/s", "points": n,
                           "ms": best, "binning_included": True,
                           "GBps": 40.0 * n / (best * 1e-3) / 1e9,
                           "frac_hbm": 40.0 * n / (best * 1e-3) / 1e9 / peak,
-                          "self_consistent": ok,
+                          "self_consistent": ok, "brute_force_4096_queries_exact": brute_ok,
                           "own_partner_fraction": float((idx_out.long() == inv).float().mean())}
         srt = api.SRTSolver(10, ctx)
         srt.SetPrintFlag(False)
@@ -406,17 +459,105 @@ def secondary_arap(args, api, ctx, stream, peak, d, pts, faces):
     return out
 
 
-def run_pairs(args):
-    """configs[3] (C4): 28 = C(8,2) view pairs of an 8-view turntable, each pair the C1 workload
-    (two 640x480 depth maps -> unproject -> RemoveOutliers -> SRT -> Depth2Model mesh -> apply ->
-    deformation -> Model2Depth), sharded pair -> rank u % N with no data-path collective
-    (mvs_partition_units).  A step = every rank's share of the pairs once, host buffers in and out
-    (the depth maps live in host memory, as the reference reads them from disk)."""
+# ------------------------------------------------------------------------- C4: view pairs
+def build_pair_work(api, pipeline, ctx, units):
+    """Setup (untimed): the two depth maps + lattice matches of every pair this rank owns."""
+    work = []
+    m2d = api.Model2Depth(ctx)
+    for u in units:
+        sc = pipeline.make_scene(side=72, view_angle_deg=10.0 + 1.5 * u, seed=0)
+        ca, cb = api.make_camera(*sc["cam_a"]), api.make_camera(*sc["cam_b"])
+        m2d.SetInput([sc["verts_a"], sc["verts_b"]], [None, None], [sc["faces"], sc["faces"]], [[ca], [cb]])
+        da, db = m2d.render(0)[0], m2d.render(1)[0]
+        pa, va = api.unproject_depth(da, ca, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
+        pb, vb = api.unproject_depth(db, cb, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
+        mt = pipeline.lattice_matches(pa, va, sc["cam_b"], vb, sc["planted"], 640, 480, seed=u)
+        work.append((da, ca, db, cb, mt, sc["planted"], u))
+    return work
+
+
+def c4_pairs(args, api, ctx, stream, world, rank, dist, steps, warmup, clocks_index=None):
+    """configs[3] (C4): 28 = C(8,2) view pairs of an 8-view turntable, each pair the C1 workload (two
+    640x480 depth maps -> matched pixels unprojected -> RemoveOutliers -> SRT -> Depth2Model mesh ->
+    apply -> deformation -> Model2Depth), sharded pair u -> rank u % N with no data-path collective
+    (mvs_partition_units).  A step = every rank's share once, as ONE mvs_stitch_pairs call per rank
+    (library worker threads, one stream each); host buffers in and out (the depth maps live in host
+    memory, as the reference reads them from disk), every output of every pair written back."""
     import ctypes as C
     import torch
-    import torch.distributed as dist
-    from multiviewstitch_b200 import api, pipeline, _capi
+    from multiviewstitch_b200 import pipeline, _capi
+    part = (C.c_int64 * 3)()
+    _capi.check(_capi.lib().mvs_partition_units(C.c_int64(args.pairs), C.c_int(world), C.c_int(rank), part))
+    mine = [part[0] + k * part[1] for k in range(part[2])]
+    with torch.cuda.stream(stream):
+        work = build_pair_work(api, pipeline, ctx, mine)
+        batch = api.PairBatch(ctx, want_outputs=True)
+        for da, ca, db, cb, mt, _, u in work:
+            batch.add(da, ca, db, cb, mt, seed=u)
+        cores = os.cpu_count() or 1
+        want = args.pair_workers if args.pair_workers > 0 else max(1, min(12, cores // max(world, 1) - 1))
+        nw = max(1, min(want, len(work))) if work else 1
+        prm = api.pair_params(n_nodes=512, gn_iters=4, workers=nw)
 
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        outs = []
+        for _ in range(warmup):
+            if len(batch):
+                outs = batch.run(prm)
+        ctx.launch_count_reset()
+        clocks = None
+        if clocks_index is not None and rank == 0:
+            clocks = Clocks(clocks_index)
+            clocks.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            ev[s][0].record(stream)
+            if len(batch):
+                outs = batch.run(prm)  # returns after every worker stream is synchronised
+            ev[s][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        launches = ctx.launch_count()
+        clk = clocks.stop() if clocks else None
+    worst = 0.0
+    for o, wk in zip(outs, work):  # every pair must recover its planted similarity
+        ps, pR, pt = wk[5]
+        worst = max(worst, abs(o["scale"] - ps) / ps, float(np.abs(o["R"] - pR).max()))
+    bytes_in = sum(2 * w[0].size * 4 + w[4].size * 4 for w in work)
+    bytes_out = sum(o["template"].nbytes + o["deformed"].nbytes + o["facets"].nbytes + o["render"].nbytes
+                    for o in outs)
+    t = torch.tensor([dev_ms, worst, float(launches)], dtype=torch.float64, device="cuda")
+    tsum = torch.tensor([float(bytes_in), float(bytes_out)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    dev_ms, worst = t[0].item(), t[1].item()
+    return {"metric": "view_pairs_per_s", "value": args.pairs * steps / (dev_ms * 1e-3), "unit": "pairs/s",
+            "n_gpus": world, "pairs": args.pairs, "steps": steps, "warmup": warmup,
+            "ms_per_step": dev_ms / steps, "scaling": "strong",
+            "pairs_on_busiest_rank": -(-args.pairs // world), "host_workers_per_rank": nw,
+            "host_cores": os.cpu_count(),
+            "max_srt_error_vs_planted": worst, "gpu_launches_busiest_rank": int(t[2].item()),
+            "h2d_bytes_per_step": int(tsum[0].item()), "d2h_bytes_per_step": int(tsum[1].item()),
+            "wall_s_rank0": wall, "clocks": clk,
+            "workload": f"C4: {args.pairs} view pairs (two 640x480 depth maps each) sharded pair -> rank "
+                        "u % N, one mvs_stitch_pairs call per rank: RemoveOutliers + SRT + Depth2Model + "
+                        "512-node deformation (4 GN x 20 PCG) + Model2Depth per pair"}
+
+
+def run_pairs(args):
+    """--mode pairs: configs[3] as the headline line of its own run."""
+    import torch
+    import torch.distributed as dist
+    from multiviewstitch_b200 import api
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -425,99 +566,224 @@ def run_pairs(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
     ctx = api.Context(local, stream.cuda_stream)
-    part = (C.c_int64 * 3)()
-    _capi.check(_capi.lib().mvs_partition_units(C.c_int64(args.pairs), C.c_int(world), C.c_int(rank), part))
-    mine = [part[0] + k * part[1] for k in range(part[2])]
-    work = []
+    r = c4_pairs(args, api, ctx, stream, world, rank, dist, args.steps, max(3, args.warmup), local)
+    if rank == 0:
+        line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64",
+                "data": "synthetic",
+                "config": {"workload": r["workload"], "pairs_on_busiest_rank": r["pairs_on_busiest_rank"],
+                           "l2": "host buffers per pair", "host_workers_per_rank": r["host_workers_per_rank"]},
+                "max_srt_error_vs_planted": r["max_srt_error_vs_planted"],
+                "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": r["d2h_bytes_per_step"]},
+                "gpu_launches": r["gpu_launches_busiest_rank"], "clocks": r["clocks"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------- C5: vertex-sharded graph
+def c5_shard(args, api, local, stream, world, rank, dist, peak, side, nodes, steps, with_cpu=False):
+    """configs[4] (C5): ONE 5M-vertex / 20K-node graph; every rank owns a contiguous range of the
+    sorted vertex order (snapped to assembly groups), runs the per-vertex passes on it and the partial
+    fixed-point J^T J / J^T r blocks are summed with one ncclAllReduce(int64) per GN iteration; the PCG
+    runs replicated.  Integer sums: the result is BITWISE the unsharded solve — checked on rank 0 in
+    the same run (shard_bitwise_equal)."""
+    import torch
+    from multiviewstitch_b200 import synth
+    sa = argparse.Namespace(**vars(args))
+    sa.side, sa.nodes = side, nodes
+    verts, faces = synth.cube_sphere(side)
+    tv, _ = synth.cube_sphere(int(round(side * 1.027)), rot=synth.axis_angle([1, 2, 3], 0.7))
+    pts = verts.astype(np.float32)
+    tgt = synth.bend_twist(tv, 0.05).astype(np.float32)
+    del verts, tv
+    n, nt = len(pts), len(tgt)
+    ctx = api.Context(local, stream.cuda_stream)
+    if world > 1:
+        uid = [api.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+    out = {}
     with torch.cuda.stream(stream):
-        m2d = api.Model2Depth(ctx)
-        for u in mine:  # setup: the pair's two depth maps + matches (not timed)
-            sc = pipeline.make_scene(side=72, view_angle_deg=10.0 + 1.5 * u, seed=0)
-            ca, cb = api.make_camera(*sc["cam_a"]), api.make_camera(*sc["cam_b"])
-            m2d.SetInput([sc["verts_a"], sc["verts_b"]], [None, None], [sc["faces"], sc["faces"]], [[ca], [cb]])
-            da, db = m2d.render(0)[0], m2d.render(1)[0]
-            pa, va = api.unproject_depth(da, ca, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
-            pb, vb = api.unproject_depth(db, cb, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
-            mt = pipeline.lattice_matches(pa, va, sc["cam_b"], vb, sc["planted"], 640, 480, seed=u)
-            work.append((da, ca, db, cb, mt, sc["planted"], u))
-
-        want = args.pair_workers if args.pair_workers > 0 else min(4, max(1, (os.cpu_count() or 1) // world))
-        nw = max(1, min(want, len(work)))
-        if nw == 1:
-            def step():
-                return [pipeline.stitch_pair(da, ca, db, cb, mt, ctx, n_nodes=512, gn_iters=4, seed=u)
-                        for da, ca, db, cb, mt, _, u in work]
-        else:
-            # independent pairs: nw host threads, each with its own context (own stream, own side
-            # stream); a pair's launches and host glue overlap with the other workers' — the ctypes
-            # calls release the GIL.  Every worker synchronises its context before the step returns,
-            # so the CUDA events that bracket the step on `stream` span all of the work.
-            from concurrent.futures import ThreadPoolExecutor
-            pool = ThreadPoolExecutor(nw)
-            wctx = [api.Context(local) for _ in range(nw)]
-
-            def run_share(k):
-                res = [(i, pipeline.stitch_pair(*work[i][:5], wctx[k], n_nodes=512, gn_iters=4,
-                                                seed=work[i][6]))
-                       for i in range(k, len(work), nw)]
-                wctx[k].sync()
-                return res
-
-            def step():
-                res = [None] * len(work)
-                for part in pool.map(run_share, range(nw)):
-                    for i, o in part:
-                        res[i] = o
-                return res
+        t0 = time.perf_counter()
+        d = api.Deformation(pts, None, faces, ctx)
+        ids = d.SampleFPS(nodes, 0)
+        d.BuildGraph(4, 8)
+        stream.synchronize()
+        t_setup = time.perf_counter() - t0
+        st = d.Stats()
+        m, nnz = st["nodes"], st["pattern_blocks"]
+        per = (n + world - 1) // world
+        d.SetShard(rank * per, min(n, (rank + 1) * per))
+        tgt4 = torch.zeros((nt, 4), dtype=torch.float32, device="cuda")
+        tgt4[:, :3] = torch.from_numpy(tgt).cuda()
+        stream.synchronize()
+        d.SetTargetDev(tgt4.data_ptr(), None, nt)
+        prm = api.gn_params(gn_iters=args.gn_iters, pcg_iters=args.pcg_iters, corr_mode=1)
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
         def barrier():
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
 
-        for _ in range(max(3, args.warmup)):
-            outs = step()
-        ctx.launch_count_reset()
-        if nw > 1:
-            for c in wctx:
-                c.launch_count_reset()
-        clocks = Clocks(local)
-        if rank == 0:
-            clocks.start()
+        for _ in range(3):
+            d.Solve(prm)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-              for _ in range(args.steps)]
+              for _ in range(steps)]
         barrier()
-        for s in range(args.steps):
+        for s in range(steps):
+            flush.fill_(s & 0xFF)
             ev[s][0].record(stream)
-            outs = step()
+            d.Solve(prm)
             ev[s][1].record(stream)
         barrier()
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-        launches = ctx.launch_count() if nw == 1 else sum(c.launch_count() for c in wctx)
-        clk = clocks.stop() if rank == 0 else None
-    # every pair must recover its planted similarity
-    worst = 0.0
-    for o, wk in zip(outs, work):
-        ps, pR, pt = wk[5]
-        worst = max(worst, abs(o["scale"] - ps) / ps, float(np.abs(o["R"] - pR).max()))
-    t = torch.tensor([dev_ms, worst], dtype=torch.float64, device="cuda")
+        # one profiled solve for the per-family times of THIS rank's share
+        ctx.prof_enable(True)
+        ctx.prof_reset()
+        d.Solve(prm)
+        stream.synchronize()
+        prof = ctx.prof()
+        ctx.prof_enable(False)
+        out_dev = d.Vertices()
+        x_dev = d.NodeState()
+        equal = None
+        if world > 1 and rank == 0:
+            ctx1 = api.Context(local, stream.cuda_stream)  # no communicator: the plain one-rank solve
+            d1 = api.Deformation(pts, None, faces, ctx1)
+            d1.SetNodes(ids)
+            d1.BuildGraph(4, 8)
+            d1.SetTargetDev(tgt4.data_ptr(), None, nt)
+            d1.Solve(prm)
+            equal = bool(np.array_equal(d1.Vertices(), out_dev) and np.array_equal(d1.NodeState(), x_dev))
+            d1.close()
+        d.close()
+        del flush, tgt4
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, worst = t[0].item(), t[1].item()
-    if rank == 0:
-        line = {"metric": "view_pairs_per_s", "value": args.pairs * args.steps / (dev_ms * 1e-3),
-                "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-                "config": {"workload": f"C4: {args.pairs} view pairs (two 640x480 depth maps each) sharded "
-                                       "pair -> rank u % N, SRT + deformation + Model2Depth per pair",
-                           "pairs_on_busiest_rank": -(-args.pairs // world), "l2": "host buffers per pair",
-                           "host_workers_per_rank": nw},
-                "max_srt_error_vs_planted": worst, "gpu_launches": int(launches), "clocks": clk}
-        print(json.dumps(line), flush=True)
-    if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    dev_ms = t[0].item()
+    nup = (nnz + m) // 2
+    out = {"metric": METRIC, "value": args.gn_iters * steps / (dev_ms * 1e-3), "unit": UNIT,
+           "n_gpus": world, "steps": steps, "ms_per_step": dev_ms / steps, "scaling": "strong",
+           "verts": n, "target_points": nt, "nodes": m, "pattern_blocks": nnz,
+           "setup_s_untimed": t_setup,
+           "bytes_allreduced_per_gn_iteration": int((nup * 16 + m * 12) * 8) if world > 1 else 0,
+           "shard_bitwise_equal": equal,
+           "families_ms_per_step_rank0": {k: round(v[0], 4) for k, v in
+                                          sorted(prof.items(), key=lambda kv: -kv[1][0])},
+           "workload": f"C5: {n}-vertex mesh, {m}-node graph, vertex ranges sharded over {world} rank(s), "
+                       f"ncclAllReduce(int64) of the upper-triangle J^T J blocks + J^T r per GN iteration, "
+                       f"replicated PCG; {args.gn_iters} GN x {args.pcg_iters} PCG + vertex update"}
+    if with_cpu and rank == 0:
+        import oracle
+        t0 = time.perf_counter()
+        widx, w = oracle.node_weights(pts, pts[ids], 4)
+        graph = oracle.node_graph(pts[ids], 8)
+        t_setup_cpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        _, oo, _ = oracle.gn_solve(pts, None, ids, widx, w, graph,
+                                   oracle.gn_params(gn_iters=args.gn_iters, pcg_iters=args.pcg_iters,
+                                                    corr_mode=1), tpts=tgt)
+        t_cpu = time.perf_counter() - t0
+        diag = float(np.linalg.norm(pts.max(0) - pts.min(0)))
+        out["cpu_baseline"] = {"value": args.gn_iters / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"1 full solve ({t_cpu:.1f} s; node ids taken from the GPU "
+                                         f"sampling, weights/graph setup {t_setup_cpu:.1f} s not counted)",
+                               "max_abs_diff_vs_gpu_over_bbox_diag": float(np.abs(oo - out_dev).max() / diag)}
+    ctx.close()
+    return out
+
+
+# ------------------------------------------------------------------------- remaining kernel rooflines
+def secondary_kernels(args, api, ctx, stream, peak, d, pts, faces):
+    """SURVEY §8(d) lines the headline does not cover: Model2Depth of the benchmarked mesh into a
+    640x480 view (16 B/vertex + 12 B/triangle + 12 B/pixel), RANSAC hypothesis scoring on a full
+    640x480 match set (32 B/match/hypothesis streamed; fp64-compute leaning: ~100 flop per match and
+    hypothesis) and the PCA / bounding-box sweeps of PointSetUtils (24 B/point/pass, doubles)."""
+    import torch
+    from multiviewstitch_b200 import synth
+    out = {}
+    n, nf = len(pts), len(faces)
+    with torch.cuda.stream(stream):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        # ---- Model2Depth
+        K = synth.c1_intrinsics()
+        cam = api.make_camera(K, np.eye(3), np.array([0.0, 0.0, 4.0]), 640, 480)
+        p4 = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+        p4[:, :3] = torch.from_numpy(pts).cuda()
+        f_dev = torch.from_numpy(np.ascontiguousarray(faces, np.int32)).cuda()
+        img = torch.empty((480, 640), dtype=torch.float32, device="cuda")
+        stream.synchronize()
+        best = None
+        for rep in range(4):
+            ev[0].record(stream)
+            api.model2depth_dev(p4.data_ptr(), n, f_dev.data_ptr(), nf, [cam], img.data_ptr(), ctx=ctx)
+            ev[1].record(stream)
+            stream.synchronize()
+            ms = ev[0].elapsed_time(ev[1])
+            best = ms if rep == 1 or (rep > 1 and ms < best) else best  # rep 0 = warm-up
+        b = 16 * n + 12 * nf + 12 * 640 * 480
+        out["model2depth"] = {"verts": n, "facets": nf, "image": "640x480", "ms": best,
+                              "covered_pixels": int((img > 0).sum().item()),
+                              "GBps": b / (best * 1e-3) / 1e9, "frac_hbm": b / (best * 1e-3) / 1e9 / peak,
+                              "bytes_formula": "16 n + 12 F + 12 w h (SURVEY 8(d))",
+                              "note": "includes the camera upload and the image clear of one call"}
+        del p4, f_dev, img
+        # ---- RANSAC scoring
+        nm = 640 * 480
+        (Kc, R1, t1, w, h), (_, R2, t2, _, _) = synth.camera_pair()
+        c1, c2 = api.make_camera(Kc, R1, t1, w, h), api.make_camera(Kc, R2, t2, w, h)
+        pp, qq = synth.planted_pairs(nm, seed=11, noise=1e-3)
+        srt = api.SRTSolver(200, ctx)
+        srt.SetPrintFlag(False)
+        srt.SetInput(pp, qq, c1, c2)
+        srt.EstimateTransformRansac(None, seed=1)
+        ctx.prof_enable(True)
+        ctx.prof_reset()
+        reps = 3
+        for rep in range(reps):
+            srt.EstimateTransformRansac(None, seed=2 + rep)
+        prof = ctx.prof()
+        ctx.prof_enable(False)
+        srt.close()
+        ms = prof.get("srt_residual", (0.0, 0))[0] / reps
+        if ms > 0:
+            hm = 200.0 * nm
+            out["srt_ransac_scoring"] = {"matches": nm, "hypotheses": 200, "ms": ms,
+                                         "hypothesis_matches_per_s": hm / (ms * 1e-3),
+                                         "GBps_streamed_model": 48.0 * hm / (ms * 1e-3) / 1e9,
+                                         "frac_hbm_streamed_model": 48.0 * hm / (ms * 1e-3) / 1e9 / peak,
+                                         "fp64_GFLOPs": 100.0 * hm / (ms * 1e-3) / 1e9,
+                                         "note": "matches are six float64 planes (48 B/match) that stay in "
+                                                 "L2 across the 200 hypotheses; the kernel is fp64-compute "
+                                                 "bound (4 projections = ~100 fp64 flop + 8 divisions per "
+                                                 "match and hypothesis), the GB/s is the streamed-model figure"}
+        # ---- PointSetUtils sweeps
+        np_pts = 4_000_000
+        big = np.random.default_rng(3).normal(size=(np_pts, 3))
+        psu = api.PointSetUtils(ctx)
+        psu.SetInput(big)
+        psu.CalcPivots(3)
+        ctx.prof_enable(True)
+        ctx.prof_reset()
+        psu.SetInput(big)
+        psu.CalcPivots(3)
+        prof = ctx.prof()
+        ctx.prof_enable(False)
+        sweeps = {}
+        for k in ("ps_sum", "ps_bbox", "ps_cov"):
+            if k in prof and prof[k][0] > 0:
+                msk = prof[k][0] / max(prof[k][1], 1)
+                sweeps[k] = {"ms": msk, "GBps": 24.0 * np_pts / (msk * 1e-3) / 1e9,
+                             "frac_hbm": 24.0 * np_pts / (msk * 1e-3) / 1e9 / peak}
+        out["pointset_sweeps"] = {"points": np_pts, "bytes_per_point_per_pass": 24, "kernels": sweeps}
+    return out
 
 
 def run_b200(args):
@@ -537,6 +803,12 @@ def run_b200(args):
     ctx = api.Context(local, stream.cuda_stream)
     shard = args.mode == "shard" and world > 1
 
+    peaks = {}
+    pk_file = ROOT / "MEASURED_PEAKS.json"
+    if pk_file.exists():
+        peaks = json.loads(pk_file.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
     pts, nrm, faces, tgt = workload(args, 0 if (shard or world == 1) else rank)
     n, nt = len(pts), len(tgt)
     if shard:
@@ -544,15 +816,20 @@ def run_b200(args):
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     with torch.cuda.stream(stream):
         d = api.Deformation(pts, nrm, faces, ctx)
         d.SampleFPS(args.nodes, 0)
         d.BuildGraph(4, 8)
         m = len(d.Nodes())
-        rp, col, *_ = d.System()
-        nnz = len(col)
+        st = d.Stats()
+        nnz = st["pattern_blocks"]
         global NRUNS
-        NRUNS = int(d.Stats()["tuple_runs"])
+        NRUNS = int(st["tuple_runs"])
         if shard:
             per = (n + world - 1) // world
             d.SetShard(rank * per, min(n, (rank + 1) * per))
@@ -564,24 +841,11 @@ def run_b200(args):
         prm = api.gn_params(gn_iters=args.gn_iters, pcg_iters=args.pcg_iters, corr_mode=1)
         flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
-        def solve():
-            d.GNBegin(prm)
-            for _ in range(args.gn_iters):
-                d.GNStep()
-            d.GNEnd()
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
         for _ in range(max(3, args.warmup)):
-            solve()
-        # ---- timed: device-resident
+            d.Solve(prm)
+        # ---- timed: device-resident, one library call per step, profiling off
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(args.steps)]
-        ctx.prof_enable(True)
-        ctx.prof_reset()
         ctx.launch_count_reset()
         clocks = Clocks(local)
         if rank == 0:
@@ -591,16 +855,30 @@ def run_b200(args):
         for s in range(args.steps):
             flush.fill_(s & 0xFF)  # L2 flush between timed steps (outside the event pair)
             ev[s][0].record(stream)
-            solve()
+            d.Solve(prm)
             ev[s][1].record(stream)
         barrier()
         t_wall = time.perf_counter() - t_wall0
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         launches = ctx.launch_count()
-        prof = ctx.prof()
-        ctx.prof_enable(False)
         clk = clocks.stop() if rank == 0 else None
         out_dev = d.Vertices()
+        x_dev = d.NodeState()
+
+        # ---- the same K steps again with the per-family event profiling on (families, roofline)
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.steps)]
+        ctx.prof_enable(True)
+        ctx.prof_reset()
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)
+            ev3[s][0].record(stream)
+            d.Solve(prm)
+            ev3[s][1].record(stream)
+        stream.synchronize()
+        prof = ctx.prof()
+        ctx.prof_enable(False)
+        prof_ms = sum(a.elapsed_time(b) for a, b in ev3)
 
         # ---- timed: end to end through the host-buffer C ABI
         e2e_ms = None
@@ -611,8 +889,8 @@ def run_b200(args):
             import ctypes as C
 
             def solve_e2e():
-                d.SetTarget(tgt_h)  # H2D + NN grid build
-                solve()
+                d.SetTarget(tgt_h)  # H2D + NN structure build
+                d.Solve(prm)
                 api.check(api.lib().mvs_deform_get_vertices_f32(
                     d._h, out_h.ctypes.data_as(C.POINTER(C.c_float))))  # D2H
 
@@ -621,8 +899,6 @@ def run_b200(args):
             ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                    for _ in range(args.steps)]
             barrier()
-            ctx.prof_enable(True)
-            ctx.prof_reset()
             for s in range(args.steps):
                 flush.fill_(s & 0xFF)
                 ev2[s][0].record(stream)
@@ -630,11 +906,10 @@ def run_b200(args):
                 ev2[s][1].record(stream)
             barrier()
             e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
-            prof_e2e = ctx.prof()
-            ctx.prof_enable(False)
             # fixed-point block sums: the two legs agree bit for bit
             dg = float(np.linalg.norm(pts.max(0) - pts.min(0)))
             e2e_diff = float(np.abs(out_h - out_dev).max() / dg)
+            d.SetTargetDev(tgt4.data_ptr(), None, nt)
 
     # ---- vertex-sharded mode: the all-reduced solve must carry the bits of the unsharded one
     shard_equal = None
@@ -648,10 +923,9 @@ def run_b200(args):
                 d1.SetTargetDev(tgt4.data_ptr(), None, nt)
                 d1.Solve(prm)
                 shard_equal = bool(np.array_equal(d1.Vertices(), out_dev)
-                                   and np.array_equal(d1.NodeState(), d.NodeState()))
+                                   and np.array_equal(d1.NodeState(), x_dev))
                 d1.close()
-        if world > 1:
-            dist.barrier()
+        dist.barrier()
 
     # ---- max over ranks
     if world > 1:
@@ -663,18 +937,16 @@ def run_b200(args):
     solves_total = args.steps * (1 if shard else world)
     value = args.gn_iters * solves_total / (dev_ms * 1e-3)
 
+    line = None
     if rank == 0:
-        # roofline of the dominant kernel family over the timed region
+        # roofline of the dominant kernel family (profiled pass over the same K steps)
         fam = {k: v for k, v in prof.items() if algo_bytes(k, n, nt, m, nnz, args.pcg_iters)}
         top = max(fam, key=lambda k: fam[k][0])
-        calls = args.steps * args.gn_iters
-        avg_ms = fam[top][0] / calls
-        peaks = {}
-        pk_file = ROOT / "MEASURED_PEAKS.json"
-        if pk_file.exists():
-            peaks = json.loads(pk_file.read_text())
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        n_local = (min(n, (rank + 1) * ((n + world - 1) // world)) - rank * ((n + world - 1) // world)) if shard else n
+        avg_ms = fam[top][0] / max(fam[top][1], 1)
+        n_local = n
+        if shard:
+            per = (n + world - 1) // world
+            n_local = min(n, (rank + 1) * per) - rank * per
         ab = algo_bytes(top, n_local, nt, m, nnz, args.pcg_iters)
         achieved = ab / (avg_ms * 1e-3) / 1e9
         traffic = None
@@ -684,55 +956,57 @@ def run_b200(args):
         roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "algorithmic_bytes_per_launch_group": ab, "avg_ms": avg_ms,
-                    "launches_per_group": 1,
-                    "bytes_formula": ALGO_BYTES_DOC.get(top)}
+                    "algorithmic_bytes_per_launch": ab, "avg_ms": avg_ms,
+                    "launches_timed": int(fam[top][1]),
+                    "bytes_formula": ALGO_BYTES_DOC.get(top),
+                    "measured": "CUDA events inside the library around every launch of the family, "
+                                "profiled pass over the same K steps (the timed pass runs with them off)"}
         families = {}
         for k, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             b = algo_bytes(k, n_local, nt, m, nnz, args.pcg_iters)
-            per = ms / calls if k.startswith(("gn_", "pcg_")) else ms / args.steps
-            families[k] = {"ms_per_step": ms / args.steps, "launches": cnt,
-                           "share": ms / dev_ms if world == 1 or True else None}
-            if b:
-                families[k]["GBps"] = b / (per * 1e-3) / 1e9
+            families[k] = {"ms_per_step": ms / args.steps, "launches": cnt, "share": ms / prof_ms}
+            if b and cnt:
+                families[k]["GBps"] = b / (ms / cnt * 1e-3) / 1e9
                 families[k]["frac_hbm"] = families[k]["GBps"] / peak
 
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            t_setup, t_solve, out_cpu, graph_parts = cpu_solve(args, pts, tgt, args.ref_gn_iters)
+            ref_it = args.ref_gn_iters if args.ref_gn_iters > 0 else args.gn_iters
+            t_setup, t_solve, out_cpu, graph_parts = cpu_solve(args, pts, tgt, ref_it)
             diag = float(np.linalg.norm(pts.max(0) - pts.min(0)))
-            cpu = {"value": args.ref_gn_iters / t_solve, "unit": UNIT, "cores": 1, "kind": "port",
+            cpu = {"value": ref_it / t_solve, "unit": UNIT, "cores": 1, "kind": "port",
                    "host_cores": os.cpu_count(),
-                   "sample": f"1 solve of {args.ref_gn_iters} GN x {args.pcg_iters} PCG iterations on the "
+                   "sample": f"1 solve of {ref_it} GN x {args.pcg_iters} PCG iterations on the "
                              f"full workload ({t_solve:.1f} s; graph setup {t_setup:.1f} s not counted)"}
-            if args.ref_gn_iters == args.gn_iters:
+            if ref_it == args.gn_iters:
                 cpu["max_abs_diff_vs_gpu_over_bbox_diag"] = float(np.abs(out_cpu - out_dev).max() / diag)
             try:
-                cpu["openmp_courtesy"] = cpu_solve_openmp(args, pts, tgt, args.ref_gn_iters, graph_parts)
+                cpu["openmp_courtesy"] = cpu_solve_openmp(args, pts, tgt, ref_it, graph_parts)
             except Exception as exc:  # never lose the headline line over the courtesy number
                 cpu["openmp_courtesy"] = {"error": repr(exc)}
 
-        secondary = None
+        secondary = {}
         if not args.no_secondary and world == 1:
             try:
-                secondary = secondary_c2(args, api, ctx, stream, peak)
+                secondary.update(secondary_c2(args, api, ctx, stream, peak))
             except Exception as exc:  # the headline line must still be printed
-                secondary = {"error": repr(exc)}
+                secondary["c2_error"] = repr(exc)
             try:
                 secondary["arap"] = secondary_arap(args, api, ctx, stream, peak, d, pts, faces)
             except Exception as exc:
                 secondary["arap"] = {"error": repr(exc)}
+            try:
+                secondary["kernels"] = secondary_kernels(args, api, ctx, stream, peak, d, pts, faces)
+            except Exception as exc:
+                secondary["kernels"] = {"error": repr(exc)}
 
+        cfg = base_config(args, n, nt)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "strong" if shard else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args, n), "verts": n, "target_points": nt,
-                           "nodes": m, "pattern_blocks": nnz, "tuple_runs": d.Stats()["tuple_runs"],
-                           "mode": args.mode,
-                           "step": f"one {args.gn_iters}-iteration solve",
-                           "l2": "512 MiB flush write between timed steps; per-iteration working "
-                                 "set ~100 MB"},
+                "config": cfg,
+                "graph": {"pattern_blocks": nnz, "tuple_runs": st["tuple_runs"]},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": None if e2e_ms is None else {
                     "value": args.gn_iters * args.steps * world / (e2e_ms * 1e-3), "unit": UNIT,
@@ -740,11 +1014,34 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(nt * 12), "d2h_bytes_per_step": int(n * 12),
                     "max_abs_diff_vs_resident_over_bbox_diag": e2e_diff},
                 "gpu_launches": int(launches), "clocks": clk,
-                "wall_s_timed_region": t_wall, "secondary": secondary, "families": families,
-                "shard_bitwise_equal": shard_equal,
-                "e2e_families_ms_per_step": None if e2e_ms is None else {
-                    k: round(v[0] / args.steps, 4) for k, v in
-                    sorted(prof_e2e.items(), key=lambda kv: -kv[1][0])}}
+                "wall_s_timed_region": t_wall, "profiled_pass_ms_per_step": prof_ms / args.steps,
+                "secondary": secondary, "families": families,
+                "shard_bitwise_equal": shard_equal}
+
+    # ---- release the headline workload before the two partitions
+    with torch.cuda.stream(stream):
+        d.close()
+        del tgt4, flush
+    torch.cuda.empty_cache()
+
+    # ---- north_star's partitions, at every N (secondary.c4_pairs, secondary.c5_shard)
+    if not args.no_secondary and args.mode == "objects":
+        c4 = c5 = None
+        if not args.no_c4:
+            try:
+                c4 = c4_pairs(args, api, ctx, stream, world, rank, dist, 3, 3)
+            except Exception as exc:
+                c4 = {"error": repr(exc)}
+        if not args.no_c5:
+            try:
+                c5 = c5_shard(args, api, local, stream, world, rank, dist, peak, args.c5_side,
+                              args.c5_nodes, args.c5_steps, with_cpu=args.c5_cpu)
+            except Exception as exc:
+                c5 = {"error": repr(exc)}
+        if rank == 0:
+            line["secondary"]["c4_pairs"] = c4
+            line["secondary"]["c5_shard"] = c5
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -379,6 +379,54 @@ int mvs_unproject_pixels(mvs_ctx* ctx, const float* inv_depth, const mvs_camera*
                          double max_dsp, const int32_t* uv, int64_t n, double* out_xyz,
                          int32_t* valid);
 
+/* ---------------------------------------------------------------- view pairs ---------------- */
+/* The hot path of a list of INDEPENDENT view pairs in one call — what Processor runs per pair
+ * [ref: Processor/Processor.cpp:629-826 `for k` pair loop; per pair :751-765 RemoveOutliers,
+ * :806-823 SRTSolver::EstimateTransform + ResidualError + chain, :1025-1026 apply, :1130-1137
+ * Deformation, :1190-1191 Model2Depth]:
+ *   matched pixels -> unprojected matches -> RemoveOutliers -> closed-form SRT + residual ->
+ *   Depth2Model mesh of view A moved by (s, R, t) -> deformation-graph Gauss-Newton onto the valid
+ *   points of view B -> Model2Depth of the deformed mesh into camera B.
+ * Inputs are caller-owned HOST buffers (the reference reads the depth maps from disk); optional
+ * outputs are caller-owned host buffers that may be NULL.  The pairs are worked through by
+ * `workers` host threads of the library, each with its own stream, so one pair's host glue
+ * overlaps the others' kernels; results do not depend on the worker count. */
+typedef struct mvs_pair_job {
+  const float* depth_a;      /* w*h inverse depths of view A (the template view) */
+  const mvs_camera* cam_a;
+  const float* depth_b;      /* w*h inverse depths of view B (the target view) */
+  const mvs_camera* cam_b;
+  const int32_t* matches;    /* n_matches x 4 pixel pairs (u_a, v_a, u_b, v_b) */
+  int64_t n_matches;
+  uint64_t seed;             /* RANSAC sample seed of this pair */
+  /* optional outputs (NULL = not wanted) */
+  int32_t* kept_idx;         /* capacity n_matches: indices of the surviving matches */
+  double* template_xyz;      /* capacity w*h*3: view-A mesh vertices in the frame of view B */
+  int32_t* facets;           /* capacity 6*(w-1)*(h-1) */
+  double* deformed_xyz;      /* capacity w*h*3: deformed vertices */
+  float* render;             /* w*h: Model2Depth of the deformed mesh in camera B */
+} mvs_pair_job;
+typedef struct mvs_pair_params {
+  double min_dsp, max_dsp;       /* config.txt:23-24 (0.0025, 0.3) */
+  double smooth_threshold;       /* config.txt:38 (0.12) */
+  mvs_outlier_params outliers;   /* seed is taken from the job */
+  int64_t n_nodes;               /* deformation-graph nodes (farthest point sampling), 512 */
+  mvs_gn_params gn;              /* corr_mode 1, 4 GN x 20 PCG by default */
+  int32_t workers;               /* host threads; 0 = min(8, hardware threads / 2) */
+  int32_t reserved;
+} mvs_pair_params;
+typedef struct mvs_pair_result {
+  int32_t status;                /* MVS_OK or the error of this pair */
+  int32_t reserved;
+  double scale, R[9], t[3];      /* x_B = s R x_A + t */
+  double err;                    /* RemoveOutliers' err_all / size of the last round */
+  double residual;               /* SRTSolver::ResidualError at (s, R, t) */
+  int64_t n_kept, n_template, n_facets, n_target;
+} mvs_pair_result;
+int mvs_pair_default_params(mvs_pair_params* p);
+int mvs_stitch_pairs(mvs_ctx* ctx, const mvs_pair_job* jobs, int64_t n_jobs,
+                     const mvs_pair_params* params, mvs_pair_result* results);
+
 /* ---------------------------------------------------------------- multi-GPU ---------------- */
 /* One process per GPU. id: 128-byte NCCL unique id produced on rank 0 and broadcast by the
  * caller's launcher (torch.distributed / MPI / file). */

@@ -57,6 +57,29 @@ class ArapParams(C.Structure):
                 ("cg_tol", C.c_double)]
 
 
+class PairJob(C.Structure):
+    """mvs_pair_job [ref: Processor/Processor.cpp:629-826 one iteration of the pair loop]"""
+    _fields_ = [("depth_a", C.POINTER(C.c_float)), ("cam_a", C.POINTER(Camera)),
+                ("depth_b", C.POINTER(C.c_float)), ("cam_b", C.POINTER(Camera)),
+                ("matches", C.POINTER(C.c_int32)), ("n_matches", C.c_int64), ("seed", C.c_uint64),
+                ("kept_idx", C.POINTER(C.c_int32)), ("template_xyz", C.POINTER(C.c_double)),
+                ("facets", C.POINTER(C.c_int32)), ("deformed_xyz", C.POINTER(C.c_double)),
+                ("render", C.POINTER(C.c_float))]
+
+
+class PairParams(C.Structure):
+    _fields_ = [("min_dsp", C.c_double), ("max_dsp", C.c_double), ("smooth_threshold", C.c_double),
+                ("outliers", OutlierParams), ("n_nodes", C.c_int64), ("gn", GNParams),
+                ("workers", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PairResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("reserved", C.c_int32), ("scale", C.c_double),
+                ("R", C.c_double * 9), ("t", C.c_double * 3), ("err", C.c_double),
+                ("residual", C.c_double), ("n_kept", C.c_int64), ("n_template", C.c_int64),
+                ("n_facets", C.c_int64), ("n_target", C.c_int64)]
+
+
 def declared_symbols() -> list[str]:
     """Every function the header declares (used by the symbol-export test)."""
     txt = HEADER.read_text()

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from ._capi import (AlignParams, ArapParams, Camera, GNParams, MvsError, OutlierParams,  # noqa: F401
-                    check, lib)
+                    PairJob, PairParams, PairResult, check, lib)
 
 
 def _f32(a):
@@ -856,3 +856,77 @@ def unproject_depth(inv_depth, cam: Camera, min_dsp: float, max_dsp: float,
                                     C.c_double(min_dsp), C.c_double(max_dsp),
                                     _ptr(out, C.c_double), _ptr(valid, C.c_int32)))
     return out, valid
+
+
+# ============================================================================ view pairs
+def pair_params(**kw) -> PairParams:
+    """mvs_pair_params with the library defaults (config.txt values), overridden by keyword;
+    `gn` and `outliers` take the nested structures, gn_iters / pcg_iters / iter_num / pixel_err /
+    adapt_ratio are shortcuts into them."""
+    p = PairParams()
+    check(lib().mvs_pair_default_params(C.byref(p)))
+    for k, v in kw.items():
+        if k in ("gn_iters", "pcg_iters"):
+            setattr(p.gn, k, v)
+        elif k in ("iter_num", "pixel_err", "adapt_ratio", "rounds"):
+            setattr(p.outliers, k, v)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+class PairBatch:
+    """A list of independent view pairs for mvs_stitch_pairs [ref: Processor/Processor.cpp:629-826].
+    add() keeps the host arrays alive; run() is ONE library call for all pairs."""
+
+    def __init__(self, ctx: Context | None = None, want_outputs: bool = True):
+        self._ctx = ctx
+        self._jobs = []
+        self._keep = []
+        self._out = []
+        self.want_outputs = want_outputs
+
+    def add(self, depth_a, cam_a: Camera, depth_b, cam_b: Camera, matches, seed: int = 0):
+        da = _f32(depth_a).reshape(-1)
+        db = _f32(depth_b).reshape(-1)
+        mt = _i32(matches).reshape(-1, 4)
+        npx = cam_a.w * cam_a.h
+        j = PairJob()
+        j.depth_a, j.cam_a = _ptr(da, C.c_float), C.pointer(cam_a)
+        j.depth_b, j.cam_b = _ptr(db, C.c_float), C.pointer(cam_b)
+        j.matches, j.n_matches, j.seed = _ptr(mt, C.c_int32), len(mt), seed
+        o = None
+        if self.want_outputs:
+            o = dict(kept=np.empty(len(mt), np.int32), template=np.empty((npx, 3), np.float64),
+                     facets=np.empty((2 * (cam_a.w - 1) * (cam_a.h - 1), 3), np.int32),
+                     deformed=np.empty((npx, 3), np.float64), render=np.empty(npx, np.float32))
+            j.kept_idx = _ptr(o["kept"], C.c_int32)
+            j.template_xyz = _ptr(o["template"], C.c_double)
+            j.facets = _ptr(o["facets"], C.c_int32)
+            j.deformed_xyz = _ptr(o["deformed"], C.c_double)
+            j.render = _ptr(o["render"], C.c_float)
+        self._jobs.append(j)
+        self._keep.append((da, db, mt, cam_a, cam_b))
+        self._out.append(o)
+
+    def __len__(self):
+        return len(self._jobs)
+
+    def run(self, params: PairParams | None = None):
+        n = len(self._jobs)
+        jobs = (PairJob * n)(*self._jobs)
+        res = (PairResult * n)()
+        prm = params if params is not None else pair_params()
+        check(lib().mvs_stitch_pairs(_ctxh(self._ctx), jobs, C.c_int64(n), C.byref(prm), res))
+        outs = []
+        for r, o, k in zip(res, self._out, self._keep):
+            d = dict(scale=r.scale, R=np.array(r.R[:]).reshape(3, 3), t=np.array(r.t[:]), err=r.err,
+                     residual=r.residual, n_kept=r.n_kept, n_template=r.n_template,
+                     n_facets=r.n_facets, n_target=r.n_target)
+            if o is not None:
+                cam = k[3]
+                d.update(kept=o["kept"][:r.n_kept], template=o["template"][:r.n_template],
+                         facets=o["facets"][:r.n_facets], deformed=o["deformed"][:r.n_template],
+                         render=o["render"].reshape(cam.h, cam.w))
+            outs.append(d)
+        return outs

@@ -194,7 +194,10 @@ void ctx_retain(mvs_ctx* ctx) {
   std::lock_guard<std::mutex> lk(g_ref_mu);
   ++ctx->refs;
 }
+void stitch_pool_release(mvs_ctx* parent);  // stitch.cu: worker contexts of mvs_stitch_pairs
+
 static void ctx_free(mvs_ctx* ctx) {
+  stitch_pool_release(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   mvs_comm_destroy(ctx);

@@ -1,0 +1,286 @@
+// stitch.cu — mvs_stitch_pairs: the hot path of a list of independent view pairs in ONE library
+// call (the reference's independent `for k` pair loop, Processor/Processor.cpp:
+// 629-826, and per pair the sequence :751-765 RemoveOutliers, :806-823 SRTSolver, :1025-1026 apply,
+// :1130-1137 Deformation, :1190-1191 Model2Depth).
+//
+// Host side only: a pool of worker threads, each with its OWN context (own stream, side stream,
+// stream-ordered allocation pool, pinned staging), works through the jobs k, k + W, k + 2W, ...
+// Pairs are independent, so one pair's host glue and stream synchronisations overlap the other
+// workers' kernels; nothing here is Python, so no interpreter lock serialises the glue.  Every
+// worker context lives as long as the parent context (created once, reused by later calls).
+//
+// Per pair, in the reference's call order:
+//   matched pixels --unproject--> p, q                      [Camera/Camera.cpp:40-44,61-67]
+//   RemoveOutliers (rounds x RANSAC + symmetric inlier test) [Processor/Processor.cpp:177-269]
+//   SRTSolver::EstimateTransform + ResidualError             [Processor/Processor.cpp:814-818]
+//   Depth2Model mesh of view 1, s R p + t into frame 2       [Depth2Model.cpp:7-82, Processor.cpp:1025]
+//   Deformation onto the unprojected view-2 points (GN)      [Processor/Processor.cpp:1135-1137]
+//   Model2Depth of the deformed mesh into camera 2           [Processor/Processor.cpp:1190-1191]
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <thread>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace mvs {
+
+struct StitchPool {
+  std::mutex mu;
+  std::vector<mvs_ctx*> workers;
+};
+
+static std::mutex g_pools_mu;
+static std::map<mvs_ctx*, StitchPool*> g_pools;
+
+static StitchPool* pool_for(mvs_ctx* parent) {
+  std::lock_guard<std::mutex> lk(g_pools_mu);
+  auto it = g_pools.find(parent);
+  if (it != g_pools.end()) return it->second;
+  StitchPool* p = new StitchPool();
+  g_pools[parent] = p;
+  return p;
+}
+
+// called by mvs_ctx_destroy of the parent
+void stitch_pool_release(mvs_ctx* parent) {
+  StitchPool* p = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_pools_mu);
+    auto it = g_pools.find(parent);
+    if (it == g_pools.end()) return;
+    p = it->second;
+    g_pools.erase(it);
+  }
+  for (mvs_ctx* w : p->workers) mvs_ctx_destroy(w);
+  delete p;
+}
+
+// wall-clock stage accounting of a worker (MVS_STITCH_TRACE=1 prints the sums per call to stderr)
+enum { ST_UNPROJ, ST_OUTLIERS, ST_SRT, ST_D2M, ST_APPLY, ST_CREATE, ST_FPS, ST_TARGET, ST_SOLVE,
+       ST_GET, ST_RENDER, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"unproject", "remove_outliers", "srt", "depth2model",
+                                            "apply_srt", "deform_create", "sample_fps", "set_target",
+                                            "solve(graph+gn)", "get_vertices", "model2depth"};
+struct StageClock {
+  double* acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageClock(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  void lap(int stage) {
+    auto t1 = std::chrono::steady_clock::now();
+    if (acc) acc[stage] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+};
+
+static int run_pair(mvs_ctx* ctx, const mvs_pair_job& job, const mvs_pair_params& prm,
+                    mvs_pair_result& out, double* stage_ms) {
+  StageClock clk(stage_ms);
+  const mvs_camera* ca = job.cam_a;
+  const mvs_camera* cb = job.cam_b;
+  const int64_t nm = job.n_matches;
+  const int64_t npx = (int64_t)ca->w * ca->h;
+  out.status = MVS_OK;
+  out.n_kept = out.n_template = out.n_facets = out.n_target = 0;
+  // ---- matched pixels -> 3-D matches
+  std::vector<int32_t> uv((size_t)nm * 2);
+  std::vector<double> p((size_t)nm * 3), q((size_t)nm * 3);
+  std::vector<int32_t> okf((size_t)nm);
+  for (int64_t i = 0; i < nm; ++i) {
+    uv[2 * i] = job.matches[4 * i];
+    uv[2 * i + 1] = job.matches[4 * i + 1];
+  }
+  MVS_TRY(mvs_unproject_pixels(ctx, job.depth_a, ca, prm.min_dsp, prm.max_dsp, uv.data(), nm,
+                               p.data(), okf.data()));
+  for (int64_t i = 0; i < nm; ++i) {
+    uv[2 * i] = job.matches[4 * i + 2];
+    uv[2 * i + 1] = job.matches[4 * i + 3];
+  }
+  MVS_TRY(mvs_unproject_pixels(ctx, job.depth_b, cb, prm.min_dsp, prm.max_dsp, uv.data(), nm,
+                               q.data(), okf.data()));
+  clk.lap(ST_UNPROJ);
+  // ---- RemoveOutliers
+  std::vector<int32_t> keep((size_t)nm);
+  int64_t nk = 0;
+  mvs_outlier_params op = prm.outliers;
+  op.seed = job.seed;
+  MVS_TRY(mvs_remove_outliers(ctx, p.data(), q.data(), nm, ca, cb, &op, keep.data(), &nk, &out.err,
+                              nullptr));
+  out.n_kept = nk;
+  clk.lap(ST_OUTLIERS);
+  if (job.kept_idx) memcpy(job.kept_idx, keep.data(), sizeof(int32_t) * (size_t)nk);
+  if (nk < 3) {
+    set_error("stitch_pairs: fewer than 3 matches survive RemoveOutliers");
+    return MVS_ERR_DEGENERATE;
+  }
+  // ---- closed-form SRT on the inliers + residual
+  std::vector<double> pk((size_t)nk * 3), qk((size_t)nk * 3);
+  for (int64_t i = 0; i < nk; ++i) {
+    memcpy(&pk[3 * i], &p[3 * (size_t)keep[i]], sizeof(double) * 3);
+    memcpy(&qk[3 * i], &q[3 * (size_t)keep[i]], sizeof(double) * 3);
+  }
+  {
+    mvs_srt* s = nullptr;
+    MVS_TRY(mvs_srt_create(ctx, &s));
+    int rc = mvs_srt_set_iteration_num(s, op.iter_num);
+    if (rc == MVS_OK) rc = mvs_srt_set_print(s, 0);
+    if (rc == MVS_OK) rc = mvs_srt_set_input(s, pk.data(), qk.data(), nk, ca, cb);
+    if (rc == MVS_OK) rc = mvs_srt_estimate(s, &out.scale, out.R, out.t);
+    if (rc == MVS_OK) rc = mvs_srt_residual(s, out.scale, out.R, out.t, &out.residual);
+    mvs_srt_destroy(s);
+    MVS_TRY(rc);
+  }
+  clk.lap(ST_SRT);
+  // ---- template = view-1 mesh, moved into the frame of view 2
+  int64_t np = 0, nf = 0;
+  std::vector<double> va((size_t)npx * 3);
+  std::vector<int32_t> fa((size_t)6 * (ca->w - 1) * (ca->h - 1));
+  MVS_TRY(mvs_depth2model(ctx, job.depth_a, ca, prm.min_dsp, prm.max_dsp, prm.smooth_threshold,
+                          va.data(), nullptr, fa.data(), &np, &nf));
+  clk.lap(ST_D2M);
+  out.n_template = np;
+  out.n_facets = nf;
+  if (np <= 0) {
+    set_error("stitch_pairs: view 1 has no valid depth");
+    return MVS_ERR_DEGENERATE;
+  }
+  MVS_TRY(mvs_apply_srt(ctx, va.data(), nullptr, np, out.scale, out.R, out.t));
+  clk.lap(ST_APPLY);
+  if (job.template_xyz) memcpy(job.template_xyz, va.data(), sizeof(double) * 3 * (size_t)np);
+  if (job.facets) memcpy(job.facets, fa.data(), sizeof(int32_t) * 3 * (size_t)nf);
+  // ---- deformation onto view 2
+  mvs_deform* d = nullptr;
+  MVS_TRY(mvs_deform_create(ctx, va.data(), nullptr, np, fa.data(), nf, &d));
+  clk.lap(ST_CREATE);
+  int rc = mvs_deform_sample_fps(d, std::min<int64_t>(prm.n_nodes, np), 0);
+  clk.lap(ST_FPS);
+  if (rc == MVS_OK)
+    rc = mvs_deform_set_target_depth(d, job.depth_b, cb, prm.min_dsp, prm.max_dsp, &out.n_target);
+  clk.lap(ST_TARGET);
+  if (rc == MVS_OK) rc = mvs_deform_solve(d, &prm.gn);
+  clk.lap(ST_SOLVE);
+  if (rc == MVS_OK) rc = mvs_deform_get_vertices(d, va.data());
+  mvs_deform_destroy(d);
+  MVS_TRY(rc);
+  clk.lap(ST_GET);
+  if (job.deformed_xyz) memcpy(job.deformed_xyz, va.data(), sizeof(double) * 3 * (size_t)np);
+  // ---- re-projection of the deformed mesh into camera 2
+  if (job.render)
+    MVS_TRY(mvs_model2depth_f64(ctx, va.data(), np, fa.data(), nf, cb, 1, 0.f, 0.f, job.render));
+  clk.lap(ST_RENDER);
+  return MVS_OK;
+}
+
+}  // namespace mvs
+
+using namespace mvs;
+
+extern "C" {
+
+int mvs_pair_default_params(mvs_pair_params* p) {
+  if (!p) return MVS_ERR_INVALID_ARG;
+  p->min_dsp = 0.0025;         // config.txt:23
+  p->max_dsp = 0.3;            // config.txt:24
+  p->smooth_threshold = 0.12;  // config.txt:38
+  mvs_outlier_default_params(&p->outliers);
+  p->outliers.pixel_err = 60.0;    // config.txt
+  p->outliers.adapt_ratio = 0.75;  // config.txt
+  p->n_nodes = 512;
+  mvs_gn_default_params(&p->gn);
+  p->gn.gn_iters = 4;
+  p->gn.corr_mode = 1;
+  p->workers = 0;
+  return MVS_OK;
+}
+
+int mvs_stitch_pairs(mvs_ctx* ctx, const mvs_pair_job* jobs, int64_t n_jobs,
+                     const mvs_pair_params* params, mvs_pair_result* results) {
+  if (!ctx) ctx = default_ctx();
+  if (!ctx) return MVS_ERR_NO_DEVICE;
+  MVS_TRY(ctx_ensure_device(ctx));
+  if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !results))) {
+    set_error("stitch_pairs: bad argument");
+    return MVS_ERR_INVALID_ARG;
+  }
+  mvs_pair_params def;
+  if (!params) {
+    mvs_pair_default_params(&def);
+    params = &def;
+  }
+  for (int64_t i = 0; i < n_jobs; ++i) {
+    const mvs_pair_job& j = jobs[i];
+    if (!j.depth_a || !j.depth_b || !j.cam_a || !j.cam_b || j.n_matches < 0 ||
+        (j.n_matches > 0 && !j.matches) || j.cam_a->w <= 1 || j.cam_a->h <= 1 ||
+        j.cam_b->w != j.cam_a->w || j.cam_b->h != j.cam_a->h) {
+      set_error("stitch_pairs: job %lld is malformed", (long long)i);
+      return MVS_ERR_INVALID_ARG;
+    }
+  }
+  if (n_jobs == 0) return MVS_OK;
+  int want = params->workers > 0 ? params->workers
+                                 : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+  int W = (int)std::min<int64_t>(std::max(1, want), n_jobs);
+  StitchPool* pool = pool_for(ctx);
+  std::lock_guard<std::mutex> lk(pool->mu);  // one stitch call per parent context at a time
+  while ((int)pool->workers.size() < W) {
+    mvs_ctx* w = nullptr;
+    MVS_TRY(mvs_ctx_create(&w, ctx->device, nullptr));
+    pool->workers.push_back(w);
+  }
+  // the workers start after everything already queued on the parent's stream
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::atomic<int64_t> next{0};
+  std::vector<std::string> errs((size_t)W);
+  std::vector<int64_t> launches((size_t)W, 0);
+  const char* trace_env = getenv("MVS_STITCH_TRACE");
+  const bool trace = trace_env && trace_env[0] == '1';
+  std::vector<double> stage_ms(trace ? (size_t)W * ST_COUNT : 0, 0.0);
+  auto body = [&](int k) {
+    mvs_ctx* w = pool->workers[k];
+    if (ctx_ensure_device(w) != MVS_OK) return;
+    int64_t before = w->launch_count;
+    for (;;) {
+      int64_t i = next.fetch_add(1);
+      if (i >= n_jobs) break;
+      int rc = run_pair(w, jobs[i], *params, results[i], trace ? &stage_ms[(size_t)k * ST_COUNT] : nullptr);
+      results[i].status = rc;
+      if (rc != MVS_OK && errs[k].empty()) errs[k] = mvs_last_error();
+    }
+    cudaStreamSynchronize(w->stream);
+    launches[k] = w->launch_count - before;
+  };
+  if (W == 1) {
+    body(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int k = 0; k < W; ++k) th.emplace_back(body, k);
+    for (auto& t : th) t.join();
+  }
+  MVS_TRY(ctx_ensure_device(ctx));
+  if (trace) {
+    fprintf(stderr, "[mvs_stitch_pairs] %lld pairs, %d workers, ms per pair (wall, per worker thread):",
+            (long long)n_jobs, W);
+    for (int s = 0; s < ST_COUNT; ++s) {
+      double sum = 0;
+      for (int k = 0; k < W; ++k) sum += stage_ms[(size_t)k * ST_COUNT + s];
+      fprintf(stderr, " %s %.3f", kStageNames[s], sum / (double)n_jobs);
+    }
+    fprintf(stderr, "\n");
+  }
+  for (int k = 0; k < W; ++k) ctx->launch_count += launches[k];  // the call's launches, on the caller's context
+  for (int64_t i = 0; i < n_jobs; ++i)
+    if (results[i].status != MVS_OK) {
+      for (int k = 0; k < W; ++k)
+        if (!errs[k].empty()) {
+          set_error("stitch_pairs: pair %lld failed: %s", (long long)i, errs[k].c_str());
+          break;
+        }
+      return results[i].status;
+    }
+  return MVS_OK;
+}
+
+}  // extern "C"

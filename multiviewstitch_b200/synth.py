@@ -208,8 +208,9 @@ def cube_sphere(n, radius=1.0, bumps=0.05, rot=None):
     P = np.concatenate(pts, 0)
     F = np.concatenate(quads, 0)
     # weld the duplicated edge / corner vertices (exact grid positions: round to a fine lattice)
-    key = np.round(P * (1 << 20)).astype(np.int64)
-    _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    key = np.round(P * (1 << 20)).astype(np.int64) + (1 << 20)  # three 21-bit lattice coordinates
+    key = (key[:, 0] << 42) | (key[:, 1] << 21) | key[:, 2]      # packed: a 1-D unique is ~10x faster
+    _, first, inv = np.unique(key, return_index=True, return_inverse=True)
     order = np.argsort(first)               # keep the original vertex order (face-major)
     rank = np.empty_like(order)
     rank[order] = np.arange(len(order))

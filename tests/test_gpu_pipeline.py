@@ -158,3 +158,45 @@ def test_two_view_pair_end_to_end(ctx):
 def MINMAX(d):
     v = d[d > 0]
     return v.min() >= pipeline.MIN_DSP and v.max() <= pipeline.MAX_DSP
+
+
+def _pair_inputs(ctx, u, side=48):
+    sc = pipeline.make_scene(side=side, view_angle_deg=10.0 + 1.5 * u, seed=0)
+    ca, cb = api.make_camera(*sc["cam_a"]), api.make_camera(*sc["cam_b"])
+    m2d = api.Model2Depth(ctx)
+    m2d.SetInput([sc["verts_a"], sc["verts_b"]], [None, None], [sc["faces"], sc["faces"]], [[ca], [cb]])
+    da, db = m2d.render(0)[0], m2d.render(1)[0]
+    pa, va = api.unproject_depth(da, ca, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
+    pb, vb = api.unproject_depth(db, cb, pipeline.MIN_DSP, pipeline.MAX_DSP, ctx)
+    mt = pipeline.lattice_matches(pa, va, sc["cam_b"], vb, sc["planted"], 640, 480, seed=u)
+    return da, ca, db, cb, mt, sc["planted"]
+
+
+@pytest.mark.parametrize("workers", [1, 3])
+def test_stitch_pairs_one_call_equals_stage_by_stage(ctx, workers):
+    """mvs_stitch_pairs (Processor.cpp:629-826): all pairs in ONE library call, worked
+    through by library threads with their own streams — every output carries the bits of the
+    stage-by-stage sequence (itself checked against the oracle above), for any worker count."""
+    pairs = [_pair_inputs(ctx, u) for u in range(4)]
+    batch = api.PairBatch(ctx)
+    for u, (da, ca, db, cb, mt, _) in enumerate(pairs):
+        batch.add(da, ca, db, cb, mt, seed=u)
+    outs = batch.run(api.pair_params(n_nodes=200, gn_iters=3, workers=workers))
+    for u, ((da, ca, db, cb, mt, planted), o) in enumerate(zip(pairs, outs)):
+        ref = pipeline.stitch_pair(da, ca, db, cb, mt, ctx, n_nodes=200, gn_iters=3, seed=u)
+        assert o["scale"] == ref["scale"] and np.array_equal(o["R"], ref["R"])
+        assert np.array_equal(o["t"], ref["t"]) and np.array_equal(o["kept"], ref["kept"])
+        assert o["err"] == ref["err"] and o["residual"] == ref["residual"]
+        assert np.array_equal(o["facets"], ref["facets"])
+        assert np.array_equal(o["template"], ref["template"])
+        assert np.array_equal(o["deformed"], ref["deformed"])
+        assert np.array_equal(o["render"], ref["render"])
+        assert o["n_target"] == int((db > 0).sum())
+        ps, pR, _ = planted
+        assert abs(o["scale"] - ps) < 2e-2 * ps and np.abs(o["R"] - pR).max() < 2e-2
+    # a malformed job is an error code, not a crash
+    bad = api.PairBatch(ctx)
+    da, ca, db, cb, mt, _ = pairs[0]
+    bad.add(np.zeros_like(da), ca, db, cb, mt)
+    with pytest.raises(_capi.MvsError):
+        bad.run(api.pair_params(workers=1))
