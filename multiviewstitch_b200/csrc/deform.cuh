@@ -55,7 +55,7 @@ struct mvs_deform {
   std::vector<int> h_row_ptr;  // host copy of row_ptr (solver launch planning)
   std::vector<int> h_grp_start;  // first sorted vertex of every assembly group, then n
   bool pcg_plan_valid = false;
-  int pcg_rs = 1, pcg_grid = 0, pcg_stage = 0;
+  int pcg_rs = 1, pcg_grid = 0, pcg_stage = 0, pcg_threads = 256;
   size_t pcg_smem = 0;
   mvs::DevBuf<float> sys;
   // order-independent accumulation: J^T J / J^T r are summed as 64-bit fixed point (integer atomics

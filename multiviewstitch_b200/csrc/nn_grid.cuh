@@ -171,8 +171,16 @@ constexpr float kPyrFirstRadius = 0.75f;
 // fastest with ~3 (C2: 2.22 ms at 3, 2.29 at 2, 2.31 at 4.5); the deformation target, whose first
 // iteration queries from up to 5 % of the diagonal away, with ~6 (C3 correspondence passes of one
 // solve: 2.82 ms at 3, 2.60 at 4.5, 2.52 at 6, 2.72 at 8, 2.63 at 12).
+// search radius, in cells, above which a walk consults the oriented slab records
+#ifndef MVS_PYR_SLAB_R
+#define MVS_PYR_SLAB_R 1.5f
+#endif
+constexpr float kPyrSlabRadius = MVS_PYR_SLAB_R;
 constexpr float kPyrPpcNear = 3.0f;
-constexpr float kPyrPpcFar = 6.0f;
+#ifndef MVS_PYR_PPC_FAR
+#define MVS_PYR_PPC_FAR 6.0f
+#endif
+constexpr float kPyrPpcFar = MVS_PYR_PPC_FAR;
 
 // sparse occupancy pyramid (nn_pyramid.cuh)
 struct PyrParams {
@@ -188,6 +196,11 @@ struct PyrParams {
   const int* occ_start;
   const float4* pts;
   int64_t n;
+  // oriented slab bounds (nn_pyramid.cuh: slab_d2): two float4 per record, {unit normal, lateral
+  // radius} {centre, half thickness}.  cslab[2 oi] bounds the points of occupied cell oi; bslab[2 oi]
+  // bounds ALL points of the brick whose first occupied cell is oi.  Null = boxes only.
+  const float4* cslab;
+  const float4* bslab;
 };
 
 }  // namespace mvs
@@ -220,7 +233,7 @@ struct mvs_nn_index {
   mvs::DevBuf<unsigned long long> pyr_keys, pyr_keys2, pyr_m2, pyr_m3, pyr_m4;
   mvs::DevBuf<ulonglong2> pyr_b1;
   mvs::DevBuf<int> pyr_vals, pyr_order, pyr_flag, pyr_occ;
-  mvs::DevBuf<float4> pyr_pts;
+  mvs::DevBuf<float4> pyr_pts, pyr_cslab, pyr_bslab;
   mvs::DevBuf<char> pyr_tmp;
 };
 

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "linalg3.h"
 #include "nn_pyramid.cuh"
 
 namespace mvs {
@@ -86,6 +87,83 @@ __global__ void k_pyr_up(const unsigned long long* __restrict__ child, int child
   int x = (int)(t % cx), y = (int)((t / cx) % cy), z = (int)(t / ((int64_t)cx * cy));
   unsigned bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
   atomicOr(parent + ((size_t)(z >> 2) * py + (y >> 2)) * px + (x >> 2), 1ull << bit);
+}
+
+// ---- oriented slab bounds (nn_pyramid.cuh: slab_d2)
+// Fit of one point range: centre, normal = eigenvector of the smallest eigenvalue of the covariance
+// (any unit vector gives a VALID bound — extents are measured from the points with the final normal,
+// in the float arithmetic the query uses — the fit only makes it tight), half thickness along the
+// normal and lateral radius, both inflated against rounding.
+constexpr int kSlabMaxPoints = 4096;  // longer ranges (degenerate grids) get a record that never prunes
+
+__device__ void slab_fit(const float4* __restrict__ pts, int s, int e, float h, float4* out) {
+  int cnt = e - s;
+  if (cnt <= 0 || cnt > kSlabMaxPoints) {
+    out[0] = make_float4(1.f, 0.f, 0.f, INFINITY);
+    out[1] = make_float4(0.f, 0.f, 0.f, INFINITY);
+    return;
+  }
+  double c[3] = {0, 0, 0};
+  for (int i = s; i < e; ++i) {
+    float4 p = __ldg(pts + i);
+    c[0] += p.x; c[1] += p.y; c[2] += p.z;
+  }
+  for (int a = 0; a < 3; ++a) c[a] /= (double)cnt;
+  double C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = s; i < e; ++i) {
+    float4 p = __ldg(pts + i);
+    double d[3] = {p.x - c[0], p.y - c[1], p.z - c[2]};
+    for (int a = 0; a < 3; ++a)
+      for (int b = a; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+  }
+  C[3] = C[1]; C[6] = C[2]; C[7] = C[5];
+  double wv[3], Q[9];
+  sym_eig3(C, wv, Q);
+  double nn = sqrt(Q[0] * Q[0] + Q[3] * Q[3] + Q[6] * Q[6]);
+  float n[3] = {1.f, 0.f, 0.f};
+  if (nn > 0.5 && nn < 2.0) {
+    n[0] = (float)(Q[0] / nn); n[1] = (float)(Q[3] / nn); n[2] = (float)(Q[6] / nn);
+  }
+  float cf[3] = {(float)c[0], (float)c[1], (float)c[2]};
+  float smin = INFINITY, smax = -INFINITY;
+  for (int i = s; i < e; ++i) {
+    float4 p = __ldg(pts + i);
+    float sv = n[0] * (p.x - cf[0]) + n[1] * (p.y - cf[1]) + n[2] * (p.z - cf[2]);
+    smin = fminf(smin, sv);
+    smax = fmaxf(smax, sv);
+  }
+  float mid = 0.5f * (smin + smax);
+  cf[0] += mid * n[0]; cf[1] += mid * n[1]; cf[2] += mid * n[2];
+  float t = 0.f, r2 = 0.f;
+  for (int i = s; i < e; ++i) {  // extents about the FINAL centre, evaluated as slab_d2 evaluates them
+    float4 p = __ldg(pts + i);
+    float vx = p.x - cf[0], vy = p.y - cf[1], vz = p.z - cf[2];
+    float sv = n[0] * vx + n[1] * vy + n[2] * vz;
+    float ux = vx - sv * n[0], uy = vy - sv * n[1], uz = vz - sv * n[2];
+    t = fmaxf(t, fabsf(sv));
+    r2 = fmaxf(r2, ux * ux + uy * uy + uz * uz);
+  }
+  float eps = 4e-6f * (fabsf(cf[0]) + fabsf(cf[1]) + fabsf(cf[2]) + 8.f * h);
+  out[0] = make_float4(n[0], n[1], n[2], sqrtf(r2) * 1.00001f + eps);
+  out[1] = make_float4(cf[0], cf[1], cf[2], t * 1.00001f + eps);
+}
+
+__global__ void k_pyr_cell_slabs(const float4* __restrict__ pts, const int* __restrict__ occ_start,
+                                 int n_occ, float h, float4* __restrict__ cslab) {
+  int oi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (oi >= n_occ) return;
+  slab_fit(pts, occ_start[oi], occ_start[oi + 1], h, cslab + 2 * (size_t)oi);
+}
+
+__global__ void k_pyr_brick_slabs(const float4* __restrict__ pts, const int* __restrict__ occ_start,
+                                  const ulonglong2* __restrict__ b1, int64_t nb1, float h,
+                                  float4* __restrict__ bslab) {
+  int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= nb1) return;
+  ulonglong2 rec = b1[b];
+  if (!rec.x) return;
+  int first = (int)rec.y, cells = __popcll(rec.x);
+  slab_fit(pts, occ_start[first], occ_start[first + cells], h, bslab + 2 * (size_t)first);
 }
 
 static void set_geom(const float mn[3], const float mx[3], float h, PyrGeom& g) {
@@ -238,9 +316,21 @@ int nn_build_pyramid(mvs_nn_index* idx, const float4* pts, int64_t n, float targ
     k_pyr_up<<<div_up(nb3, 256), 256, 0, st>>>(idx->pyr_m3.p, 1, g.d3[0], g.d3[1], g.d3[2],
                                                idx->pyr_m4.p, g.d4[0], g.d4[1]);
   }
+  const bool slabs = !degenerate && getenv("MVS_PYR_NO_SLABS") == nullptr;
+  if (slabs) {
+    MVS_TRY(idx->pyr_cslab.reserve((size_t)2 * n_occ + 2));
+    MVS_TRY(idx->pyr_bslab.reserve((size_t)2 * n_occ + 2));
+    ProfScope ps(ctx, "pyr_slabs", 2);
+    k_pyr_cell_slabs<<<div_up(n_occ, 128), 128, 0, st>>>(idx->pyr_pts.p, idx->pyr_occ.p, n_occ, g.h,
+                                                         idx->pyr_cslab.p);
+    k_pyr_brick_slabs<<<div_up(nb1, 128), 128, 0, st>>>(idx->pyr_pts.p, idx->pyr_occ.p, idx->pyr_b1.p,
+                                                        nb1, g.h, idx->pyr_bslab.p);
+  }
   MVS_CUDA(cudaGetLastError());
   MVS_CUDA(cudaStreamSynchronize(st));  // n32 is on the stack
   PyrParams& P = idx->pyr;
+  P.cslab = slabs ? idx->pyr_cslab.p : nullptr;
+  P.bslab = slabs ? idx->pyr_bslab.p : nullptr;
   for (int a = 0; a < 3; ++a) {
     P.bmin[a] = g.bmin[a];
     P.dims[a] = g.dims[a];

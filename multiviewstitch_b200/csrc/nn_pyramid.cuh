@@ -19,6 +19,10 @@
 #pragma once
 #include "nn_grid.cuh"
 
+#ifndef MVS_PYR_GROW
+#define MVS_PYR_GROW 2.f
+#endif
+
 namespace mvs {
 
 __device__ __forceinline__ unsigned long long box_mask(int xl, int xh, int yl, int yh, int zl,
@@ -39,6 +43,25 @@ __device__ __forceinline__ float aabb_d2(const float q[3], float lx, float ly, f
   return gx * gx + gy * gy + gz * gz;
 }
 
+// Lower bound of the squared distance from q to any point of a set bounded by an oriented slab
+// record {n (unit), R} {c, t}: every point p of the set satisfies |n.(p - c)| <= t and
+// |(p - c) - (n.(p - c)) n| <= R (both inflated at build time).  With v = q - c:
+//   |p - q|^2 = (n.(p - q))^2 + |P (p - q)|^2 >= max(|n.v| - t, 0)^2 + max(|P v| - R, 0)^2.
+// A scan surface is a thin sheet inside a cell or brick: the axis-aligned box of the cell reaches
+// half a cell towards a query above the sheet, the slab does not — for a query at distance d from the
+// surface the box test keeps the ~2 pi d / h cells of a disc of radius sqrt(2 d h), the slab test
+// the handful under the query.  `e` absorbs the float rounding of the evaluation.
+__device__ __forceinline__ float slab_d2(const float q[3], float mg, float4 a, float4 b) {
+  float vx = q[0] - b.x, vy = q[1] - b.y, vz = q[2] - b.z;
+  float s = a.x * vx + a.y * vy + a.z * vz;
+  float ux = vx - s * a.x, uy = vy - s * a.y, uz = vz - s * a.z;
+  float lat = sqrtf(ux * ux + uy * uy + uz * uz);
+  float e = 4e-6f * (fabsf(vx) + fabsf(vy) + fabsf(vz)) + mg;
+  float gap = fmaxf(fabsf(s) - b.w - e, 0.f);
+  float l = fmaxf(lat - a.w - e, 0.f);
+  return gap * gap + l * l;
+}
+
 // state of one query's walk
 struct PyrWalk {
   float q[3];
@@ -46,6 +69,7 @@ struct PyrWalk {
   float cap2;   // search radius^2 of this walk (INFINITY: the visitor's own bound only)
   int lo[3], hi[3];  // box of fine cells that can hold a point within the bound
   int hint[3];       // the query's own cell (clamped to the grid): ring centre
+  float slab_r2;     // squared search radius above which the slab records are consulted
 };
 
 // Children (bits of `occ`) of node (nx,ny,nz) that lie in the walk's box, nearest ring first.
@@ -74,8 +98,14 @@ __device__ __forceinline__ void pyr_children(const PyrWalk& w, unsigned long lon
 
 template <class Visitor>
 __device__ __forceinline__ void pyr_scan_cell(const PyrParams& P, unsigned long long m, int base,
-                                              int bit, Visitor& vis) {
+                                              int bit, Visitor& vis, bool slabs = false,
+                                              const float* q = nullptr, float mg = 0.f,
+                                              float bound = 0.f) {
   int oi = base + __popcll(m & ((1ull << bit) - 1ull));
+  if (slabs) {
+    float4 a = __ldg(P.cslab + 2 * (size_t)oi), b = __ldg(P.cslab + 2 * (size_t)oi + 1);
+    if (slab_d2(q, mg, a, b) > bound) return;
+  }
   int s = __ldg(P.occ_start + oi), e = __ldg(P.occ_start + oi + 1);
   int i = s;
   for (; i + 2 <= e; i += 2) {  // two points in flight
@@ -95,11 +125,23 @@ __device__ __forceinline__ void pyr_scan_brick(const PyrParams& P, const PyrWalk
       fminf(vis.worst2(), w.cap2))
     return;
   ulonglong2 rec = __ldg(P.b1 + ((size_t)z1 * P.d1[1] + y1) * P.d1[0] + x1);
+  if (!rec.x) return;
+  // slab bounds pay once the search radius exceeds about a cell (far queries: the first
+  // Gauss-Newton iteration); below that the boxes prune as well and the record loads cost more
+  const bool slabs = P.cslab != nullptr && fminf(vis.worst2(), w.cap2) > w.slab_r2;
+  if (slabs) {
+    float4 a = __ldg(P.bslab + 2 * (size_t)rec.y), b = __ldg(P.bslab + 2 * (size_t)rec.y + 1);
+    if (slab_d2(w.q, w.mg, a, b) > fminf(vis.worst2(), w.cap2)) return;
+  }
   pyr_children(w, rec.x, x1, y1, z1, 0, [&](int cx, int cy, int cz, int t) {
+    const float bound = fminf(vis.worst2(), w.cap2);
+#ifdef MVS_PYR_SKIP_CELL_BOX
+    if (!slabs)
+#endif
     if (aabb_d2(w.q, P.bmin[0] + cx * P.h, P.bmin[1] + cy * P.h, P.bmin[2] + cz * P.h, P.h, w.mg) >
-        fminf(vis.worst2(), w.cap2))
+        bound)
       return;
-    pyr_scan_cell(P, rec.x, (int)rec.y, t, vis);
+    pyr_scan_cell(P, rec.x, (int)rec.y, t, vis, slabs, w.q, w.mg, bound);
   });
 }
 
@@ -173,6 +215,7 @@ __device__ __forceinline__ void pyr_search(const PyrParams& P, float qx, float q
 #pragma unroll
   for (int a = 0; a < 3; ++a) w.hint[a] = grid_coord(w.q[a], P.bmin[a], P.inv_h, P.dims[a]);
   w.mg = 1e-3f * P.h + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
+  w.slab_r2 = kPyrSlabRadius * kPyrSlabRadius * P.h * P.h;
   if (vis.worst2() < INFINITY) {
     pyr_walk(P, w, INFINITY, vis);
     return;
@@ -197,7 +240,7 @@ __device__ __forceinline__ void pyr_search(const PyrParams& P, float qx, float q
       pyr_walk(P, w, INFINITY, vis);
       return;
     }
-    r *= 2.f;
+    r *= MVS_PYR_GROW;
   }
 }
 

@@ -21,6 +21,8 @@
 //   * the search direction of a neighbour row is rebuilt on the fly as z_l + beta p_prev_l, which
 //     saves the third barrier a separate "p = z + beta p" phase would need.
 // Standard PCG recurrences, identical to oracle/deform.cpp pcg(); vectors float32, scalars float64.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "deform.cuh"
@@ -28,8 +30,11 @@
 namespace mvs {
 
 constexpr int kRowLanes = 16;
-constexpr int kPcgThreads = 256;
-constexpr int kGroups = kPcgThreads / kRowLanes;  // row groups per CTA
+// CTA size is a launch parameter (256: two CTAs per SM, 512: one): fewer, larger CTAs halve the
+// arrivals of every grid exchange.  MVS_PCG_THREADS overrides the planner's choice.
+constexpr int kPcgMaxThreads = 512;
+constexpr int kPcgMaxWarps = kPcgMaxThreads / 32;
+constexpr int kPcgDefaultThreads = 512;  // C3: 149.1 us per 20 iterations against 151 at 256
 
 struct PcgArgs {
   const int* row_ptr;
@@ -94,14 +99,14 @@ __device__ __forceinline__ unsigned long long ld_flag(const double* p) {
 //   fixed order; (4) the totals reach the other warps through shared memory.  Consumers read the
 //   exchanged vectors with ld.global.cg (L2), never through L1.
 // Every CTA runs the same number of phases (control flow depends only on the identical totals).
-template <int N>
+template <int N, int T>
 __device__ __forceinline__ void grid_exchange(double (&v)[N], double* red, double* ring,
                                               unsigned& phase, int ncta, double (&out)[N]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int W = kPcgThreads / 32;
+  constexpr int W = T / 32;
   constexpr int U = 8;           // slots per lane in flight
-  double* red1 = red;            // W x 2: CTA partial
-  double* red2 = red + W * 2;    // 2: totals
+  double* red1 = red;                       // W x 2: CTA partial
+  double* red2 = red + kPcgMaxWarps * 2;    // 2: totals
 #pragma unroll
   for (int j = 0; j < N; ++j) v[j] = warp_sum(v[j]);
   if (lane == 0)
@@ -118,7 +123,6 @@ __device__ __forceinline__ void grid_exchange(double (&v)[N], double* red, doubl
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         s[j] = 0.0;
-#pragma unroll
         for (int w = 0; w < W; ++w) s[j] += red1[w * 2 + j];
       }
       fence_acq_rel();
@@ -207,14 +211,18 @@ __device__ __forceinline__ long long fx_limb(double v, const FxUnit& u, int limb
 // FENCE = false: a pure all-reduce.  The p.q exchange needs no memory ordering — the search
 // directions a CTA stored before it are read by other CTAs only after the NEXT (fenced) exchange —
 // so it skips the release/acquire fences (each waits for the CTA's outstanding stores).
-template <int N, bool FENCE = true>
+// `post(tot, extra)` runs on ONE thread of the CTA between the decode and the closing barrier and
+// leaves derived scalars (the step lengths: one float64 division each) in extra[0..1], which every
+// thread reads after the barrier — instead of every thread issuing its own float64 division.
+template <int N, int T, bool FENCE = true, class Post>
 __device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
                                                  unsigned long long* words, unsigned& wi, int ncta,
-                                                 const FxUnit (&unit)[N], double (&out)[N]) {
+                                                 const FxUnit (&unit)[N], double (&out)[N],
+                                                 Post&& post) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int W = kPcgThreads / 32;
-  double* red1 = red;          // W x 2: CTA partial
-  double* red2 = red + W * 2;  // N x 2 limb sums
+  constexpr int W = T / 32;
+  double* red1 = red;                     // W x 2: CTA partial
+  double* red2 = red + kPcgMaxWarps * 2;  // N x 2 limb sums
 #pragma unroll
   for (int j = 0; j < N; ++j) v[j] = warp_sum(v[j]);
   if (lane == 0)
@@ -224,7 +232,6 @@ __device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
   if (threadIdx.x < 2 * N) {
     const int j = threadIdx.x >> 1, limb = threadIdx.x & 1;
     double s = 0.0;
-#pragma unroll
     for (int w = 0; w < W; ++w) s += red1[w * 2 + j];
     FxUnit u = unit[0];
     if (N > 1 && j == 1) u = unit[N - 1];
@@ -241,6 +248,13 @@ __device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
     if (FENCE && threadIdx.x == 0) fence_acq_rel();
     long long sum = (long long)(b & ((1ull << kCountShift) - 1ull)) - (long long)ncta * kLimbBias;
     red2[threadIdx.x] = (double)sum;
+    __syncwarp((1u << (2 * N)) - 1u);
+    if (threadIdx.x == 0) {
+      double tot[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) tot[j] = red2[2 * j] * unit[j].hi + red2[2 * j + 1] * unit[j].lo;
+      post(tot, red2 + 2 * N);
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -299,10 +313,11 @@ __device__ __forceinline__ void entry_mac(float (&acc)[12], const float4* __rest
 
 // zp[buf][row][k] = (z, p): z of the row after the update of an iteration, p its search direction;
 // iteration `it` reads buffer (it+1)&1 (written during iteration it-1) and writes buffer it&1.
-template <int RS>
-__global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
+template <int RS, int T>
+__global__ void __launch_bounds__(T, 512 / T) k_pcg_persistent(PcgArgs a) {
   extern __shared__ float4 smem_dyn[];
-  __shared__ double red[(kPcgThreads / 32) * 2 + 4];
+  __shared__ double red[kPcgMaxWarps * 2 + 8];
+  constexpr int kGroups = T / kRowLanes;  // row groups of this CTA
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int k = lane & (kRowLanes - 1);
@@ -315,8 +330,8 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
   const bool lane_on = k < 12;
   float2* zp = reinterpret_cast<float2*>(a.zbuf);  // 2 x m x 12 float2
   unsigned phase = 0;
-  for (int i = blockIdx.x * kPcgThreads + threadIdx.x; i < a.ring_count + a.word_count;
-       i += gridDim.x * kPcgThreads) {
+  for (int i = blockIdx.x * T + threadIdx.x; i < a.ring_count + a.word_count;
+       i += gridDim.x * T) {
     if (i < a.ring_count)
       a.next_ring[i] = kSlotEmpty;
     else
@@ -333,8 +348,8 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
   if (a.stage_smem) {
     int nb = (nz1 - nz0) * 4;
     int* scol = reinterpret_cast<int*>(smem_dyn + nb);
-    for (int i = threadIdx.x; i < nb; i += kPcgThreads) smem_dyn[i] = __ldg(Bsrc + i);
-    for (int i = threadIdx.x; i < nz1 - nz0; i += kPcgThreads) scol[i] = __ldg(csrc + i);
+    for (int i = threadIdx.x; i < nb; i += T) smem_dyn[i] = __ldg(Bsrc + i);
+    for (int i = threadIdx.x; i < nz1 - nz0; i += T) scol[i] = __ldg(csrc + i);
     Bs = smem_dyn;
     cs = scol;
     __syncthreads();
@@ -380,7 +395,7 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
   double rz, bn2;
   {
     double tot[2];
-    grid_exchange<2>(acc, red, a.ring, phase, ncta, tot);
+    grid_exchange<2, T>(acc, red, a.ring, phase, ncta, tot);
     rz = tot[0];
     bn2 = tot[1];
   }
@@ -390,10 +405,11 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
   const FxUnit unit_b[2] = {fx_unit_for(rz), fx_unit_for(bn2)};
   FxUnit unit_a[1] = {fx_unit_for(0.0)};
   int it = 0;
+  float beta_next = 0.f;
   for (; it < a.iters; ++it) {
     if (a.tol > 0.0 && rn2 <= a.tol * a.tol * bn2) break;  // uniform over the grid
     // ---- phase A: p = z + beta p ; q = (H + lambda) p ; p.q
-    float beta = (it > 0 && rz_old > 0.0) ? (float)(rz / rz_old) : 0.f;
+    const float beta = beta_next;  // rz / rz_old, divided once per CTA inside the last exchange
     const float4* zprev = reinterpret_cast<const float4*>(zp + (size_t)((it + 1) & 1) * m * 12);
     float2* zcur = zp + (size_t)(it & 1) * m * 12;
     float qv[RS];
@@ -442,15 +458,20 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
       pq[0] += (double)p[s] * (double)y;
     }
     double pqa[1];
+    float alpha;
+    double* extra = red + kPcgMaxWarps * 2;
     if (it == 0) {  // magnitude of p.q unknown yet: exact slot exchange, then fix its unit
-      grid_exchange<1>(pq, red, a.ring, phase, ncta, pqa);
+      grid_exchange<1, T>(pq, red, a.ring, phase, ncta, pqa);
       unit_a[0] = fx_unit_for(fabs(pqa[0]));
+      alpha = (pqa[0] > 0.0 && rz > 0.0) ? (float)(rz / pqa[0]) : 0.f;
     } else {
-      grid_exchange_fx<1, false>(pq, red, a.words, wi, ncta, unit_a, pqa);
+      grid_exchange_fx<1, T, false>(pq, red, a.words, wi, ncta, unit_a, pqa,
+                                 [&](const double (&tot)[1], double* ex) {
+                                   ex[0] = (tot[0] > 0.0 && rz > 0.0) ? (double)(float)(rz / tot[0]) : 0.0;
+                                 });
+      alpha = (float)extra[2];
     }
-    // ---- phase B: alpha ; delta += alpha p ; r -= alpha q ; z = M^-1 r ; r.z, |r|^2
-    double pqt = pqa[0];
-    float alpha = (pqt > 0.0 && rz > 0.0) ? (float)(rz / pqt) : 0.f;
+    // ---- phase B: delta += alpha p ; r -= alpha q ; z = M^-1 r ; r.z, |r|^2
     acc[0] = acc[1] = 0.0;
 #pragma unroll
     for (int s = 0; s < RS; ++s) {
@@ -475,9 +496,13 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
     rz_old = rz;
     {
       double tot[2];
-      grid_exchange_fx<2>(acc, red, a.words, wi, ncta, unit_b, tot);
+      grid_exchange_fx<2, T>(acc, red, a.words, wi, ncta, unit_b, tot,
+                          [&](const double (&t2)[2], double* ex) {
+                            ex[0] = rz_old > 0.0 ? (double)(float)(t2[0] / rz_old) : 0.0;
+                          });
       rz = tot[0];
       rn2 = tot[1];
+      beta_next = (float)extra[4];
     }
   }
   // ---- x += delta
@@ -497,20 +522,24 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg_persistent(PcgArgs a) {
   }
 }
 
-template <int RS>
-static int launch_pcg(mvs_deform* h, PcgArgs& a, int grid, size_t smem) {
-  auto kern = k_pcg_persistent<RS>;
+template <int RS, int T>
+static int launch_pcg_t(mvs_deform* h, PcgArgs& a, int grid, size_t smem) {
+  auto kern = k_pcg_persistent<RS, T>;
   if (smem > 48 * 1024)
     MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {&a};
-  MVS_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kPcgThreads), args, smem,
-                                       h->ctx->stream));
+  MVS_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(T), args, smem, h->ctx->stream));
   return MVS_OK;
 }
-
 template <int RS>
-static int max_coresident(size_t smem, int num_sms, int* out) {
-  auto kern = k_pcg_persistent<RS>;
+static int launch_pcg(mvs_deform* h, PcgArgs& a, int grid, size_t smem) {
+  return h->pcg_threads == 512 ? launch_pcg_t<RS, 512>(h, a, grid, smem)
+                               : launch_pcg_t<RS, 256>(h, a, grid, smem);
+}
+
+template <int RS, int T>
+static int max_coresident_t(size_t smem, int num_sms, int* out) {
+  auto kern = k_pcg_persistent<RS, T>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -520,9 +549,14 @@ static int max_coresident(size_t smem, int num_sms, int* out) {
     }
   }
   int per_sm = 0;
-  MVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPcgThreads, smem));
+  MVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
   *out = per_sm * num_sms;
   return MVS_OK;
+}
+template <int RS>
+static int max_coresident(size_t smem, int num_sms, int threads, int* out) {
+  return threads == 512 ? max_coresident_t<RS, 512>(smem, num_sms, out)
+                        : max_coresident_t<RS, 256>(smem, num_sms, out);
 }
 
 // Picks the row-slot count RS, the grid and whether the matrix slice fits in shared memory.
@@ -533,44 +567,58 @@ static int plan_pcg(mvs_deform* h) {
   // the smallest row-slot count whose grid is co-resident: a CTA walks its RS slots one after the
   // other in every phase, so 20,000 rows run 5 slots on 250 CTAs instead of 8 slots on 157
   const int rs_opts[7] = {1, 2, 3, 4, 5, 6, 8};
+  int t_opts[2] = {kPcgDefaultThreads, kPcgDefaultThreads == 256 ? 512 : 256};
+  int nt_opts = 2;
+  if (const char* env = getenv("MVS_PCG_THREADS")) {
+    int t = atoi(env);
+    if (t == 256 || t == 512) {
+      t_opts[0] = t;
+      nt_opts = 1;
+    }
+  }
   for (int stage = 1; stage >= 0; --stage) {
-    for (int oi = 0; oi < 7; ++oi) {
-      int RS = rs_opts[oi];
-      int rpc = RS * kGroups;
-      int grid = (int)((m + rpc - 1) / rpc);
-      size_t smem = 0;
-      if (stage) {
-        int worst = 0;
-        for (int64_t r0 = 0; r0 < m; r0 += rpc) {
-          int64_t r1 = std::min<int64_t>(m, r0 + rpc);
-          worst = std::max(worst, h->h_row_ptr[r1] - h->h_row_ptr[r0]);
+    for (int ti = 0; ti < nt_opts; ++ti) {
+      const int T = t_opts[ti];
+      const int kGroups = T / kRowLanes;
+      for (int oi = 0; oi < 7; ++oi) {
+        int RS = rs_opts[oi];
+        int rpc = RS * kGroups;
+        int grid = (int)((m + rpc - 1) / rpc);
+        size_t smem = 0;
+        if (stage) {
+          int worst = 0;
+          for (int64_t r0 = 0; r0 < m; r0 += rpc) {
+            int64_t r1 = std::min<int64_t>(m, r0 + rpc);
+            worst = std::max(worst, h->h_row_ptr[r1] - h->h_row_ptr[r0]);
+          }
+          smem = (size_t)worst * (64 + 4) + 16;
+          if (smem > 200 * 1024) continue;
         }
-        smem = (size_t)worst * (64 + 4) + 16;
-        if (smem > 200 * 1024) continue;
-      }
-      int cap = 0;
-      switch (RS) {
-        case 1: MVS_TRY(max_coresident<1>(smem, ctx->num_sms, &cap)); break;
-        case 2: MVS_TRY(max_coresident<2>(smem, ctx->num_sms, &cap)); break;
-        case 3: MVS_TRY(max_coresident<3>(smem, ctx->num_sms, &cap)); break;
-        case 4: MVS_TRY(max_coresident<4>(smem, ctx->num_sms, &cap)); break;
-        case 5: MVS_TRY(max_coresident<5>(smem, ctx->num_sms, &cap)); break;
-        case 6: MVS_TRY(max_coresident<6>(smem, ctx->num_sms, &cap)); break;
-        default: MVS_TRY(max_coresident<8>(smem, ctx->num_sms, &cap)); break;
-      }
-      // the exchange words count arrivals in 10 bits (kCountShift): fewer than 1024 CTAs
-      if (grid <= cap && grid < 1024) {
-        h->pcg_rs = RS;
-        h->pcg_grid = grid;
-        h->pcg_smem = smem;
-        h->pcg_stage = stage;
-        h->pcg_plan_valid = true;
-        return MVS_OK;
+        int cap = 0;
+        switch (RS) {
+          case 1: MVS_TRY(max_coresident<1>(smem, ctx->num_sms, T, &cap)); break;
+          case 2: MVS_TRY(max_coresident<2>(smem, ctx->num_sms, T, &cap)); break;
+          case 3: MVS_TRY(max_coresident<3>(smem, ctx->num_sms, T, &cap)); break;
+          case 4: MVS_TRY(max_coresident<4>(smem, ctx->num_sms, T, &cap)); break;
+          case 5: MVS_TRY(max_coresident<5>(smem, ctx->num_sms, T, &cap)); break;
+          case 6: MVS_TRY(max_coresident<6>(smem, ctx->num_sms, T, &cap)); break;
+          default: MVS_TRY(max_coresident<8>(smem, ctx->num_sms, T, &cap)); break;
+        }
+        // the exchange words count arrivals in 10 bits (kCountShift): fewer than 1024 CTAs
+        if (grid <= cap && grid < 1024) {
+          h->pcg_rs = RS;
+          h->pcg_threads = T;
+          h->pcg_grid = grid;
+          h->pcg_smem = smem;
+          h->pcg_stage = stage;
+          h->pcg_plan_valid = true;
+          return MVS_OK;
+        }
       }
     }
   }
   set_error("pcg: %lld nodes exceed the co-resident capacity of the persistent solver (max %d rows)",
-            (long long)m, 8 * kGroups * ctx->num_sms * 2);
+            (long long)m, 8 * (kPcgMaxThreads / kRowLanes) * ctx->num_sms);
   return MVS_ERR_CAPACITY;
 }
 
@@ -620,7 +668,7 @@ int pcg_solve(mvs_deform* h) {
   a.iters = h->prm.pcg_iters;
   a.lambda = (float)h->prm.lambda;
   a.tol = h->prm.pcg_tol;
-  a.rows_per_cta = h->pcg_rs * kGroups;
+  a.rows_per_cta = h->pcg_rs * (h->pcg_threads / kRowLanes);
   a.stage_smem = h->pcg_stage;
   ProfScope ps(ctx, "pcg_solve");
   switch (h->pcg_rs) {
