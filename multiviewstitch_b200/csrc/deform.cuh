@@ -55,6 +55,7 @@ struct mvs_deform {
   std::vector<int> h_row_ptr;  // host copy of row_ptr (solver launch planning)
   std::vector<int> h_grp_start;  // first sorted vertex of every assembly group, then n
   bool pcg_plan_valid = false;
+  bool pcg_launch_per_phase = false;  // graph too large for the persistent cooperative solver
   int pcg_rs = 1, pcg_grid = 0, pcg_stage = 0, pcg_threads = 256;
   size_t pcg_smem = 0;
   mvs::DevBuf<float> sys;
@@ -143,7 +144,7 @@ constexpr int kGrpRuns = 4;             // runs per assembly group
 constexpr int kGrpMax = 14 * kGrpRuns;  // 10 upper-triangle block tiles + 4 gradient tiles per run
 
 // scal[] slots
-enum { S_RZ = 0, S_PQ = 1, S_RZ_NEW = 2, S_BNORM2 = 3, S_RNORM2 = 4, S_EFIT = 8, S_EROT = 9,
+enum { S_RZ = 0, S_PQ = 1, S_RZ_NEW = 2, S_BNORM2 = 3, S_RNORM2 = 4, S_PQ_CUR = 5, S_EFIT = 8, S_EROT = 9,
        S_EREG = 10, S_SIZE = 16 };
 
 // deform_graph.cu

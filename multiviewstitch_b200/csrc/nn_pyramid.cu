@@ -380,7 +380,18 @@ struct CountingNN {
     ++npts;
     l.point(p);
   }
+#ifdef MVS_PYR_STATS
+  int st[8];
+#endif
 };
+#ifdef MVS_PYR_STATS
+__device__ __forceinline__ void pyr_stats_out(CountingNN& c, const int* s) {
+  for (int k = 0; k < 8; ++k) c.st[k] = s[k];
+}
+#endif
+#ifdef MVS_PYR_STATS
+__device__ int* g_stat_buf = nullptr;
+#endif
 __global__ void __launch_bounds__(128)
     k_nn1_pyr_count(PyrParams P, const float4* __restrict__ q, int64_t nq, int* __restrict__ out_idx,
                     float* __restrict__ out_d2) {
@@ -393,8 +404,15 @@ __global__ void __launch_bounds__(128)
   long long t0 = clock64();
   pyr_search(P, qq.x, qq.y, qq.z, c);
   long long t1 = clock64();
+#ifdef MVS_PYR_STATS
+  // debug layout: out_idx[i] = points tested; out_d2 reused as 8 floats per query when nq*8 fits
+  if (out_idx) out_idx[i] = c.npts;
+  if (out_d2) out_d2[i] = (float)(c.st[0] + 100 * c.st[1]) + 1e4f * (float)c.st[2] + 1e7f * 0.f;
+  if (g_stat_buf) for (int k = 0; k < 8; ++k) g_stat_buf[8 * i + k] = c.st[k];
+#else
   if (out_idx) out_idx[i] = c.npts;
   if (out_d2) out_d2[i] = (float)(t1 - t0);
+#endif
 }
 
 int nn_nn1_pyramid(mvs_nn_index* idx, const float4* q, const int* perm, int64_t nq, int* out_idx,
@@ -406,8 +424,27 @@ int nn_nn1_pyramid(mvs_nn_index* idx, const float4* q, const int* perm, int64_t 
   }
   if (nq <= 0) return MVS_OK;
   if (getenv("MVS_PYR_DEBUG")) {
+#ifdef MVS_PYR_STATS
+    static DevBuf<int> stat;
+    MVS_TRY(stat.reserve((size_t)nq * 8));
+    int* sp = stat.p;
+    MVS_CUDA(cudaMemcpyToSymbolAsync(g_stat_buf, &sp, sizeof(sp), 0, cudaMemcpyHostToDevice, ctx->stream));
+#endif
     k_nn1_pyr_count<<<div_up(nq, 128), 128, 0, ctx->stream>>>(idx->pyr, q, nq, out_idx, out_d2);
     MVS_CUDA(cudaGetLastError());
+#ifdef MVS_PYR_STATS
+    {
+      std::vector<int> hs((size_t)nq * 8);
+      MVS_CUDA(cudaMemcpyAsync(hs.data(), stat.p, sizeof(int) * 8 * nq, cudaMemcpyDeviceToHost, ctx->stream));
+      MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+      double sum[8] = {0};
+      for (int64_t i = 0; i < nq; ++i)
+        for (int k = 0; k < 8; ++k) sum[k] += hs[(size_t)8 * i + k];
+      fprintf(stderr, "[pyr stats] per query: walks %.2f upper nodes %.2f brick box %.2f brick slab %.2f "
+                      "cell box %.2f cell slab %.2f\n", sum[0] / nq, sum[1] / nq, sum[2] / nq, sum[3] / nq,
+              sum[4] / nq, sum[5] / nq);
+    }
+#endif
     return MVS_OK;
   }
   ProfScope ps(ctx, "nn1_pyramid");

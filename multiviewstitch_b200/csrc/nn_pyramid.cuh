@@ -70,7 +70,17 @@ struct PyrWalk {
   int lo[3], hi[3];  // box of fine cells that can hold a point within the bound
   int hint[3];       // the query's own cell (clamped to the grid): ring centre
   float slab_r2;     // squared search radius above which the slab records are consulted
+#ifdef MVS_PYR_STATS
+  int st[8];         // walks, upper nodes, brick box tests, brick slab tests, cell box, cell slab, cells scanned, -
+#endif
 };
+#ifdef MVS_PYR_STATS
+template <class V>
+__device__ __forceinline__ void pyr_stats_out(V&, const int*) {}
+#define PYR_STAT(w, k) (++const_cast<PyrWalk&>(w).st[k])
+#else
+#define PYR_STAT(w, k) ((void)0)
+#endif
 
 // Children (bits of `occ`) of node (nx,ny,nz) that lie in the walk's box, nearest ring first.
 // `sh`: log2 of the child edge in fine cells.  f(cx, cy, cz, bit) is called per child.
@@ -121,6 +131,7 @@ template <class Visitor>
 __device__ __forceinline__ void pyr_scan_brick(const PyrParams& P, const PyrWalk& w, int x1, int y1,
                                                int z1, Visitor& vis) {
   float s1 = 4.f * P.h;
+  PYR_STAT(w, 2);
   if (aabb_d2(w.q, P.bmin[0] + x1 * s1, P.bmin[1] + y1 * s1, P.bmin[2] + z1 * s1, s1, w.mg) >
       fminf(vis.worst2(), w.cap2))
     return;
@@ -130,17 +141,20 @@ __device__ __forceinline__ void pyr_scan_brick(const PyrParams& P, const PyrWalk
   // Gauss-Newton iteration); below that the boxes prune as well and the record loads cost more
   const bool slabs = P.cslab != nullptr && fminf(vis.worst2(), w.cap2) > w.slab_r2;
   if (slabs) {
+    PYR_STAT(w, 3);
     float4 a = __ldg(P.bslab + 2 * (size_t)rec.y), b = __ldg(P.bslab + 2 * (size_t)rec.y + 1);
     if (slab_d2(w.q, w.mg, a, b) > fminf(vis.worst2(), w.cap2)) return;
   }
   pyr_children(w, rec.x, x1, y1, z1, 0, [&](int cx, int cy, int cz, int t) {
     const float bound = fminf(vis.worst2(), w.cap2);
+    PYR_STAT(w, 4);
 #ifdef MVS_PYR_SKIP_CELL_BOX
     if (!slabs)
 #endif
     if (aabb_d2(w.q, P.bmin[0] + cx * P.h, P.bmin[1] + cy * P.h, P.bmin[2] + cz * P.h, P.h, w.mg) >
         bound)
       return;
+    if (slabs) PYR_STAT(w, 5);
     pyr_scan_cell(P, rec.x, (int)rec.y, t, vis, slabs, w.q, w.mg, bound);
   });
 }
@@ -150,6 +164,7 @@ __device__ __forceinline__ void pyr_scan_brick(const PyrParams& P, const PyrWalk
 template <class Visitor>
 __device__ __forceinline__ void pyr_walk(const PyrParams& P, PyrWalk& w, float cap2, Visitor& vis) {
   w.cap2 = cap2;
+  PYR_STAT(w, 0);
   float w2 = fminf(vis.worst2(), cap2);
   if (w2 < INFINITY) {
     float r = sqrtf(w2) * 1.000001f + w.mg;
@@ -187,11 +202,13 @@ __device__ __forceinline__ void pyr_walk(const PyrParams& P, PyrWalk& w, float c
       for (int x4 = w.lo[0] >> 8; x4 <= (w.hi[0] >> 8); ++x4) {
         unsigned long long o4 = __ldg(P.m4 + ((size_t)z4 * P.d4[1] + y4) * P.d4[0] + x4);
         pyr_children(w, o4, x4, y4, z4, 6, [&](int x3, int y3, int z3, int) {
+          PYR_STAT(w, 1);
           if (aabb_d2(w.q, P.bmin[0] + x3 * s3, P.bmin[1] + y3 * s3, P.bmin[2] + z3 * s3, s3, w.mg) >
               fminf(vis.worst2(), w.cap2))
             return;
           unsigned long long o3 = __ldg(P.m3 + ((size_t)z3 * P.d3[1] + y3) * P.d3[0] + x3);
           pyr_children(w, o3, x3, y3, z3, 4, [&](int x2, int y2, int z2, int) {
+            PYR_STAT(w, 1);
             if (aabb_d2(w.q, P.bmin[0] + x2 * s2, P.bmin[1] + y2 * s2, P.bmin[2] + z2 * s2, s2,
                         w.mg) > fminf(vis.worst2(), w.cap2))
               return;
@@ -216,6 +233,14 @@ __device__ __forceinline__ void pyr_search(const PyrParams& P, float qx, float q
   for (int a = 0; a < 3; ++a) w.hint[a] = grid_coord(w.q[a], P.bmin[a], P.inv_h, P.dims[a]);
   w.mg = 1e-3f * P.h + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz));
   w.slab_r2 = kPyrSlabRadius * kPyrSlabRadius * P.h * P.h;
+#ifdef MVS_PYR_STATS
+  for (int k = 0; k < 8; ++k) w.st[k] = 0;
+  struct StatOut {
+    PyrWalk& w;
+    Visitor& v;
+    __device__ ~StatOut() { pyr_stats_out(v, w.st); }
+  } stat_out{w, vis};
+#endif
   if (vis.worst2() < INFINITY) {
     pyr_walk(P, w, INFINITY, vis);
     return;

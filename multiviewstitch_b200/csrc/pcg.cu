@@ -26,6 +26,7 @@
 #include <algorithm>
 
 #include "deform.cuh"
+#include "reduce.cuh"
 
 namespace mvs {
 
@@ -562,6 +563,11 @@ static int max_coresident(size_t smem, int num_sms, int threads, int* out) {
 // Picks the row-slot count RS, the grid and whether the matrix slice fits in shared memory.
 static int plan_pcg(mvs_deform* h) {
   if (h->pcg_plan_valid) return MVS_OK;
+  h->pcg_launch_per_phase = getenv("MVS_PCG_LAUNCHES") != nullptr;  // test switch
+  if (h->pcg_launch_per_phase) {
+    h->pcg_plan_valid = true;
+    return MVS_OK;
+  }
   mvs_ctx* ctx = h->ctx;
   int64_t m = h->m;
   // the smallest row-slot count whose grid is co-resident: a CTA walks its RS slots one after the
@@ -617,14 +623,209 @@ static int plan_pcg(mvs_deform* h) {
       }
     }
   }
-  set_error("pcg: %lld nodes exceed the co-resident capacity of the persistent solver (max %d rows)",
-            (long long)m, 8 * (kPcgMaxThreads / kRowLanes) * ctx->num_sms);
-  return MVS_ERR_CAPACITY;
+  // not co-resident: the launch-per-phase solver (pcg_solve_launches)
+  h->pcg_launch_per_phase = true;
+  h->pcg_plan_valid = true;
+  return MVS_OK;
+}
+
+// ------------------------------------------------------------------ launch-per-phase solver
+// Graphs whose rows are not co-resident in one cooperative grid (more than ~37,000 nodes: the
+// reference's own 16-NN sampling rule, Deformation.cpp:63-106, yields 60-100 K nodes on a 1M-vertex
+// mesh) run the same recurrences as three launches per iteration — product + p.q, update + r.z,
+// direction — with the scalars kept on the device (no host synchronisation) and the same fixed-order
+// float64 reductions (reduce.cuh), so the solve stays bit-reproducible.  At that size every launch
+// streams tens of MB, so launch latency no longer dominates.
+constexpr int kLThreads = 256;
+constexpr int kLGroups = kLThreads / kRowLanes;
+
+struct PcgLArgs {
+  const int* row_ptr;
+  const int* col;
+  const float* B;
+  const float* Rot;
+  const float* Minv;
+  const float* rhs;
+  float* x;
+  float *r, *z, *p, *q, *d;  // m x 12 each
+  double* scal;              // S_RZ, S_PQ, S_RZ_NEW, S_BNORM2, S_RNORM2
+  double* partials;
+  unsigned* ticket;
+  int64_t m;
+  float lambda;
+  double tol;
+};
+
+// z_row = M^-1 r_row over the 16-lane group (lane k holds r[k])
+__device__ __forceinline__ float precond_row(const float* __restrict__ Minv, int64_t j, int k,
+                                             int gbase, float rk, bool act) {
+  float zv = 0.f;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    float rq = __shfl_sync(0xffffffffu, rk, gbase + q);
+    if (act) zv += __ldg(Minv + j * 144 + k * 12 + q) * rq;
+  }
+  return zv;
+}
+
+__global__ void __launch_bounds__(kLThreads) k_pcgl_init(PcgLArgs a) {
+  __shared__ double smem[64];
+  const int lane = threadIdx.x & 31, k = lane & (kRowLanes - 1), gbase = lane & ~(kRowLanes - 1);
+  int64_t j = (int64_t)blockIdx.x * kLGroups + threadIdx.x / kRowLanes;
+  bool act = j < a.m && k < 12;
+  float rk = act ? -__ldg(a.rhs + j * 12 + k) : 0.f;
+  float zv = precond_row(a.Minv, j, k, gbase, rk, act);
+  if (act) {
+    a.r[j * 12 + k] = rk;
+    a.z[j * 12 + k] = zv;
+    a.p[j * 12 + k] = zv;
+    a.d[j * 12 + k] = 0.f;
+  }
+  double v[2] = {(double)rk * (double)zv, (double)rk * (double)rk};
+  double out[2];
+  if (grid_reduce_sum<2>(v, smem, a.partials, a.ticket, out) && threadIdx.x == 0) {
+    a.scal[S_RZ] = out[0];
+    a.scal[S_BNORM2] = out[1];
+    a.scal[S_RNORM2] = out[1];
+    a.scal[S_PQ] = 0.0;  // iterations run (as the persistent kernel reports them)
+  }
+}
+
+// q = (H + lambda I) p, p.q
+__global__ void __launch_bounds__(kLThreads) k_pcgl_product(PcgLArgs a) {
+  __shared__ double smem[32];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, k = lane & (kRowLanes - 1), gbase = lane & ~(kRowLanes - 1);
+  int64_t j = (int64_t)blockIdx.x * kLGroups + threadIdx.x / kRowLanes;
+  bool on = j < a.m, act = on && k < 12;
+  const bool stop = a.tol > 0.0 && a.scal[S_RNORM2] <= a.tol * a.tol * a.scal[S_BNORM2];
+  float pk = act ? a.p[j * 12 + k] : 0.f;
+  float ya[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) ya[q] = 0.f;
+  if (on && !stop) {
+    const int t0 = __ldg(a.row_ptr + j), t1 = __ldg(a.row_ptr + j + 1);
+    for (int t = t0 + k; t < t1; t += kRowLanes) {
+      const int l = __ldg(a.col + t);
+      const float4* pl = reinterpret_cast<const float4*>(a.p + (size_t)l * 12);
+      float4 u0 = __ldg(pl), u1 = __ldg(pl + 1), u2 = __ldg(pl + 2);
+      float pv[12] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w, u2.x, u2.y, u2.z, u2.w};
+      const float4* Bt = reinterpret_cast<const float4*>(a.B) + (size_t)t * 4;
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa) {
+        float4 b = __ldg(Bt + aa);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          ya[3 * aa + r] += b.x * pv[r] + b.y * pv[3 + r] + b.z * pv[6 + r] + b.w * pv[9 + r];
+      }
+    }
+  }
+  float y = group_reduce_scatter(ya, k);
+  y += a.lambda * pk;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    float pq = __shfl_sync(full, pk, gbase + q);
+    if (act && k < 9) y += __ldg(a.Rot + j * 81 + k * 9 + q) * pq;
+  }
+  if (!act || stop) y = 0.f;
+  if (act) a.q[j * 12 + k] = y;
+  double v[1] = {(double)pk * (double)y};
+  double out[1];
+  if (grid_reduce_sum<1>(v, smem, a.partials, a.ticket, out) && threadIdx.x == 0)
+    a.scal[S_PQ_CUR] = out[0];  // p.q of this iteration
+}
+
+// alpha ; d += alpha p ; r -= alpha q ; z = M^-1 r ; r.z, |r|^2
+__global__ void __launch_bounds__(kLThreads) k_pcgl_update(PcgLArgs a) {
+  __shared__ double smem[64];
+  const int lane = threadIdx.x & 31, k = lane & (kRowLanes - 1), gbase = lane & ~(kRowLanes - 1);
+  int64_t j = (int64_t)blockIdx.x * kLGroups + threadIdx.x / kRowLanes;
+  bool act = j < a.m && k < 12;
+  const double rz = a.scal[S_RZ], pq = a.scal[S_PQ_CUR];
+  const bool stop = a.tol > 0.0 && a.scal[S_RNORM2] <= a.tol * a.tol * a.scal[S_BNORM2];
+  const float alpha = (!stop && pq > 0.0 && rz > 0.0) ? (float)(rz / pq) : 0.f;
+  float rk = 0.f, zv = 0.f;
+  if (act) {
+    rk = a.r[j * 12 + k] - alpha * a.q[j * 12 + k];
+    a.d[j * 12 + k] += alpha * a.p[j * 12 + k];
+    a.r[j * 12 + k] = rk;
+  }
+  zv = precond_row(a.Minv, j, k, gbase, rk, act);
+  if (act) a.z[j * 12 + k] = zv;
+  double v[2] = {(double)rk * (double)zv, (double)rk * (double)rk};
+  double out[2];
+  if (grid_reduce_sum<2>(v, smem, a.partials, a.ticket, out) && threadIdx.x == 0) {
+    a.scal[S_RZ_NEW] = out[0];
+    if (!stop) {
+      a.scal[S_RNORM2] = out[1];
+      a.scal[S_PQ] += 1.0;
+    }
+  }
+}
+
+// beta = rz_new / rz ; p = z + beta p.  Every block reads both scalars; k_pcgl_roll (next launch)
+// then moves rz_new into rz.
+__global__ void __launch_bounds__(256) k_pcgl_direction(PcgLArgs a) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const double rz = a.scal[S_RZ], rzn = a.scal[S_RZ_NEW];
+  const bool stop = a.tol > 0.0 && a.scal[S_RNORM2] <= a.tol * a.tol * a.scal[S_BNORM2];
+  const float beta = (!stop && rz > 0.0) ? (float)(rzn / rz) : 0.f;
+  if (t < a.m * 12 && !stop) a.p[t] = a.z[t] + beta * a.p[t];
+}
+__global__ void k_pcgl_roll(double* scal) { scal[S_RZ] = scal[S_RZ_NEW]; }
+
+__global__ void __launch_bounds__(256) k_pcgl_finish(PcgLArgs a, float* __restrict__ delta) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= a.m * 12) return;
+  float dv = a.d[t];
+  a.x[t] += dv;
+  delta[t] = dv;
+}
+
+static int pcg_solve_launches(mvs_deform* h) {
+  mvs_ctx* ctx = h->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t m = h->m;
+  const size_t N = (size_t)m * 12;
+  PcgLArgs a;
+  a.row_ptr = h->row_ptr.p;
+  a.col = h->col.p;
+  a.B = h->B();
+  a.Rot = h->Rot();
+  a.Minv = h->Minv.p;
+  a.rhs = h->rhs();
+  a.x = h->x.p;
+  a.r = h->pcg.p;
+  a.z = h->pcg.p + N;
+  a.p = h->pcg.p + 2 * N;
+  a.q = h->pcg.p + 3 * N;
+  a.d = h->pcg.p + 5 * N;
+  float* delta = h->pcg.p + 4 * N;
+  a.scal = h->scal.p;
+  const int grid = (int)((m + kLGroups - 1) / kLGroups);
+  MVS_TRY(h->partials.reserve((size_t)grid * 2 + 16));
+  a.partials = h->partials.p;
+  a.ticket = h->ticket.p;
+  a.m = m;
+  a.lambda = (float)h->prm.lambda;
+  a.tol = h->prm.pcg_tol;
+  ProfScope ps(ctx, "pcg_solve", 2 + 4 * std::max(h->prm.pcg_iters, 0));
+  k_pcgl_init<<<grid, kLThreads, 0, st>>>(a);
+  for (int it = 0; it < h->prm.pcg_iters; ++it) {
+    k_pcgl_product<<<grid, kLThreads, 0, st>>>(a);
+    k_pcgl_update<<<grid, kLThreads, 0, st>>>(a);
+    k_pcgl_direction<<<div_up((int64_t)N, 256), 256, 0, st>>>(a);
+    k_pcgl_roll<<<1, 1, 0, st>>>(a.scal);
+  }
+  k_pcgl_finish<<<div_up((int64_t)N, 256), 256, 0, st>>>(a, delta);
+  MVS_CUDA(cudaGetLastError());
+  return MVS_OK;
 }
 
 int pcg_solve(mvs_deform* h) {
   mvs_ctx* ctx = h->ctx;
   MVS_TRY(plan_pcg(h));
+  if (h->pcg_launch_per_phase) return pcg_solve_launches(h);
   int64_t m = h->m;
   size_t N = (size_t)m * 12;
   PcgArgs a;

@@ -200,3 +200,28 @@ def test_gn_parity_quarter_million_vertices(ctx):
                                oracle.gn_params(gn_iters=6, pcg_iters=20, corr_mode=1), tpts=tv)
     err = np.abs(out - oo).max() / diag(pts)
     assert err <= POS_TOL, err
+
+
+def test_reference_sampling_rule_on_a_large_mesh_launch_per_phase_pcg(ctx):
+    """Deformation.cpp:63-106 as written (16-NN suppression, no prescribed node count) on a
+    700K-vertex mesh gives more nodes than one cooperative grid holds (37,888 rows): the solve then
+    runs the launch-per-phase PCG.  Node ids, weights and the solve against the oracle."""
+    verts, faces = synth.cube_sphere(342)
+    pts = verts.astype(np.float32)
+    d = api.Deformation(pts, None, faces, ctx)
+    ids = d.UniformSampling(16)
+    assert np.array_equal(ids, oracle.uniform_sampling(pts, 16))
+    m = len(ids)
+    assert m > 37888, m
+    targets = synth.bend_twist(verts, 0.03)
+    d.SetTargets(targets)
+    prm = api.gn_params(gn_iters=2, pcg_iters=20, corr_mode=2)
+    d.Solve(prm)
+    out = d.Vertices()
+    widx, w = oracle.node_weights(pts, pts[ids], 4)
+    graph = oracle.node_graph(pts[ids], 8)
+    _, oo, _ = oracle.gn_solve(pts, None, ids, widx, w, graph,
+                               oracle.gn_params(gn_iters=2, pcg_iters=20, corr_mode=2), targets=targets)
+    err = np.abs(out - oo).max() / diag(pts)
+    assert err <= POS_TOL, err
+    assert np.abs(out - targets).max() < 0.5 * np.abs(pts - targets).max()
