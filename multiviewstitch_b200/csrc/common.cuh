@@ -171,6 +171,13 @@ inline int grid_for(const mvs_ctx* ctx, int64_t work_items, int block, int ctas_
   return (int)(need < 1 ? 1 : need);
 }
 
+// Raises a kernel's dynamic shared-memory limit to at least `bytes` on `device` — ONCE: the limit
+// only ever grows and is remembered per (kernel, device).  cudaFuncSetAttribute waits for the device
+// (measured on B200, scratch/cluster_overlap2.cu: eight host threads that each launch a 1 ms kernel on
+// their own stream run in 1.0 ms per round, and in 7.3 ms when each sets the attribute before its
+// launch), so calling it per launch serialises every stream of the process.
+int ensure_dyn_smem(const void* kernel, int device, int bytes);
+
 int pinned_reserve(mvs_ctx* ctx, size_t bytes);
 
 // Host <-> device helpers on the context stream.

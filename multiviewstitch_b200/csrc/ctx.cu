@@ -1,6 +1,7 @@
 // ctx.cu — context lifetime, error string, profiling scopes, launch accounting.
 #include <algorithm>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -114,6 +115,17 @@ int ctx_resolve_prof(mvs_ctx* ctx) {
     ctx->event_pool.push_back(p.stop);
   }
   ctx->pending.clear();
+  return MVS_OK;
+}
+
+int ensure_dyn_smem(const void* kernel, int device, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> limit;
+  std::lock_guard<std::mutex> lk(mu);
+  int& cur = limit[std::make_pair(kernel, device)];
+  if (bytes <= cur || bytes <= 48 * 1024) return MVS_OK;
+  MVS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  cur = bytes;
   return MVS_OK;
 }
 
@@ -290,6 +302,10 @@ int mvs_ctx_create(mvs_ctx** out, int device, void* stream) {
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
       unsigned long long keep = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      if (getenv("MVS_POOL_NO_INTERNAL_DEPS")) {
+        int off = 0;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
+      }
     }
     cudaGetLastError();
   }

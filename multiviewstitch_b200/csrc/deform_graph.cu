@@ -126,44 +126,66 @@ __global__ void __launch_bounds__(256)
 
 // Farthest point sampling of a small point set (n <= 8 x kFpsCap: the C1/C4 view meshes) in ONE
 // launch of one thread-block cluster.  The per-step launch above costs ~7 us per node whatever n is;
-// here the 8 CTAs keep their share of the points and of the running minimum distances in shared
-// memory, publish one candidate each (value, index, position) in a double-buffered slot, meet at
-// the cluster barrier, and every warp reads the 8 candidates through distributed shared memory and
-// picks the winner — one cluster barrier per node, no global traffic.  Same result as the oracle
-// (orc_sample_fps): FMA-free float32 distances, farthest point with the lowest index on ties.
+// here every thread keeps its PPT points AND their running minimum distances in registers (the loop
+// over them is fully unrolled: 12 instructions per point, no shared-memory traffic), the argmax of a
+// warp is two REDUX instructions (maximum of the float bits — distances are non-negative — then the
+// minimum index among the lanes that hold it), the CTAs publish one candidate each (value, index,
+// position) in a double-buffered slot, meet at the cluster barrier, and every warp reads the 8
+// candidates through distributed shared memory and picks the winner — one cluster barrier per node,
+// no global traffic.  Same result as the oracle (orc_sample_fps): FMA-free float32 distances,
+// farthest point with the lowest index on ties.
 namespace cg = cooperative_groups;
 constexpr int kFpsCluster = 8;
 constexpr int kFpsThreads = 512;
-constexpr int kFpsCap = 12288;  // points per CTA (16 B each in shared memory)
+constexpr int kFpsMaxPpt = 24;                        // points per thread
+constexpr int kFpsCap = kFpsThreads * kFpsMaxPpt;     // points per CTA (12 B each in shared memory)
 
 struct FpsCand {
-  float v;
+  unsigned v;  // float bits of the running minimum distance (>= 0: ordered like unsigned)
   int i;
   float x, y, z;
 };
 
-__global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThreads, 1)
+// (max value, lowest index among the lanes holding it) over the lanes of `mask`
+__device__ __forceinline__ void warp_argmax(unsigned mask, unsigned& vb, int& bi) {
+  unsigned vmax = __reduce_max_sync(mask, vb);
+  int cand = vb == vmax ? bi : 0x7fffffff;
+  bi = __reduce_min_sync(mask, cand);
+  vb = vmax;
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(kFpsThreads, 1)
     k_fps_cluster(const float4* __restrict__ pts, int n, int n_nodes, int first,
                   int* __restrict__ out_ids) {
   extern __shared__ float fps_smem[];
-  __shared__ float sv[kFpsThreads / 32];
+  __shared__ unsigned sv[kFpsThreads / 32];
   __shared__ int si[kFpsThreads / 32];
   __shared__ FpsCand cand[2];
+  const unsigned full = 0xffffffffu;
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
-  const int per = (n + kFpsCluster - 1) / kFpsCluster;
+  const int nblk = (int)cl.num_blocks();  // cluster size is a launch attribute (<= kFpsCluster)
+  const int per = (n + nblk - 1) / nblk;
   const int b0 = rank * per;
   const int cnt = max(0, min(per, n - b0));
+  // the CTA's coordinates once more in shared memory: the winner's position is read from there
   float* xs = fps_smem;
   float* ys = xs + per;
   float* zs = ys + per;
-  float* md = zs + per;
-  for (int k = threadIdx.x; k < cnt; k += kFpsThreads) {
-    float4 p = __ldg(pts + b0 + k);
-    xs[k] = p.x;
-    ys[k] = p.y;
-    zs[k] = p.z;
-    md[k] = INFINITY;
+  float x[PPT], y[PPT], z[PPT], md[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int k = threadIdx.x + j * kFpsThreads;
+    if (k < cnt) {
+      float4 p = __ldg(pts + b0 + k);
+      x[j] = p.x; y[j] = p.y; z[j] = p.z;
+      md[j] = INFINITY;
+      xs[k] = p.x; ys[k] = p.y; zs[k] = p.z;
+    } else {
+      x[j] = y[j] = z[j] = 0.f;
+      md[j] = -1.0f;  // never updated (d >= 0), never selected (best starts at -1, strict >)
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 c = __ldg(pts + first);
@@ -173,48 +195,31 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
     if (rank == 0 && threadIdx.x == 0) out_ids[s] = cur;
     float best = -1.0f;
     int bi = 0x7fffffff;
-    for (int k = threadIdx.x; k < cnt; k += kFpsThreads) {
-      float d = dist2_rn(xs[k], ys[k], zs[k], c.x, c.y, c.z);
-      float m = md[k];
-      if (d < m) {
-        m = d;
-        md[k] = d;
-      }
-      if (m > best || (m == best && b0 + k < bi)) {
-        best = m;
-        bi = b0 + k;
-      }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) {
-        best = ov;
-        bi = oi;
+    for (int j = 0; j < PPT; ++j) {  // ascending index: strict > keeps the lowest index of a tie
+      float d = dist2_rn(x[j], y[j], z[j], c.x, c.y, c.z);
+      float m = fminf(md[j], d);
+      md[j] = m;
+      if (m > best) {
+        best = m;
+        bi = b0 + threadIdx.x + j * kFpsThreads;
       }
     }
+    unsigned vb = best < 0.f ? 0u : __float_as_uint(best);
+    warp_argmax(full, vb, bi);
     if (lane == 0) {
-      sv[warp] = best;
+      sv[warp] = vb;
       si[warp] = bi;
     }
     __syncthreads();
     const int slot = s & 1;
     if (warp == 0) {
-      best = lane < kFpsThreads / 32 ? sv[lane] : -1.0f;
+      vb = lane < kFpsThreads / 32 ? sv[lane] : 0u;
       bi = lane < kFpsThreads / 32 ? si[lane] : 0x7fffffff;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) {
-          best = ov;
-          bi = oi;
-        }
-      }
+      warp_argmax(full, vb, bi);
       if (lane == 0) {
         FpsCand cd;
-        cd.v = best;
+        cd.v = vb;
         cd.i = bi;
         const bool has = bi != 0x7fffffff;
         cd.x = has ? xs[bi - b0] : 0.f;
@@ -227,27 +232,48 @@ __global__ void __cluster_dims__(kFpsCluster, 1, 1) __launch_bounds__(kFpsThread
     // passed the barrier of the step in between (so nobody still reads it)
     cl.sync();
     FpsCand w;
-    w.v = -2.0f;
+    w.v = 0u;
     w.i = 0x7fffffff;
     w.x = w.y = w.z = 0.f;
-    if (lane < kFpsCluster) w = *cl.map_shared_rank(&cand[slot], lane);
-#pragma unroll
-    for (int o = kFpsCluster / 2; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, w.v, o);
-      int oi = __shfl_xor_sync(0xffffffffu, w.i, o);
-      float ox = __shfl_xor_sync(0xffffffffu, w.x, o);
-      float oy = __shfl_xor_sync(0xffffffffu, w.y, o);
-      float oz = __shfl_xor_sync(0xffffffffu, w.z, o);
-      if (ov > w.v || (ov == w.v && oi < w.i)) {
-        w.v = ov; w.i = oi; w.x = ox; w.y = oy; w.z = oz;
-      }
-    }
-    cur = __shfl_sync(0xffffffffu, w.i, 0);
-    c.x = __shfl_sync(0xffffffffu, w.x, 0);
-    c.y = __shfl_sync(0xffffffffu, w.y, 0);
-    c.z = __shfl_sync(0xffffffffu, w.z, 0);
+    if (lane < nblk) w = *cl.map_shared_rank(&cand[slot], lane);
+    unsigned wv = w.v;
+    int wi = w.i;
+    warp_argmax(full, wv, wi);
+    // the lane that holds the winner hands out its position (a CTA without points has index INT_MAX
+    // and loses every tie; the winner index is unique)
+    const unsigned holders = __ballot_sync(full, lane < nblk && w.v == wv && w.i == wi);
+    const int src = holders ? __ffs((int)holders) - 1 : 0;
+    cur = wi;
+    c.x = __shfl_sync(full, w.x, src);
+    c.y = __shfl_sync(full, w.y, src);
+    c.z = __shfl_sync(full, w.z, src);
   }
   cl.sync();  // no CTA leaves while a peer may still read its candidate slots
+}
+
+template <int PPT>
+static int launch_fps_cluster(mvs_ctx* ctx, const float4* pts, int n, int n_nodes, int first, int* out,
+                              int nblk) {
+  int per = (n + nblk - 1) / nblk;
+  size_t smem = (size_t)per * 12;
+  auto kern = k_fps_cluster<PPT>;
+  MVS_TRY(ensure_dyn_smem((const void*)kern, ctx->device, kFpsCap * 12));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(nblk);
+  cfg.blockDim = dim3(kFpsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nblk;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfScope ps(ctx, "fps_cluster");
+  MVS_CUDA(cudaLaunchKernelEx(&cfg, kern, pts, n, n_nodes, first, out));
+  return MVS_OK;
 }
 
 // ------------------------------------------------------------------ per-vertex node weights
@@ -1086,15 +1112,30 @@ int mvs_deform_sample_fps(mvs_deform* h, int64_t n_nodes, int64_t first_vertex) 
     // small set: the whole sampling in one cluster launch
     DevBuf<int> out;
     MVS_TRY(out.reserve((size_t)n_nodes));
-    int per = (int)((n + kFpsCluster - 1) / kFpsCluster);
-    size_t smem = (size_t)per * 16;
-    MVS_CUDA(cudaFuncSetAttribute(k_fps_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kFpsCap * 16)));
-    {
-      ProfScope ps(ctx, "fps_cluster");
-      k_fps_cluster<<<kFpsCluster, kFpsThreads, smem, ctx->stream>>>(h->v0.p, (int)n, (int)n_nodes,
-                                                                      (int)first_vertex, out.p);
+    // cluster size: the fewest CTAs that hold the set at <= 12 points per thread (fewer CTAs leave
+    // room for other streams' samplings), points per thread: the smallest unrolled variant
+    int nblk = kFpsCluster;
+    if (const char* env = getenv("MVS_FPS_CLUSTER")) {
+      int e = atoi(env);
+      if (e == 1 || e == 2 || e == 4 || e == 8) nblk = e;
     }
+    while (nblk < kFpsCluster && (int64_t)nblk * kFpsCap < n) nblk *= 2;
+    const int per = (int)((n + nblk - 1) / nblk);
+    const int ppt = (per + kFpsThreads - 1) / kFpsThreads;
+    const float4* P = h->v0.p;
+    const int nn = (int)n, nd = (int)n_nodes, f0 = (int)first_vertex;
+    if (ppt <= 3)
+      MVS_TRY(launch_fps_cluster<3>(ctx, P, nn, nd, f0, out.p, nblk));
+    else if (ppt <= 6)
+      MVS_TRY(launch_fps_cluster<6>(ctx, P, nn, nd, f0, out.p, nblk));
+    else if (ppt <= 9)
+      MVS_TRY(launch_fps_cluster<9>(ctx, P, nn, nd, f0, out.p, nblk));
+    else if (ppt <= 12)
+      MVS_TRY(launch_fps_cluster<12>(ctx, P, nn, nd, f0, out.p, nblk));
+    else if (ppt <= 16)
+      MVS_TRY(launch_fps_cluster<16>(ctx, P, nn, nd, f0, out.p, nblk));
+    else
+      MVS_TRY(launch_fps_cluster<kFpsMaxPpt>(ctx, P, nn, nd, f0, out.p, nblk));
     MVS_CUDA(cudaGetLastError());
     std::vector<int32_t> ids((size_t)n_nodes);
     MVS_TRY(d2h_sync(ctx, ids.data(), out.p, sizeof(int) * n_nodes));

@@ -526,8 +526,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_pcg_persistent(PcgArgs a) {
 template <int RS, int T>
 static int launch_pcg_t(mvs_deform* h, PcgArgs& a, int grid, size_t smem) {
   auto kern = k_pcg_persistent<RS, T>;
-  if (smem > 48 * 1024)
-    MVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the limit was raised once, by the planner (ensure_dyn_smem): no attribute call per launch
   void* args[] = {&a};
   MVS_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(T), args, smem, h->ctx->stream));
   return MVS_OK;
@@ -542,8 +541,10 @@ template <int RS, int T>
 static int max_coresident_t(size_t smem, int num_sms, int* out) {
   auto kern = k_pcg_persistent<RS, T>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    // raised once to the planner's ceiling (200 KB), not per candidate size
+    if (ensure_dyn_smem((const void*)kern, dev, 200 * 1024) != MVS_OK) {
       cudaGetLastError();
       *out = 0;
       return MVS_OK;

@@ -28,10 +28,24 @@
 
 namespace mvs {
 
+// host scratch of one worker, kept between pairs and calls: a fresh 7 MB std::vector per pair costs a
+// zero fill plus an mmap/munmap pair, and with a dozen workers those serialise on the process's
+// address-space lock
+struct PairScratch {
+  std::vector<int32_t> uv, okf, keep, fa;
+  std::vector<double> p, q, pk, qk, va;
+};
+
 struct StitchPool {
   std::mutex mu;
   std::vector<mvs_ctx*> workers;
+  std::vector<PairScratch*> scratch;
 };
+
+template <class T>
+static inline void ensure(std::vector<T>& v, size_t n) {
+  if (v.size() < n) v.resize(n);
+}
 
 static std::mutex g_pools_mu;
 static std::map<mvs_ctx*, StitchPool*> g_pools;
@@ -56,6 +70,7 @@ void stitch_pool_release(mvs_ctx* parent) {
     g_pools.erase(it);
   }
   for (mvs_ctx* w : p->workers) mvs_ctx_destroy(w);
+  for (PairScratch* sc : p->scratch) delete sc;
   delete p;
 }
 
@@ -66,19 +81,25 @@ static const char* kStageNames[ST_COUNT] = {"unproject", "remove_outliers", "srt
                                             "apply_srt", "deform_create", "sample_fps", "set_target",
                                             "solve(graph+gn)", "get_vertices", "model2depth"};
 struct StageClock {
-  double* acc;
+  double* acc;  // [ST_COUNT] milliseconds, then [ST_COUNT] kernel launches
+  mvs_ctx* ctx;
+  int64_t l0;
   std::chrono::steady_clock::time_point t0;
-  explicit StageClock(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  StageClock(double* a, mvs_ctx* c) : acc(a), ctx(c), l0(c->launch_count), t0(std::chrono::steady_clock::now()) {}
   void lap(int stage) {
     auto t1 = std::chrono::steady_clock::now();
-    if (acc) acc[stage] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (acc) {
+      acc[stage] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+      acc[ST_COUNT + stage] += (double)(ctx->launch_count - l0);
+    }
+    l0 = ctx->launch_count;
     t0 = t1;
   }
 };
 
-static int run_pair(mvs_ctx* ctx, const mvs_pair_job& job, const mvs_pair_params& prm,
+static int run_pair(mvs_ctx* ctx, PairScratch& S, const mvs_pair_job& job, const mvs_pair_params& prm,
                     mvs_pair_result& out, double* stage_ms) {
-  StageClock clk(stage_ms);
+  StageClock clk(stage_ms, ctx);
   const mvs_camera* ca = job.cam_a;
   const mvs_camera* cb = job.cam_b;
   const int64_t nm = job.n_matches;
@@ -86,9 +107,17 @@ static int run_pair(mvs_ctx* ctx, const mvs_pair_job& job, const mvs_pair_params
   out.status = MVS_OK;
   out.n_kept = out.n_template = out.n_facets = out.n_target = 0;
   // ---- matched pixels -> 3-D matches
-  std::vector<int32_t> uv((size_t)nm * 2);
-  std::vector<double> p((size_t)nm * 3), q((size_t)nm * 3);
-  std::vector<int32_t> okf((size_t)nm);
+  std::vector<int32_t>&uv = S.uv, &okf = S.okf, &keep = S.keep, &fa = S.fa;
+  std::vector<double>&p = S.p, &q = S.q, &pk = S.pk, &qk = S.qk, &va = S.va;
+  ensure(uv, (size_t)nm * 2);
+  ensure(p, (size_t)nm * 3);
+  ensure(q, (size_t)nm * 3);
+  ensure(okf, (size_t)nm);
+  ensure(keep, (size_t)nm);
+  ensure(pk, (size_t)nm * 3);
+  ensure(qk, (size_t)nm * 3);
+  ensure(va, (size_t)npx * 3);
+  ensure(fa, (size_t)6 * (ca->w - 1) * (ca->h - 1));
   for (int64_t i = 0; i < nm; ++i) {
     uv[2 * i] = job.matches[4 * i];
     uv[2 * i + 1] = job.matches[4 * i + 1];
@@ -103,7 +132,6 @@ static int run_pair(mvs_ctx* ctx, const mvs_pair_job& job, const mvs_pair_params
                                q.data(), okf.data()));
   clk.lap(ST_UNPROJ);
   // ---- RemoveOutliers
-  std::vector<int32_t> keep((size_t)nm);
   int64_t nk = 0;
   mvs_outlier_params op = prm.outliers;
   op.seed = job.seed;
@@ -117,7 +145,6 @@ static int run_pair(mvs_ctx* ctx, const mvs_pair_job& job, const mvs_pair_params
     return MVS_ERR_DEGENERATE;
   }
   // ---- closed-form SRT on the inliers + residual
-  std::vector<double> pk((size_t)nk * 3), qk((size_t)nk * 3);
   for (int64_t i = 0; i < nk; ++i) {
     memcpy(&pk[3 * i], &p[3 * (size_t)keep[i]], sizeof(double) * 3);
     memcpy(&qk[3 * i], &q[3 * (size_t)keep[i]], sizeof(double) * 3);
@@ -136,8 +163,6 @@ static int run_pair(mvs_ctx* ctx, const mvs_pair_job& job, const mvs_pair_params
   clk.lap(ST_SRT);
   // ---- template = view-1 mesh, moved into the frame of view 2
   int64_t np = 0, nf = 0;
-  std::vector<double> va((size_t)npx * 3);
-  std::vector<int32_t> fa((size_t)6 * (ca->w - 1) * (ca->h - 1));
   MVS_TRY(mvs_depth2model(ctx, job.depth_a, ca, prm.min_dsp, prm.max_dsp, prm.smooth_threshold,
                           va.data(), nullptr, fa.data(), &np, &nf));
   clk.lap(ST_D2M);
@@ -229,6 +254,7 @@ int mvs_stitch_pairs(mvs_ctx* ctx, const mvs_pair_job* jobs, int64_t n_jobs,
     mvs_ctx* w = nullptr;
     MVS_TRY(mvs_ctx_create(&w, ctx->device, nullptr));
     pool->workers.push_back(w);
+    pool->scratch.push_back(new PairScratch());
   }
   // the workers start after everything already queued on the parent's stream
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -237,7 +263,7 @@ int mvs_stitch_pairs(mvs_ctx* ctx, const mvs_pair_job* jobs, int64_t n_jobs,
   std::vector<int64_t> launches((size_t)W, 0);
   const char* trace_env = getenv("MVS_STITCH_TRACE");
   const bool trace = trace_env && trace_env[0] == '1';
-  std::vector<double> stage_ms(trace ? (size_t)W * ST_COUNT : 0, 0.0);
+  std::vector<double> stage_ms(trace ? (size_t)W * 2 * ST_COUNT : 0, 0.0);
   auto body = [&](int k) {
     mvs_ctx* w = pool->workers[k];
     if (ctx_ensure_device(w) != MVS_OK) return;
@@ -245,7 +271,7 @@ int mvs_stitch_pairs(mvs_ctx* ctx, const mvs_pair_job* jobs, int64_t n_jobs,
     for (;;) {
       int64_t i = next.fetch_add(1);
       if (i >= n_jobs) break;
-      int rc = run_pair(w, jobs[i], *params, results[i], trace ? &stage_ms[(size_t)k * ST_COUNT] : nullptr);
+      int rc = run_pair(w, *pool->scratch[k], jobs[i], *params, results[i], trace ? &stage_ms[(size_t)k * 2 * ST_COUNT] : nullptr);
       results[i].status = rc;
       if (rc != MVS_OK && errs[k].empty()) errs[k] = mvs_last_error();
     }
@@ -264,9 +290,12 @@ int mvs_stitch_pairs(mvs_ctx* ctx, const mvs_pair_job* jobs, int64_t n_jobs,
     fprintf(stderr, "[mvs_stitch_pairs] %lld pairs, %d workers, ms per pair (wall, per worker thread):",
             (long long)n_jobs, W);
     for (int s = 0; s < ST_COUNT; ++s) {
-      double sum = 0;
-      for (int k = 0; k < W; ++k) sum += stage_ms[(size_t)k * ST_COUNT + s];
-      fprintf(stderr, " %s %.3f", kStageNames[s], sum / (double)n_jobs);
+      double sum = 0, ln = 0;
+      for (int k = 0; k < W; ++k) {
+        sum += stage_ms[(size_t)k * 2 * ST_COUNT + s];
+        ln += stage_ms[(size_t)k * 2 * ST_COUNT + ST_COUNT + s];
+      }
+      fprintf(stderr, " %s %.3f (%.0f launches)", kStageNames[s], sum / (double)n_jobs, ln / (double)n_jobs);
     }
     fprintf(stderr, "\n");
   }
