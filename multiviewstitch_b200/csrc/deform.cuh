@@ -167,6 +167,15 @@ int arap_solve(mvs_deform* h, const double* ctrl_xyz_host, const int32_t* ctrl_i
 
 // pcg.cu
 int pcg_solve(mvs_deform* h);
+// device-resident building blocks of mvs_stitch_pairs (pipeline.cu, pointset.cu, deform_api.cu)
+int depth2model_dev(mvs_ctx* ctx, const float* inv_depth_host, const mvs_camera* cam, double min_dsp,
+                    double max_dsp, double smooth_threshold, DevBuf<double>* xyz, DevBuf<int>* tex,
+                    DevBuf<int>* facets, int64_t* n_points, int64_t* n_facets);
+int apply_srt_dev_f64(mvs_ctx* ctx, double* xyz_dev, int64_t n, double scale, const double R[9],
+                      const double t[3]);
+int deform_create_dev_f64(mvs_ctx* ctx, const double* xyz_dev, int64_t n, const int* facets_dev,
+                          int64_t nf, mvs_deform** out);
+int deform_vertices_dev(mvs_deform* h, const float4** cur);
 // model2depth.cu: inverse-depth image (host) -> valid world points compacted in pixel order (device)
 int unproject_compact_f4(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam, double min_dsp,
                          double max_dsp, DevBuf<float4>& out, DevBuf<int>& scan_tmp, int64_t* count);

@@ -305,6 +305,53 @@ int mvs_deform_create_f32(mvs_ctx* ctx, const float* pts, const float* normals, 
   return finish_create(h, facets, out);
 }
 
+}  // extern "C"
+
+namespace mvs {
+__global__ void k_xyz_f64_to_f4_dev(const double* __restrict__ in, float4* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_float4((float)in[3 * i], (float)in[3 * i + 1], (float)in[3 * i + 2], 0.f);
+}
+
+// Deformation(points, normals = none, facets) from DEVICE-resident doubles and facets: the same
+// float32 rounding as mvs_deform_create (upload, then cast on the device), no host copies.  The
+// facets come from depth2model_dev and index [0, n) by construction.
+int deform_create_dev_f64(mvs_ctx* ctx, const double* xyz_dev, int64_t n, const int* facets_dev,
+                          int64_t nf, mvs_deform** out) {
+  mvs_deform* h = nullptr;
+  int32_t dummy = 0;
+  MVS_TRY(create_common(ctx, n, nf > 0 ? &dummy : nullptr, 0, out, &h));
+  h->nf = nf;
+  int st = h->v0.reserve((size_t)n);
+  if (st == MVS_OK) st = h->nrm0.reserve((size_t)n);
+  if (st == MVS_OK) st = h->facets.reserve((size_t)3 * nf + 1);
+  if (st == MVS_OK) {
+    cudaStream_t s = h->ctx->stream;
+    ProfScope ps(h->ctx, "convert_xyz");
+    k_xyz_f64_to_f4_dev<<<div_up(n, 256), 256, 0, s>>>(xyz_dev, h->v0.p, n);
+    cudaMemsetAsync(h->nrm0.p, 0, sizeof(float4) * n, s);
+    if (nf > 0)
+      cudaMemcpyAsync(h->facets.p, facets_dev, sizeof(int) * 3 * nf, cudaMemcpyDeviceToDevice, s);
+    if (cudaGetLastError() != cudaSuccess) st = MVS_ERR_CUDA;
+  }
+  if (st != MVS_OK) {
+    mvs_deform_destroy(h);
+    return st;
+  }
+  *out = h;
+  return MVS_OK;
+}
+
+// the deformed vertices (float4, original order) where they lie on the device
+int deform_vertices_dev(mvs_deform* h, const float4** cur) {
+  *cur = h->cur_valid ? h->cur0.p : h->v0.p;
+  return MVS_OK;
+}
+}  // namespace mvs
+
+extern "C" {
+
 int mvs_deform_destroy(mvs_deform* h) {
   if (!h) return MVS_OK;
   cudaSetDevice(h->ctx->device);

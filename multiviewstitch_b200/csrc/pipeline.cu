@@ -180,6 +180,61 @@ __global__ void k_check_consistency(float* __restrict__ depth, CamK cur,
   }
 }
 
+// Depth2Model/Depth2Model.cpp:7-82 with the results left on the device (the public entry point
+// copies them out; mvs_stitch_pairs keeps them there).  Null output buffers = counts only.
+int depth2model_dev(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam, double min_dsp,
+                    double max_dsp, double smooth_threshold, DevBuf<double>* dxyz, DevBuf<int>* dtex,
+                    DevBuf<int>* dfac, int64_t* n_points, int64_t* n_facets) {
+  cudaStream_t st = ctx->stream;
+  int w = cam->w, h = cam->h;
+  int64_t npx = (int64_t)w * h, nq = (int64_t)(w - 1) * (h - 1);
+  DevBuf<float> d;
+  DevBuf<int> tab, cnt, scan_tmp;
+  MVS_TRY(d.reserve((size_t)npx));
+  MVS_TRY(tab.reserve((size_t)npx + 2));
+  MVS_TRY(cnt.reserve((size_t)(nq > 0 ? nq : 0) + 2));
+  MVS_TRY(h2d(ctx, d.p, inv_depth, sizeof(float) * npx));
+  // Depth2Model.cpp:45: float threshold from double operands
+  float thr = (float)(smooth_threshold * (max_dsp - min_dsp) / 100);
+  {
+    ProfScope ps(ctx, "d2m_valid");
+    k_d2m_valid<<<div_up(npx, 256), 256, 0, st>>>(d.p, npx, min_dsp, max_dsp, tab.p);
+  }
+  MVS_CUDA(cudaMemsetAsync(tab.p + npx, 0, sizeof(int) * 2, st));
+  MVS_TRY(exclusive_scan_inplace(ctx, tab.p, npx, scan_tmp));
+  if (nq > 0) {
+    {
+      ProfScope ps(ctx, "d2m_count");
+      k_d2m_count<<<div_up(nq, 256), 256, 0, st>>>(d.p, w, h, min_dsp, max_dsp, thr, cnt.p);
+    }
+    MVS_CUDA(cudaMemsetAsync(cnt.p + nq, 0, sizeof(int) * 2, st));
+    MVS_TRY(exclusive_scan_inplace(ctx, cnt.p, nq, scan_tmp));
+  }
+  // both counts in one round trip
+  int np = 0, nf = 0;
+  MVS_CUDA(cudaMemcpyAsync(&np, tab.p + npx, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (nq > 0) MVS_CUDA(cudaMemcpyAsync(&nf, cnt.p + nq, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MVS_CUDA(cudaStreamSynchronize(st));
+  if (n_points) *n_points = np;
+  if (n_facets) *n_facets = nf;
+  if (np > 0 && (dxyz || dtex)) {
+    if (dxyz) MVS_TRY(dxyz->reserve((size_t)np * 3));
+    if (dtex) MVS_TRY(dtex->reserve((size_t)np));
+    ProfScope ps(ctx, "d2m_points");
+    k_d2m_points<<<div_up(npx, 256), 256, 0, st>>>(d.p, tab.p, npx, to_camk(*cam), min_dsp, max_dsp,
+                                                   dxyz ? dxyz->p : nullptr, dtex ? dtex->p : nullptr);
+  }
+  if (nf > 0 && dfac) {
+    MVS_TRY(dfac->reserve((size_t)nf * 3));
+    ProfScope ps(ctx, "d2m_facets");
+    k_d2m_facets<<<div_up(nq, 256), 256, 0, st>>>(d.p, w, h, min_dsp, max_dsp, thr, tab.p, cnt.p,
+                                                  dfac->p);
+  }
+  MVS_CUDA(cudaGetLastError());
+  // d, tab, cnt are released in stream order behind the kernels that read them
+  return MVS_OK;
+}
+
 static int resolve(mvs_ctx*& ctx) {
   if (!ctx) ctx = default_ctx();
   if (!ctx) return MVS_ERR_NO_DEVICE;
@@ -269,62 +324,18 @@ int mvs_depth2model(mvs_ctx* ctx, const float* inv_depth, const mvs_camera* cam,
     set_error("depth2model: bad argument");
     return MVS_ERR_INVALID_ARG;
   }
-  cudaStream_t st = ctx->stream;
-  int w = cam->w, h = cam->h;
-  int64_t npx = (int64_t)w * h, nq = (int64_t)(w - 1) * (h - 1);
-  DevBuf<float> d;
-  DevBuf<int> tab, cnt, scan_tmp, dtex, dfac;
   DevBuf<double> dxyz;
-  MVS_TRY(d.reserve((size_t)npx));
-  MVS_TRY(tab.reserve((size_t)npx + 2));
-  MVS_TRY(cnt.reserve((size_t)(nq > 0 ? nq : 0) + 2));
-  MVS_TRY(h2d(ctx, d.p, inv_depth, sizeof(float) * npx));
-  // Depth2Model.cpp:45: float threshold from double operands
-  float thr = (float)(smooth_threshold * (max_dsp - min_dsp) / 100);
-  {
-    ProfScope ps(ctx, "d2m_valid");
-    k_d2m_valid<<<div_up(npx, 256), 256, 0, st>>>(d.p, npx, min_dsp, max_dsp, tab.p);
-  }
-  MVS_CUDA(cudaMemsetAsync(tab.p + npx, 0, sizeof(int) * 2, st));
-  MVS_TRY(exclusive_scan_inplace(ctx, tab.p, npx, scan_tmp));
-  int np = 0, nf = 0;
-  MVS_TRY(d2h_sync(ctx, &np, tab.p + npx, sizeof(int)));
-  if (nq > 0) {
-    {
-      ProfScope ps(ctx, "d2m_count");
-      k_d2m_count<<<div_up(nq, 256), 256, 0, st>>>(d.p, w, h, min_dsp, max_dsp, thr, cnt.p);
-    }
-    MVS_CUDA(cudaMemsetAsync(cnt.p + nq, 0, sizeof(int) * 2, st));
-    MVS_TRY(exclusive_scan_inplace(ctx, cnt.p, nq, scan_tmp));
-    MVS_TRY(d2h_sync(ctx, &nf, cnt.p + nq, sizeof(int)));
-  }
+  DevBuf<int> dtex, dfac;
+  int64_t np = 0, nf = 0;
+  MVS_TRY(depth2model_dev(ctx, inv_depth, cam, min_dsp, max_dsp, smooth_threshold,
+                          out_xyz ? &dxyz : nullptr, tex_index ? &dtex : nullptr,
+                          facets ? &dfac : nullptr, &np, &nf));
   if (n_points) *n_points = np;
   if (n_facets) *n_facets = nf;
-  if (np > 0 && (out_xyz || tex_index)) {
-    if (out_xyz) MVS_TRY(dxyz.reserve((size_t)np * 3));
-    if (tex_index) MVS_TRY(dtex.reserve((size_t)np));
-    {
-      ProfScope ps(ctx, "d2m_points");
-      k_d2m_points<<<div_up(npx, 256), 256, 0, st>>>(d.p, tab.p, npx, to_camk(*cam), min_dsp, max_dsp,
-                                                     out_xyz ? dxyz.p : nullptr,
-                                                     tex_index ? dtex.p : nullptr);
-    }
-    if (out_xyz)
-      MVS_TRY(d2h_async(ctx, out_xyz, dxyz.p, sizeof(double) * 3 * np));
-    if (tex_index)
-      MVS_TRY(d2h_async(ctx, tex_index, dtex.p, sizeof(int) * np));
-  }
-  if (nf > 0 && facets) {
-    MVS_TRY(dfac.reserve((size_t)nf * 3));
-    {
-      ProfScope ps(ctx, "d2m_facets");
-      k_d2m_facets<<<div_up(nq, 256), 256, 0, st>>>(d.p, w, h, min_dsp, max_dsp, thr, tab.p, cnt.p,
-                                                    dfac.p);
-    }
-    MVS_TRY(d2h_async(ctx, facets, dfac.p, sizeof(int) * 3 * nf));
-  }
-  MVS_CUDA(cudaGetLastError());
-  MVS_CUDA(cudaStreamSynchronize(st));
+  if (np > 0 && out_xyz) MVS_TRY(d2h_async(ctx, out_xyz, dxyz.p, sizeof(double) * 3 * np));
+  if (np > 0 && tex_index) MVS_TRY(d2h_async(ctx, tex_index, dtex.p, sizeof(int) * np));
+  if (nf > 0 && facets) MVS_TRY(d2h_async(ctx, facets, dfac.p, sizeof(int) * 3 * nf));
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   return MVS_OK;
 }
 

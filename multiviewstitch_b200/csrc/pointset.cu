@@ -751,6 +751,16 @@ static int local_core_impl(PsWork& w, const double* d_src, const int* d_sl, int6
   return MVS_OK;
 }
 
+// v = s R p + t in place on device doubles (n x 3): the kernel mvs_apply_srt runs, without the trip
+// through host memory (mvs_stitch_pairs)
+int apply_srt_dev_f64(mvs_ctx* ctx, double* xyz_dev, int64_t n, double scale, const double R[9],
+                      const double t[3]) {
+  if (n <= 0) return MVS_OK;
+  PsWork w;
+  MVS_TRY(w.init(ctx, n));
+  return ps_apply(w, xyz_dev, nullptr, n, kAll, scale, R, t, 0);
+}
+
 static int upload_f64(mvs_ctx* ctx, const double* host, int64_t n3, DevBuf<double>& d) {
   MVS_TRY(d.reserve((size_t)(n3 > 0 ? n3 : 1)));
   if (n3 > 0) MVS_TRY(h2d(ctx, d.p, host, sizeof(double) * n3));

@@ -24,7 +24,7 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include "deform.cuh"
 
 namespace mvs {
 
@@ -32,8 +32,8 @@ namespace mvs {
 // zero fill plus an mmap/munmap pair, and with a dozen workers those serialise on the process's
 // address-space lock
 struct PairScratch {
-  std::vector<int32_t> uv, okf, keep, fa;
-  std::vector<double> p, q, pk, qk, va;
+  std::vector<int32_t> uv, okf, keep;
+  std::vector<double> p, q, pk, qk;
 };
 
 struct StitchPool {
@@ -107,8 +107,8 @@ static int run_pair(mvs_ctx* ctx, PairScratch& S, const mvs_pair_job& job, const
   out.status = MVS_OK;
   out.n_kept = out.n_template = out.n_facets = out.n_target = 0;
   // ---- matched pixels -> 3-D matches
-  std::vector<int32_t>&uv = S.uv, &okf = S.okf, &keep = S.keep, &fa = S.fa;
-  std::vector<double>&p = S.p, &q = S.q, &pk = S.pk, &qk = S.qk, &va = S.va;
+  std::vector<int32_t>&uv = S.uv, &okf = S.okf, &keep = S.keep;
+  std::vector<double>&p = S.p, &q = S.q, &pk = S.pk, &qk = S.qk;
   ensure(uv, (size_t)nm * 2);
   ensure(p, (size_t)nm * 3);
   ensure(q, (size_t)nm * 3);
@@ -116,8 +116,6 @@ static int run_pair(mvs_ctx* ctx, PairScratch& S, const mvs_pair_job& job, const
   ensure(keep, (size_t)nm);
   ensure(pk, (size_t)nm * 3);
   ensure(qk, (size_t)nm * 3);
-  ensure(va, (size_t)npx * 3);
-  ensure(fa, (size_t)6 * (ca->w - 1) * (ca->h - 1));
   for (int64_t i = 0; i < nm; ++i) {
     uv[2 * i] = job.matches[4 * i];
     uv[2 * i + 1] = job.matches[4 * i + 1];
@@ -161,10 +159,13 @@ static int run_pair(mvs_ctx* ctx, PairScratch& S, const mvs_pair_job& job, const
     MVS_TRY(rc);
   }
   clk.lap(ST_SRT);
-  // ---- template = view-1 mesh, moved into the frame of view 2
+  // ---- template = view-1 mesh, moved into the frame of view 2: stays on the device from the depth
+  // map to the deformation handle (the stage-by-stage form moves it through host vectors three times)
   int64_t np = 0, nf = 0;
-  MVS_TRY(mvs_depth2model(ctx, job.depth_a, ca, prm.min_dsp, prm.max_dsp, prm.smooth_threshold,
-                          va.data(), nullptr, fa.data(), &np, &nf));
+  DevBuf<double> dxyz;
+  DevBuf<int> dfac;
+  MVS_TRY(depth2model_dev(ctx, job.depth_a, ca, prm.min_dsp, prm.max_dsp, prm.smooth_threshold, &dxyz,
+                          nullptr, &dfac, &np, &nf));
   clk.lap(ST_D2M);
   out.n_template = np;
   out.n_facets = nf;
@@ -172,13 +173,13 @@ static int run_pair(mvs_ctx* ctx, PairScratch& S, const mvs_pair_job& job, const
     set_error("stitch_pairs: view 1 has no valid depth");
     return MVS_ERR_DEGENERATE;
   }
-  MVS_TRY(mvs_apply_srt(ctx, va.data(), nullptr, np, out.scale, out.R, out.t));
+  MVS_TRY(apply_srt_dev_f64(ctx, dxyz.p, np, out.scale, out.R, out.t));
+  if (job.template_xyz) MVS_TRY(d2h_async(ctx, job.template_xyz, dxyz.p, sizeof(double) * 3 * np));
+  if (job.facets && nf > 0) MVS_TRY(d2h_async(ctx, job.facets, dfac.p, sizeof(int32_t) * 3 * nf));
   clk.lap(ST_APPLY);
-  if (job.template_xyz) memcpy(job.template_xyz, va.data(), sizeof(double) * 3 * (size_t)np);
-  if (job.facets) memcpy(job.facets, fa.data(), sizeof(int32_t) * 3 * (size_t)nf);
   // ---- deformation onto view 2
   mvs_deform* d = nullptr;
-  MVS_TRY(mvs_deform_create(ctx, va.data(), nullptr, np, fa.data(), nf, &d));
+  MVS_TRY(deform_create_dev_f64(ctx, dxyz.p, np, dfac.p, nf, &d));
   clk.lap(ST_CREATE);
   int rc = mvs_deform_sample_fps(d, std::min<int64_t>(prm.n_nodes, np), 0);
   clk.lap(ST_FPS);
@@ -187,14 +188,21 @@ static int run_pair(mvs_ctx* ctx, PairScratch& S, const mvs_pair_job& job, const
   clk.lap(ST_TARGET);
   if (rc == MVS_OK) rc = mvs_deform_solve(d, &prm.gn);
   clk.lap(ST_SOLVE);
-  if (rc == MVS_OK) rc = mvs_deform_get_vertices(d, va.data());
+  if (rc == MVS_OK && job.deformed_xyz) rc = mvs_deform_get_vertices(d, job.deformed_xyz);
+  clk.lap(ST_GET);
+  // ---- re-projection of the deformed mesh into camera 2, from the device-resident vertices
+  if (rc == MVS_OK && job.render) {
+    const float4* cur = nullptr;
+    deform_vertices_dev(d, &cur);
+    DevBuf<float> img;
+    rc = img.reserve((size_t)npx);
+    if (rc == MVS_OK)
+      rc = mvs_model2depth_dev(ctx, reinterpret_cast<const float*>(cur), np, dfac.p, nf, cb, 1, 0.f, 0.f,
+                               img.p);
+    if (rc == MVS_OK) rc = d2h_sync(ctx, job.render, img.p, sizeof(float) * npx);
+  }
   mvs_deform_destroy(d);
   MVS_TRY(rc);
-  clk.lap(ST_GET);
-  if (job.deformed_xyz) memcpy(job.deformed_xyz, va.data(), sizeof(double) * 3 * (size_t)np);
-  // ---- re-projection of the deformed mesh into camera 2
-  if (job.render)
-    MVS_TRY(mvs_model2depth_f64(ctx, va.data(), np, fa.data(), nf, cb, 1, 0.f, 0.f, job.render));
   clk.lap(ST_RENDER);
   return MVS_OK;
 }
