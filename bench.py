@@ -616,8 +616,8 @@ def c5_shard(args, api, local, stream, world, rank, dist, peak, side, nodes, ste
         t_setup = time.perf_counter() - t0
         st = d.Stats()
         m, nnz = st["nodes"], st["pattern_blocks"]
-        per = (n + world - 1) // world
-        d.SetShard(rank * per, min(n, (rank + 1) * per))
+        if world > 1:
+            d.SetShardInterleaved(rank, world, 8)  # 8 chunks per rank spread over the mesh
         tgt4 = torch.zeros((nt, 4), dtype=torch.float32, device="cuda")
         tgt4[:, :3] = torch.from_numpy(tgt).cuda()
         stream.synchronize()
@@ -677,8 +677,9 @@ def c5_shard(args, api, local, stream, world, rank, dist, peak, side, nodes, ste
            "shard_bitwise_equal": equal,
            "families_ms_per_step_rank0": {k: round(v[0], 4) for k, v in
                                           sorted(prof.items(), key=lambda kv: -kv[1][0])},
-           "workload": f"C5: {n}-vertex mesh, {m}-node graph, vertex ranges sharded over {world} rank(s), "
-                       f"ncclAllReduce(int64) of the upper-triangle J^T J blocks + J^T r per GN iteration, "
+           "workload": f"C5: {n}-vertex mesh, {m}-node graph, vertices sharded over {world} rank(s) (8 interleaved "
+                       f"chunks per rank), partial fixed-point J^T J blocks + J^T r summed and converted by one "
+                       f"kernel over NVLink peer memory (NCCL all-reduce as fallback) per GN iteration, "
                        f"replicated PCG; {args.gn_iters} GN x {args.pcg_iters} PCG + vertex update"}
     if with_cpu and rank == 0:
         import oracle
@@ -831,8 +832,7 @@ def run_b200(args):
         global NRUNS
         NRUNS = int(st["tuple_runs"])
         if shard:
-            per = (n + world - 1) // world
-            d.SetShard(rank * per, min(n, (rank + 1) * per))
+            d.SetShardInterleaved(rank, world, 8)
         # device-resident target (float4 records) for the HBM-resident leg
         tgt4 = torch.zeros((nt, 4), dtype=torch.float32, device="cuda")
         tgt4[:, :3] = torch.from_numpy(tgt).cuda()

@@ -439,6 +439,12 @@ int mvs_comm_destroy(mvs_ctx* ctx);
  * of the assembly group (4 runs of equal node tuples) that contains it, so ranks that split [0, n) at
  * common points tile it exactly and the all-reduced system is BITWISE the unsharded one. */
 int mvs_deform_set_shard(mvs_deform* h, int64_t v_begin, int64_t v_end);
+/* Interleaved sharding: [0, n) is cut into nranks x chunks_per_rank chunks (boundaries snapped like
+ * set_shard) and this rank owns chunks rank, rank + nranks, ...  The correspondence pass costs more
+ * where the template is far from the scan, so contiguous ranges do not balance the ranks; a few
+ * chunks per rank spread over the mesh do.  Same bits as the unsharded solve.  nranks = 0 returns to
+ * the plain range of mvs_deform_set_shard. */
+int mvs_deform_set_shard_interleaved(mvs_deform* h, int rank, int nranks, int chunks_per_rank);
 /* Work through this rank's vertex range as `parts` consecutive sub-ranges, one launch each: the
  * partial sums `parts` ranks would produce, added by the same commutative integer additions the
  * all-reduce performs — the sharded arithmetic checked on ONE GPU (result bitwise equal to

@@ -583,6 +583,10 @@ class Deformation:
         return dict(zip(("vertices", "nodes", "pattern_blocks", "tuple_runs", "facets",
                          "target_points"), [int(v) for v in out]))
 
+    def SetShardInterleaved(self, rank: int, nranks: int, chunks_per_rank: int = 8):
+        check(lib().mvs_deform_set_shard_interleaved(self._h, C.c_int(rank), C.c_int(nranks),
+                                                     C.c_int(chunks_per_rank)))
+
     def SetShardParts(self, parts: int):
         check(lib().mvs_deform_set_shard_parts(self._h, C.c_int(parts)))
 

@@ -6,6 +6,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <vector>
+
 #include "comm.cuh"
 
 namespace mvs {
@@ -17,6 +19,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) =
+      nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -47,6 +51,7 @@ static int load_nccl() {
   MVS_SYM(CommInitRank, "ncclCommInitRank");
   MVS_SYM(CommDestroy, "ncclCommDestroy");
   MVS_SYM(AllReduce, "ncclAllReduce");
+  MVS_SYM(AllGather, "ncclAllGather");
   MVS_SYM(GroupStart, "ncclGroupStart");
   MVS_SYM(GroupEnd, "ncclGroupEnd");
   MVS_SYM(GetErrorString, "ncclGetErrorString");
@@ -97,6 +102,140 @@ int comm_allreduce_sum_i64(mvs_ctx* ctx, long long* buf_dev, size_t count) {
   ctx->launch_count += 1;
   MVS_NCCL(g_nccl.AllReduce(buf_dev, buf_dev, count, ncclInt64, ncclSum, (ncclComm_t)ctx->comm,
                             ctx->stream));
+  return MVS_OK;
+}
+
+// ------------------------------------------------------------------ peer-memory link
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int peer_block_alloc(mvs_ctx* ctx, size_t n64, size_t nf, PeerLink** out) {
+  *out = nullptr;
+  PeerLink* L = new PeerLink();
+  L->off_sysf = align_up(n64 * sizeof(long long), 256);
+  L->off_flags = align_up(L->off_sysf + nf * sizeof(float), 256);
+  L->block_bytes = align_up(L->off_flags + kPeerMaxRanks * sizeof(unsigned), 1 << 21);
+  cudaError_t e = cudaMalloc(&L->block, L->block_bytes);  // plain allocation: CUDA IPC needs one
+  if (e != cudaSuccess) {
+    set_error("peer exchange block of %zu bytes: %s", L->block_bytes, cudaGetErrorString(e));
+    delete L;
+    return MVS_ERR_CUDA;
+  }
+  MVS_CUDA(cudaMemsetAsync((char*)L->block + L->off_flags, 0, kPeerMaxRanks * sizeof(unsigned),
+                           ctx->stream));
+  L->dev.nranks = ctx->nranks;
+  L->dev.rank = ctx->rank;
+  for (int r = 0; r < kPeerMaxRanks; ++r) {
+    L->dev.sys64[r] = nullptr;
+    L->dev.sysf[r] = nullptr;
+    L->dev.flags[r] = nullptr;
+  }
+  *out = L;
+  return MVS_OK;
+}
+
+struct PeerHello {  // what the ranks swap
+  cudaIpcMemHandle_t handle;
+  unsigned long long block_bytes;
+  unsigned long long offset;  // of the block inside the allocation the handle names
+};
+
+int peer_link_connect(mvs_ctx* ctx, PeerLink* L) {
+  if (L->ready) return MVS_OK;
+  if (!ctx->comm || ctx->nranks <= 1 || ctx->nranks > kPeerMaxRanks) {
+    set_error("peer link: no communicator, or more than %d ranks", kPeerMaxRanks);
+    return MVS_ERR_COMM;
+  }
+  const int n = ctx->nranks;
+  PeerHello mine;
+  memset(&mine, 0, sizeof(mine));
+  MVS_CUDA(cudaIpcGetMemHandle(&mine.handle, L->block));
+  mine.block_bytes = L->block_bytes;
+  // the handle names the whole underlying allocation: find the block's offset inside it
+  mine.offset = 0;
+  {
+    typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
+      unsigned long long base = 0;
+      size_t size = 0;
+      if (((GetRangeFn)fn)(&base, &size, (unsigned long long)(uintptr_t)L->block) == 0)
+        mine.offset = (unsigned long long)(uintptr_t)L->block - base;
+    }
+    cudaGetLastError();
+  }
+  PeerHello* d_all = nullptr;
+  MVS_CUDA(cudaMalloc((void**)&d_all, sizeof(PeerHello) * (n + 1)));
+  MVS_CUDA(cudaMemcpyAsync(d_all + n, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+  ncclResult_t r = g_nccl.AllGather(d_all + n, d_all, sizeof(PeerHello), ncclChar, (ncclComm_t)ctx->comm,
+                                    ctx->stream);
+  if (r != ncclSuccess) {
+    cudaFree(d_all);
+    set_error("peer link: ncclAllGather -> %s", g_nccl.GetErrorString(r));
+    return MVS_ERR_COMM;
+  }
+  std::vector<PeerHello> all((size_t)n);
+  MVS_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerHello) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_all);
+  for (int k = 0; k < n; ++k) {
+    char* base = nullptr;
+    if (k == ctx->rank) {
+      base = (char*)L->block;
+    } else {
+      if (all[k].block_bytes != L->block_bytes) {
+        set_error("peer link: rank %d holds a different system (%llu vs %zu bytes)", k,
+                  all[k].block_bytes, L->block_bytes);
+        return MVS_ERR_COMM;
+      }
+      void* p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, all[k].handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("peer link: cudaIpcOpenMemHandle(rank %d): %s", k, cudaGetErrorString(e));
+        return MVS_ERR_COMM;
+      }
+      L->opened[k] = p;
+      base = (char*)p + all[k].offset;
+    }
+    L->dev.sys64[k] = reinterpret_cast<long long*>(base);
+    L->dev.sysf[k] = reinterpret_cast<float*>(base + L->off_sysf);
+    L->dev.flags[k] = reinterpret_cast<unsigned*>(base + L->off_flags);
+  }
+  L->ready = true;
+  return MVS_OK;
+}
+
+void peer_link_free(PeerLink* L) {
+  if (!L) return;
+  for (int k = 0; k < kPeerMaxRanks; ++k)
+    if (L->opened[k]) cudaIpcCloseMemHandle(L->opened[k]);
+  if (L->block) cudaFree(L->block);
+  delete L;
+}
+
+// One thread per rank: publish "this rank reached `epoch`" in every rank's flag array (release, system
+// scope), then wait until every rank has published it here.  Epochs only grow, so a fast rank that is
+// already one barrier ahead cannot be mistaken for a late one.
+__global__ void k_peer_barrier(PeerLinkDev L, unsigned epoch) {
+  int r = threadIdx.x;
+  if (r >= L.nranks) return;
+  __threadfence_system();
+  unsigned* remote = L.flags[r] + L.rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const unsigned* local = L.flags[L.rank] + r;
+  unsigned v = 0, spins = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+    if (++spins > (1u << 28)) __trap();  // a lost rank becomes an error, not a hang
+  } while ((int)(v - epoch) < 0);
+}
+
+int peer_barrier(mvs_ctx* ctx, PeerLink* L) {
+  ++L->epoch;
+  ctx->launch_count += 1;
+  k_peer_barrier<<<1, 32, 0, ctx->stream>>>(L->dev, L->epoch);
+  MVS_CUDA(cudaGetLastError());
   return MVS_OK;
 }
 

@@ -127,8 +127,9 @@ struct DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
+  bool external = false;      // points into memory owned elsewhere (adopt): never freed here
   void release() {
-    if (p) {
+    if (p && !external) {
       if (async)
         cudaFreeAsync(p, st);
       else
@@ -136,9 +137,21 @@ struct DevBuf {
     }
     p = nullptr;
     cap = 0;
+    external = false;
+  }
+  // view of `n` elements inside a block somebody else owns (the IPC exchange block of a sharded solve)
+  void adopt(T* ptr, size_t n) {
+    release();
+    p = ptr;
+    cap = n;
+    external = true;
   }
   int reserve(size_t n) {
     if (n <= cap) return MVS_OK;
+    if (external) {
+      set_error("internal: an adopted buffer of %zu elements cannot grow to %zu", cap, n);
+      return MVS_ERR_STATE;
+    }
     release();
     size_t bytes = (n ? n : 1) * sizeof(T);
     AllocStream& as = alloc_stream();

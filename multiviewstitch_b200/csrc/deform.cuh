@@ -17,6 +17,7 @@
 //   block-CSR pattern row_ptr[m+1], col[nnz] (ascending, diagonal included)
 #pragma once
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -25,6 +26,7 @@
 namespace mvs {
 struct ArapState;  // arap.cu
 void arap_free(ArapState* a);
+struct PeerLink;   // comm.cuh
 }  // namespace mvs
 
 struct mvs_deform {
@@ -63,6 +65,9 @@ struct mvs_deform {
   // commute exactly), then converted to the float32 system above; only the upper triangle of the
   // block pattern is stored: layout [U: nup x 16 | rhs: m x 12]
   mvs::DevBuf<long long> sys64;
+  // vertex-sharded solves: sys64 and sys are views into ONE cudaMalloc'd exchange block that the other
+  // ranks map through CUDA IPC (comm.cuh); null on single-rank contexts
+  mvs::PeerLink* peer = nullptr;
   double fx_scale = 1.0;   // power of two, set per solve from the magnitude bound
   double diag2 = 1.0;      // squared bbox diagonal of the rest mesh
   float omega_max = 1.0f;  // largest per-vertex constraint weight
@@ -114,6 +119,11 @@ struct mvs_deform {
   // partial sums `shard_parts` ranks would produce, added by the same integer atomics the all-reduce
   // performs (mvs_deform_set_shard_parts: single-GPU check of the sharded arithmetic)
   int shard_parts = 1;
+  // interleaved sharding (mvs_deform_set_shard_interleaved): [0, n) is cut into il_nranks x il_chunks
+  // chunks and this rank takes chunks il_rank, il_rank + il_nranks, ... — the cost of the
+  // correspondence pass varies over the mesh (far regions search longer), contiguous ranges do not
+  // balance it.  il_nranks = 0: the plain range [v_begin, v_end)
+  int il_rank = 0, il_nranks = 0, il_chunks = 1;
   double energy[3] = {0, 0, 0};
   // as-rigid-as-possible solver state (arap.cu), built on first use
   mvs::ArapState* arap = nullptr;
@@ -134,14 +144,53 @@ struct mvs_deform {
     auto it = std::upper_bound(h_grp_start.begin(), h_grp_start.end(), (int)i);
     return (int64_t) * (it - 1);
   }
+  // index of the assembly group that starts at sorted vertex i (i is 0, n or a snapped boundary)
+  int group_at(int64_t i) const {
+    if (i <= 0) return 0;
+    auto it = std::lower_bound(h_grp_start.begin(), h_grp_start.end(), (int)i);
+    return (int)(it - h_grp_start.begin());
+  }
   int64_t shard_begin() const { return snap(v_begin); }
   int64_t shard_end() const { return v_end < 0 ? n : snap(v_end); }
+  // the sorted-vertex sub-ranges this rank works through, each snapped to assembly groups
+  std::vector<std::pair<int64_t, int64_t>> shard_ranges() const {
+    std::vector<std::pair<int64_t, int64_t>> out;
+    if (il_nranks > 0) {
+      const int64_t T = (int64_t)il_nranks * il_chunks;
+      for (int64_t k = il_rank; k < T; k += il_nranks) {
+        int64_t b = k == 0 ? 0 : snap(n * k / T), e = k + 1 == T ? n : snap(n * (k + 1) / T);
+        if (e > b) out.emplace_back(b, e);
+      }
+      return out;
+    }
+    const int64_t b0 = shard_begin(), e0 = shard_end();
+    const int parts = shard_parts < 1 ? 1 : shard_parts;
+    const int64_t per = (e0 - b0 + parts - 1) / parts;
+    for (int part = 0; part < parts; ++part) {
+      int64_t lo = std::min(e0, b0 + per * part), hi = std::min(e0, b0 + per * (part + 1));
+      int64_t b = part == 0 ? b0 : std::max(b0, snap(lo));
+      int64_t e = part == parts - 1 ? e0 : std::max(b0, snap(hi));
+      if (e > b) out.emplace_back(b, e);
+    }
+    return out;
+  }
 };
 
 namespace mvs {
 
 constexpr int kGrpRuns = 4;             // runs per assembly group
 constexpr int kGrpMax = 14 * kGrpRuns;  // 10 upper-triangle block tiles + 4 gradient tiles per run
+
+// the sub-ranges of one launch of the per-vertex passes (a rank's interleaved chunks): up to 16, mapped
+// from the flat thread / ticket index inside the kernel so that the chunks fill waves together
+constexpr int kMaxShardRanges = 16;
+struct ShardRanges {
+  int n;
+  int64_t b[kMaxShardRanges], e[kMaxShardRanges];
+  int64_t voff[kMaxShardRanges + 1];  // prefix sums of the vertex counts
+  int g_lo[kMaxShardRanges];          // first assembly group of each range
+  int goff[kMaxShardRanges + 1];      // prefix sums of the group counts
+};
 
 // scal[] slots
 enum { S_RZ = 0, S_PQ = 1, S_RZ_NEW = 2, S_BNORM2 = 3, S_RNORM2 = 4, S_PQ_CUR = 5, S_EFIT = 8, S_EROT = 9,

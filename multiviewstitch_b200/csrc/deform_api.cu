@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "comm.cuh"
 #include "deform.cuh"
 #include "nn_pyramid.cuh"
 
@@ -359,6 +360,12 @@ int mvs_deform_destroy(mvs_deform* h) {
   if (h->node_index) mvs_nn_index_destroy(h->node_index);
   if (h->tgt_index) mvs_nn_index_destroy(h->tgt_index);
   if (h->arap) arap_free(h->arap);
+  if (h->peer) {
+    h->sys.release();
+    h->sys64.release();
+    peer_link_free(h->peer);
+    h->peer = nullptr;
+  }
   mvs_ctx* ctx = h->ctx;
   delete h;
   ctx_release(ctx);
@@ -857,6 +864,20 @@ int mvs_deform_set_shard(mvs_deform* h, int64_t v_begin, int64_t v_end) {
   }
   h->v_begin = v_begin;
   h->v_end = v_end;
+  h->il_nranks = 0;
+  return MVS_OK;
+}
+
+int mvs_deform_set_shard_interleaved(mvs_deform* h, int rank, int nranks, int chunks_per_rank) {
+  MVS_REQUIRE(h, "null handle");
+  if (nranks < 0 || (nranks > 0 && (rank < 0 || rank >= nranks)) || chunks_per_rank < 1 ||
+      chunks_per_rank > 4096) {
+    set_error("set_shard_interleaved: bad argument");
+    return MVS_ERR_INVALID_ARG;
+  }
+  h->il_rank = rank;
+  h->il_nranks = nranks;
+  h->il_chunks = chunks_per_rank;
   return MVS_OK;
 }
 

@@ -6,9 +6,12 @@
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cmath>
 
+#include "comm.cuh"
 #include "deform.cuh"
 #include "nn_pyramid.cuh"
 
@@ -793,8 +796,24 @@ int deform_build_graph(mvs_deform* h, int node_k, int graph_k) {
     h->diag2 = d2 > 0 ? d2 : 1.0;
   }
   // 6. solver buffers
-  MVS_TRY(h->sys.reserve(h->sys_floats()));
-  MVS_TRY(h->sys64.reserve(h->sys64_count() + 2));  // + the assembly group counter
+  if (h->peer) {  // a rebuilt graph gets a fresh exchange block (the peers rebuild theirs alike)
+    h->sys.release();
+    h->sys64.release();
+    MVS_CUDA(cudaStreamSynchronize(st));
+    peer_link_free(h->peer);
+    h->peer = nullptr;
+  }
+  if (ctx->comm && ctx->nranks > 1 && ctx->nranks <= kPeerMaxRanks && !getenv("MVS_NO_PEER")) {
+    // vertex-sharded solve: the two systems live in a block the other ranks can map (comm.cuh)
+    h->sys.release();
+    h->sys64.release();
+    MVS_TRY(peer_block_alloc(ctx, h->sys64_count() + 2, h->sys_floats(), &h->peer));
+    h->sys64.adopt(reinterpret_cast<long long*>(h->peer->block), h->sys64_count() + 2);
+    h->sys.adopt(reinterpret_cast<float*>((char*)h->peer->block + h->peer->off_sysf), h->sys_floats());
+  } else {
+    MVS_TRY(h->sys.reserve(h->sys_floats()));
+    MVS_TRY(h->sys64.reserve(h->sys64_count() + 2));  // + the assembly group counter
+  }
   MVS_TRY(h->Minv.reserve((size_t)m * 144));
   MVS_TRY(h->x.reserve((size_t)m * 12));
   MVS_TRY(h->pcg.reserve((size_t)m * 12 * 6));

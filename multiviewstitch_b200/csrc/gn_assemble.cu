@@ -101,15 +101,32 @@ struct Best1 {
   }
 };
 
+// flat index of a launch -> sorted vertex inside the launch's sub-ranges (-1 past the end)
+__device__ __forceinline__ int64_t range_index(const ShardRanges& R, int64_t t) {
+  if (t >= R.voff[R.n]) return -1;
+  int k = 0;
+  while (t >= R.voff[k + 1]) ++k;
+  return R.b[k] + (t - R.voff[k]);
+}
+
+// MULTI = false: one contiguous range (the single-GPU case) passed as two scalars
+template <bool MULTI>
 __global__ void __launch_bounds__(128, 8)
     k_deform_corr(PyrParams tg, const float4* __restrict__ tpts, int* __restrict__ corr_prev,
                   const float4* __restrict__ tnrm,
                   const float4* __restrict__ v, const float4* __restrict__ nrm,
                   const int4* __restrict__ vidx, const float4* __restrict__ vw,
-                  const float4* __restrict__ g, const float* __restrict__ x, int64_t begin,
-                  int64_t end, float max_d2, float min_cos, float4* __restrict__ resid) {
-  int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= end) return;
+                  const float4* __restrict__ g, const float* __restrict__ x, ShardRanges R,
+                  int64_t begin, int64_t end, float max_d2, float min_cos,
+                  float4* __restrict__ resid) {
+  int64_t i;
+  if (MULTI) {
+    i = range_index(R, blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+    if (i < 0) return;
+  } else {
+    i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= end) return;
+  }
   float4 vi = __ldg(v + i);
   float3 q = deform_point(vi, __ldg(vidx + i), __ldg(vw + i), g, x);
   Best1 b;
@@ -144,9 +161,9 @@ __global__ void __launch_bounds__(128, 8)
 __global__ void k_deform_resid(const float4* __restrict__ v, const int4* __restrict__ vidx,
                                const float4* __restrict__ vw, const float4* __restrict__ g,
                                const float* __restrict__ x, const float4* __restrict__ targets,
-                               int64_t begin, int64_t end, float4* __restrict__ resid) {
-  int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= end) return;
+                               ShardRanges R, float4* __restrict__ resid) {
+  int64_t i = range_index(R, blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+  if (i < 0) return;
   float4 t = __ldg(targets + i);
   if (!(t.w > 0.f)) {
     resid[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -156,24 +173,31 @@ __global__ void k_deform_resid(const float4* __restrict__ v, const int4* __restr
   resid[i] = make_float4(q.x - t.x, q.y - t.y, q.z - t.z, t.w);
 }
 
-// sub-range `part` of `parts` of [b, e)
-static inline void shard_part(const mvs_deform* h, int64_t b, int64_t e, int parts, int part,
-                              int64_t* pb, int64_t* pe) {
-  if (parts <= 1) {
-    *pb = b;
-    *pe = e;
-    return;
+// the rank's sub-ranges in launch batches of at most kMaxShardRanges
+static std::vector<ShardRanges> range_batches(const mvs_deform* h) {
+  std::vector<ShardRanges> out;
+  const auto ranges = h->shard_ranges();
+  for (size_t k0 = 0; k0 < ranges.size(); k0 += kMaxShardRanges) {
+    ShardRanges R;
+    memset(&R, 0, sizeof(R));
+    R.n = (int)std::min<size_t>(kMaxShardRanges, ranges.size() - k0);
+    for (int k = 0; k < R.n; ++k) {
+      R.b[k] = ranges[k0 + k].first;
+      R.e[k] = ranges[k0 + k].second;
+      R.voff[k + 1] = R.voff[k] + (R.e[k] - R.b[k]);
+      R.g_lo[k] = h->group_at(R.b[k]);
+      int g_hi = R.e[k] >= h->n ? (int)h->ngroups : h->group_at(R.e[k]);
+      R.goff[k + 1] = R.goff[k] + std::max(0, g_hi - R.g_lo[k]);
+    }
+    out.push_back(R);
   }
-  int64_t per = (e - b + parts - 1) / parts;
-  int64_t lo = std::min(e, b + per * part), hi = std::min(e, b + per * (part + 1));
-  *pb = part == 0 ? b : std::max(b, h->snap(lo));
-  *pe = part == parts - 1 ? e : std::max(b, h->snap(hi));
+  return out;
 }
 
 int gn_deform_and_correspond(mvs_deform* h) {
   mvs_ctx* ctx = h->ctx;
-  const int64_t b0 = h->shard_begin(), e0 = h->shard_end();
-  if (e0 <= b0) return MVS_OK;
+  const auto batches = range_batches(h);
+  if (batches.empty()) return MVS_OK;
   if (h->prm.corr_mode == 1) {
     if (!h->tgt_index || !h->tgt_index->pyr_built) {
       set_error("corr_mode 1 needs a target (mvs_deform_set_target*)");
@@ -183,21 +207,28 @@ int gn_deform_and_correspond(mvs_deform* h) {
     set_error("fixed-target mode needs per-vertex targets");
     return MVS_ERR_STATE;
   }
-  const int parts = std::max(1, h->shard_parts);
-  for (int part = 0; part < parts; ++part) {
-    int64_t b, e;
-    shard_part(h, b0, e0, parts, part, &b, &e);
-    if (e <= b) continue;
+  for (const ShardRanges& R : batches) {
+    const int64_t nv = R.voff[R.n];
+    if (nv <= 0) continue;
     if (h->prm.corr_mode == 1) {
       ProfScope ps(ctx, "gn_deform_corr");
-      k_deform_corr<<<div_up(e - b, 128), 128, 0, ctx->stream>>>(
-          h->tgt_index->pyr, h->tp, h->corr_prev.p, h->tn, h->v.p, h->nrm.p, h->vidx.p, h->vw.p,
-          h->g.p, h->x.p, b, e, (float)h->prm.max_corr_dist2, (float)h->prm.min_corr_cos,
-          h->resid.p);
+      if (R.n == 1) {
+        ShardRanges none;
+        none.n = 0;
+        k_deform_corr<false><<<div_up(nv, 128), 128, 0, ctx->stream>>>(
+            h->tgt_index->pyr, h->tp, h->corr_prev.p, h->tn, h->v.p, h->nrm.p, h->vidx.p, h->vw.p,
+            h->g.p, h->x.p, none, R.b[0], R.e[0], (float)h->prm.max_corr_dist2,
+            (float)h->prm.min_corr_cos, h->resid.p);
+      } else {
+        k_deform_corr<true><<<div_up(nv, 128), 128, 0, ctx->stream>>>(
+            h->tgt_index->pyr, h->tp, h->corr_prev.p, h->tn, h->v.p, h->nrm.p, h->vidx.p, h->vw.p,
+            h->g.p, h->x.p, R, 0, 0, (float)h->prm.max_corr_dist2, (float)h->prm.min_corr_cos,
+            h->resid.p);
+      }
     } else {
       ProfScope ps(ctx, "gn_deform_resid");
-      k_deform_resid<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(
-          h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, h->targets.p, b, e, h->resid.p);
+      k_deform_resid<<<div_up(nv, 256), 256, 0, ctx->stream>>>(
+          h->v.p, h->vidx.p, h->vw.p, h->g.p, h->x.p, h->targets.p, R, h->resid.p);
     }
   }
   MVS_CUDA(cudaGetLastError());
@@ -251,8 +282,8 @@ __global__ void __launch_bounds__(kAsmWarps * 32, kAsmCtasPerSm)
                    const float4* __restrict__ resid, const float4* __restrict__ run_g,
                    const unsigned char* __restrict__ run_local, const int* __restrict__ run_start,
                    const int* __restrict__ grp_n, const int* __restrict__ grp_dst,
-                   long long* __restrict__ sys64, int nup16, int nruns, int64_t begin, int64_t end,
-                   float w_fit, float fx_scale, unsigned* __restrict__ next_group) {
+                   long long* __restrict__ sys64, int nup16, int nruns, ShardRanges R, float w_fit,
+                   float fx_scale, unsigned* __restrict__ next_group) {
   __shared__ __align__(16) float rec[kAsmWarps][32][kRecStride];
   __shared__ __align__(16) float accs[kAsmWarps][kGrpMax][16];
   const unsigned full = 0xffffffffu;
@@ -272,9 +303,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32, kAsmCtasPerSm)
     case 9: ta = 2; tb = 3; break;
     default: ta = (t - 10) & 3; tb = 4; break;  // gradient tiles read the residual (cols 16..19)
   }
-  // runs that intersect this rank's vertex range
-  const int run_lo = __float_as_int(__ldg(&v[begin].w));
-  const int run_hi = __float_as_int(__ldg(&v[end - 1].w));
+  int64_t begin = 0, end = 1;  // the sub-range of the current group (set per ticket)
   auto fetch = [&](int64_t i) {
     AsmRaw r;
     i = min(i, end - 1);  // lanes past the run are masked when the pass is processed
@@ -288,8 +317,16 @@ __global__ void __launch_bounds__(kAsmWarps * 32, kAsmCtasPerSm)
   for (;;) {
     int q = 0;
     if (lane == 0) q = (int)atomicAdd(next_group, 1u);
-    q = __shfl_sync(full, q, 0) + run_lo / kGrpRuns;
-    if (q > run_hi / kGrpRuns) break;
+    q = __shfl_sync(full, q, 0);
+    if (q >= R.goff[R.n]) break;
+    // ticket -> (sub-range, group): sub-ranges start and end on group boundaries
+    int kr = 0;
+    while (q >= R.goff[kr + 1]) ++kr;
+    q = R.g_lo[kr] + (q - R.goff[kr]);
+    begin = R.b[kr];
+    end = R.e[kr];
+    const int run_lo = R.g_lo[kr] * kGrpRuns;
+    const int run_hi = min((R.g_lo[kr] + (R.goff[kr + 1] - R.goff[kr])) * kGrpRuns, nruns) - 1;
     const int r_base = q * kGrpRuns;
     const int r_first = max(r_base, run_lo), r_last = min(r_base + kGrpRuns - 1, run_hi);
     // lane l <= kGrpRuns: first vertex of run r_base + l
@@ -467,7 +504,7 @@ __global__ void __launch_bounds__(128)
                  const int* __restrict__ graph, int gk1, int64_t m,
                  const int* __restrict__ row_ptr, const int* __restrict__ col,
                  const int* __restrict__ uidx, long long* __restrict__ B, float* __restrict__ Rot,
-                 long long* __restrict__ rhs, float w_rot, float w_reg, float fxs) {
+                 long long* __restrict__ rhs, float w_rot, float w_reg, float fxs, int add_fixed) {
   const unsigned full = 0xffffffffu;
   int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kNodeLanes;
   int k = threadIdx.x & (kNodeLanes - 1);
@@ -546,11 +583,13 @@ __global__ void __launch_bounds__(128)
       // accumulated (k_sys_convert mirrors it)
       long long* Bup = B + (size_t)__ldg(uidx + find_slot(row_ptr, col, (int)j, l)) * 16;
       long long* Bll = B + (size_t)__ldg(uidx + find_slot(row_ptr, col, l, l)) * 16;
+      if (add_fixed) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) fx_add(Bup + (j < l ? 4 * c + 3 : 12 + c), -w_reg * a[c], fxs);
-      fx_add(Bll + 15, w_reg, fxs);
+        for (int c = 0; c < 4; ++c) fx_add(Bup + (j < l ? 4 * c + 3 : 12 + c), -w_reg * a[c], fxs);
+        fx_add(Bll + 15, w_reg, fxs);
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) fx_add(rhs + (size_t)l * 12 + 9 + rr, -w_reg * r[rr], fxs);
+        for (int rr = 0; rr < 3; ++rr) fx_add(rhs + (size_t)l * 12 + 9 + rr, -w_reg * r[rr], fxs);
+      }
     }
   }
   // reduce the node's own contributions over its 16 lanes
@@ -561,7 +600,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
     for (int p = 0; p < 12; ++p) gl[p] += __shfl_xor_sync(full, gl[p], o);
   }
-  if (on && k < 4) {
+  if (on && k < 4 && add_fixed) {
     long long* Bd = B + (size_t)__ldg(uidx + find_slot(row_ptr, col, (int)j, (int)j)) * 16;
     // lane k flushes row k of the 4x4 factor and 3 gradient entries
     float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -596,7 +635,8 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
 __global__ void __launch_bounds__(128)
     k_precond(const int* __restrict__ row_ptr, const int* __restrict__ col,
               const int* __restrict__ uidx, const long long* __restrict__ U, float inv_scale,
-              const float* __restrict__ Rot, int64_t m, double lambda, float* __restrict__ Minv) {
+              const float* __restrict__ Rot, int64_t m, double lambda, float* __restrict__ Minv,
+              const float* __restrict__ Bf) {
   int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kNodeLanes;
   int lane = threadIdx.x & 31;
   int k = lane & (kNodeLanes - 1);
@@ -608,12 +648,17 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
   for (int q = 0; q < 12; ++q) a[q] = (q == k) ? 1.0 : 0.0;  // identity rows for idle lanes
   if (act) {
-    const long long* Bd = U + (size_t)__ldg(uidx + find_slot(row_ptr, col, (int)j, (int)j)) * 16;
+    const int dslot = find_slot(row_ptr, col, (int)j, (int)j);
+    const long long* Bd = U + (size_t)__ldg(uidx + dslot) * 16;
+    const float* Bdf = Bf ? Bf + (size_t)dslot * 16 : nullptr;  // the converted system (same float values)
     int ka = k / 3, kr = k - 3 * ka;
 #pragma unroll
     for (int q = 0; q < 12; ++q) {
       int qa = q / 3, qr = q - 3 * qa;
-      double v = (qr == kr) ? (double)(float)((double)__ldg(Bd + 4 * ka + qa) * (double)inv_scale) : 0.0;
+      double v = 0.0;
+      if (qr == kr)
+        v = Bdf ? (double)__ldg(Bdf + 4 * ka + qa)
+                : (double)(float)((double)__ldg(Bd + 4 * ka + qa) * (double)inv_scale);
       if (k < 9 && q < 9) v += (double)__ldg(Rot + (size_t)j * 81 + 9 * k + q);
       if (q == k) v += lambda;
       a[q] = v;
@@ -650,6 +695,49 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// ------------------------------------------------------------------ fused all-reduce + conversion
+// Vertex-sharded solve over NVLink peer memory (comm.cuh): rank r owns the slice [lo, hi) of the
+// float system's index space; for every element it LOADS the partial fixed-point sums of all ranks
+// from their exchange blocks (peer-to-peer loads), adds them — integers: the total does not depend on
+// the order —, converts exactly as k_sys_convert does (mirroring the lower triangle) and STORES the
+// float value into every rank's float system (peer-to-peer stores).  One kernel replaces
+// ncclAllReduce(int64) + k_sys_convert: per rank (N-1)/N of the slice's 8-byte partials come in and
+// (N-1)/N of its 4-byte results go out, against 2 (N-1)/N x 8 bytes per element for the all-reduce.
+// Work is split by SOURCE: a rank takes a range of pattern entries and of gradient rows; 16 lanes per
+// upper-triangle entry load its 16 fixed-point words from every rank (128 contiguous bytes per rank),
+// and store the float block where it belongs and, transposed, where its mirror belongs — every
+// partial sum crosses NVLink once.
+__global__ void __launch_bounds__(256)
+    k_peer_reduce_convert(PeerLinkDev L, int64_t e_lo, int64_t e_hi, int64_t r_lo, int64_t r_hi,
+                          int64_t nnz16, int64_t nup16, const int* __restrict__ tslot,
+                          const int* __restrict__ uidx, float inv_scale) {
+  const int el = threadIdx.x & 15;
+  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
+  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) >> 4;
+  for (int64_t e = e_lo + g0; e < e_hi; e += gstride) {
+    const int et = __ldg(tslot + e);
+    if (et < e) continue;  // lower-triangle entry: written by the lanes of its mirror
+    const int64_t src = (int64_t)__ldg(uidx + e) * 16 + el;
+    long long sum = 0;
+    for (int r = 0; r < L.nranks; ++r) sum += __ldcg(L.sys64[r] + src);
+    const float v = (float)((double)sum * (double)inv_scale);
+    const int64_t o1 = e * 16 + el, o2 = (int64_t)et * 16 + (((el & 3) << 2) | (el >> 2));
+    for (int r = 0; r < L.nranks; ++r) {
+      __stcg(L.sysf[r] + o1, v);
+      if (et != e) __stcg(L.sysf[r] + o2, v);
+    }
+  }
+  // gradient: 12 words per node row, one lane per word
+  for (int64_t i = r_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < r_hi;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    long long sum = 0;
+    for (int r = 0; r < L.nranks; ++r) sum += __ldcg(L.sys64[r] + nup16 + i);
+    const float v = (float)((double)sum * (double)inv_scale);
+    for (int r = 0; r < L.nranks; ++r) __stcg(L.sysf[r] + nnz16 + i, v);
+  }
+  __threadfence_system();  // the stores into the peers' memory are visible before this rank signals
+}
+
 // fixed-point scale: the largest power of two that cannot overflow int64 for this problem (every
 // entry is bounded by w_fit omega_max n max(1, D^2) plus the node terms)
 static float gn_fx_scale(mvs_deform* h) {
@@ -667,11 +755,11 @@ static int gn_zero_system(mvs_deform* h, cudaStream_t st) {
   return MVS_OK;
 }
 
-static int gn_launch_node_terms(mvs_deform* h, float fxs, cudaStream_t st) {
+static int gn_launch_node_terms(mvs_deform* h, float fxs, cudaStream_t st, int add_fixed = 1) {
   ProfScope ps(h->ctx, "gn_node_terms", 1, st);
   k_node_terms<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(
       h->g.p, h->x.p, h->graph.p, h->graph_k + 1, h->m, h->row_ptr.p, h->col.p, h->uidx.p, h->B64(),
-      h->Rot(), h->rhs64(), (float)h->prm.w_rot, (float)h->prm.w_reg, fxs);
+      h->Rot(), h->rhs64(), (float)h->prm.w_rot, (float)h->prm.w_reg, fxs, add_fixed);
   MVS_CUDA(cudaGetLastError());
   return MVS_OK;
 }
@@ -702,26 +790,57 @@ int gn_assemble(mvs_deform* h) {
     MVS_TRY(ctx_side_join(ctx));
   else
     MVS_TRY(gn_zero_system(h, st));
-  const int64_t b0 = h->shard_begin(), e0 = h->shard_end();
-  const int parts = std::max(1, h->shard_parts);
   unsigned* group_counter = reinterpret_cast<unsigned*>(h->sys64.p + h->sys64_count());
   bool counter_clean = true;  // zeroed together with the system
-  for (int part = 0; part < parts; ++part) {
-    int64_t b, e;
-    shard_part(h, b0, e0, parts, part, &b, &e);
-    if (e <= b) continue;
+  for (const ShardRanges& R : range_batches(h)) {
+    const int64_t ngr = R.goff[R.n], nv = R.voff[R.n];
+    if (ngr <= 0 || nv <= 0) continue;
     if (!counter_clean) MVS_CUDA(cudaMemsetAsync(group_counter, 0, sizeof(long long), st));
     counter_clean = false;
     ProfScope ps(ctx, "gn_assemble_fit");
-    int64_t warps_needed = std::min<int64_t>(h->ngroups, (e - b + 63) / 64);
+    int64_t warps_needed = std::min<int64_t>(ngr, (nv + 63) / 64);
     int grid = (int)std::min<int64_t>((warps_needed + kAsmWarps - 1) / kAsmWarps,
                                       (int64_t)ctx->num_sms * kAsmCtasPerSm);
     k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(
         h->v.p, h->vw.p, h->resid.p, h->run_g.p, h->run_local.p, h->run_start.p, h->grp_n.p,
-        h->grp_dst.p, h->sys64.p, (int)(h->nup * 16), (int)h->nruns, b, e, (float)h->prm.w_fit, fxs,
+        h->grp_dst.p, h->sys64.p, (int)(h->nup * 16), (int)h->nruns, R, (float)h->prm.w_fit, fxs,
         group_counter);
   }
   MVS_CUDA(cudaGetLastError());
+  const float inv_scale = (float)(1.0 / h->fx_scale);
+  if (ctx->comm && ctx->nranks > 1 && h->peer) {
+    // vertex-sharded solve over peer memory: the node terms enter the sum once (rank 0; every rank
+    // still needs the rotation blocks, which are node-local), then barrier -> fused reduce + convert
+    // -> barrier, and the preconditioner reads the converted float system
+    if (!h->peer->ready) MVS_TRY(peer_link_connect(ctx, h->peer));
+    MVS_TRY(gn_launch_node_terms(h, fxs, st, ctx->rank == 0 ? 1 : 0));
+    {
+      ProfScope ps(ctx, "gn_peer_barrier_in");
+      MVS_TRY(peer_barrier(ctx, h->peer));  // every rank's partial system is complete
+    }
+    {
+      ProfScope ps(ctx, "gn_peer_exchange");
+      const int64_t pe = (h->nnz + ctx->nranks - 1) / ctx->nranks;
+      const int64_t e_lo = std::min<int64_t>(h->nnz, pe * ctx->rank), e_hi = std::min<int64_t>(h->nnz, e_lo + pe);
+      const int64_t nr = h->m * 12, pr = (nr + ctx->nranks - 1) / ctx->nranks;
+      const int64_t r_lo = std::min<int64_t>(nr, pr * ctx->rank), r_hi = std::min<int64_t>(nr, r_lo + pr);
+      k_peer_reduce_convert<<<grid_for(ctx, (e_hi - e_lo) * 16 + 1, 256, 8), 256, 0, st>>>(
+          h->peer->dev, e_lo, e_hi, r_lo, r_hi, h->nnz * 16, h->nup * 16, h->tslot.p, h->uidx.p,
+          inv_scale);
+    }
+    {
+      ProfScope ps(ctx, "gn_peer_barrier_out");
+      MVS_TRY(peer_barrier(ctx, h->peer));  // nobody still reads this rank's partials or writes its floats
+    }
+    {
+      ProfScope ps(ctx, "gn_precond");
+      k_precond<<<div_up(h->m * kNodeLanes, 128), 128, 0, st>>>(
+          h->row_ptr.p, h->col.p, h->uidx.p, h->B64(), inv_scale, h->Rot(), h->m, h->prm.lambda,
+          h->Minv.p, h->B());
+    }
+    MVS_CUDA(cudaGetLastError());
+    return MVS_OK;
+  }
   if (ctx->comm && ctx->nranks > 1) {
     // vertex-sharded solve: sum the partial J^T J blocks and J^T r over ranks (NVLink/NVSwitch);
     // integer sums make the result independent of the reduction order NCCL picks
@@ -731,13 +850,12 @@ int gn_assemble(mvs_deform* h) {
   if (!forked) MVS_TRY(gn_launch_node_terms(h, fxs, st));
   // conversion (main stream) and block-Jacobi inverses (side stream) both read the finished
   // fixed-point system
-  const float inv_scale = (float)(1.0 / h->fx_scale);
   MVS_TRY(ctx_side_fork(ctx));
   {
     ProfScope ps(ctx, "gn_precond", 1, ctx->side);
     k_precond<<<div_up(h->m * kNodeLanes, 128), 128, 0, ctx->side>>>(
         h->row_ptr.p, h->col.p, h->uidx.p, h->B64(), inv_scale, h->Rot(), h->m, h->prm.lambda,
-        h->Minv.p);
+        h->Minv.p, nullptr);
   }
   {
     ProfScope ps(ctx, "gn_sys_convert");
@@ -877,14 +995,28 @@ __global__ void __launch_bounds__(128)
 int gn_energy(mvs_deform* h, double energy[3]) {
   mvs_ctx* ctx = h->ctx;
   cudaStream_t st = ctx->stream;
-  int64_t b = h->shard_begin(), e = h->shard_end();
   MVS_CUDA(cudaMemsetAsync(h->scal.p + S_EFIT, 0, sizeof(double) * 3, st));
-  if (e > b) {
+  const auto ranges = h->shard_ranges();
+  double efit_extra = 0.0;  // sub-ranges beyond the first: summed on the host (not a hot path)
+  for (size_t k = 0; k < ranges.size(); ++k) {
+    const int64_t b = ranges[k].first, e = ranges[k].second;
+    if (k > 0) {
+      double part = 0.0;
+      MVS_TRY(d2h_sync(ctx, &part, h->scal.p + S_EFIT, sizeof(double)));
+      efit_extra += part;
+    }
     ProfScope ps(ctx, "energy_fit");
     int grid = grid_for(ctx, e - b, 256, 4);
     MVS_TRY(h->partials.reserve((size_t)grid * 2 + 16));
     k_energy_fit<<<grid, 256, 0, st>>>(h->resid.p, b, e, h->prm.w_fit, h->partials.p, h->ticket.p,
                                        h->scal.p + S_EFIT);
+  }
+  if (efit_extra != 0.0) {
+    double last = 0.0;
+    MVS_TRY(d2h_sync(ctx, &last, h->scal.p + S_EFIT, sizeof(double)));
+    last += efit_extra;
+    MVS_TRY(h2d(ctx, h->scal.p + S_EFIT, &last, sizeof(double)));
+    MVS_CUDA(cudaStreamSynchronize(st));
   }
   if (ctx->comm && ctx->nranks > 1) MVS_TRY(comm_allreduce_sum_f64(ctx, h->scal.p + S_EFIT, 1));
   {

@@ -116,6 +116,26 @@ def test_sharded_arithmetic_bitwise_equal_on_one_gpu(ctx, parts):
                 assert np.array_equal(a, b)
 
 
+def test_interleaved_chunks_bitwise_equal_on_one_gpu(ctx):
+    """mvs_deform_set_shard_interleaved with one rank owning all 8 chunks: the multi-range passes give
+    the bits of the single-range solve."""
+    pts, faces, tv = cube_case(44, 49)
+    prm = api.gn_params(gn_iters=4, pcg_iters=20, corr_mode=1)
+    outs = []
+    for chunks in (0, 8):
+        d = api.Deformation(pts, None, faces, ctx)
+        d.SampleFPS(300, 0)
+        d.SetTarget(tv)
+        d.BuildGraph(4, 8)
+        if chunks:
+            d.SetShardInterleaved(0, 1, chunks)
+        d.Solve(prm)
+        outs.append((d.Vertices(), d.NodeState(), d.Energy()))
+        d.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.allclose(outs[0][2], outs[1][2], rtol=1e-12)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
