@@ -112,7 +112,8 @@ int peer_block_alloc(mvs_ctx* ctx, size_t n64, size_t nf, PeerLink** out) {
   *out = nullptr;
   PeerLink* L = new PeerLink();
   L->off_sysf = align_up(n64 * sizeof(long long), 256);
-  L->off_flags = align_up(L->off_sysf + nf * sizeof(float), 256);
+  L->off_redf = align_up(L->off_sysf + nf * sizeof(float), 256);
+  L->off_flags = align_up(L->off_redf + n64 * sizeof(float), 256);
   L->block_bytes = align_up(L->off_flags + kPeerMaxRanks * sizeof(unsigned), 1 << 21);
   cudaError_t e = cudaMalloc(&L->block, L->block_bytes);  // plain allocation: CUDA IPC needs one
   if (e != cudaSuccess) {
@@ -127,6 +128,7 @@ int peer_block_alloc(mvs_ctx* ctx, size_t n64, size_t nf, PeerLink** out) {
   for (int r = 0; r < kPeerMaxRanks; ++r) {
     L->dev.sys64[r] = nullptr;
     L->dev.sysf[r] = nullptr;
+    L->dev.redf[r] = nullptr;
     L->dev.flags[r] = nullptr;
   }
   *out = L;
@@ -200,6 +202,7 @@ int peer_link_connect(mvs_ctx* ctx, PeerLink* L) {
     }
     L->dev.sys64[k] = reinterpret_cast<long long*>(base);
     L->dev.sysf[k] = reinterpret_cast<float*>(base + L->off_sysf);
+    L->dev.redf[k] = reinterpret_cast<float*>(base + L->off_redf);
     L->dev.flags[k] = reinterpret_cast<unsigned*>(base + L->off_flags);
   }
   L->ready = true;

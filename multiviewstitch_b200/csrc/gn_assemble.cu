@@ -695,47 +695,65 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// ------------------------------------------------------------------ fused all-reduce + conversion
-// Vertex-sharded solve over NVLink peer memory (comm.cuh): rank r owns the slice [lo, hi) of the
-// float system's index space; for every element it LOADS the partial fixed-point sums of all ranks
-// from their exchange blocks (peer-to-peer loads), adds them — integers: the total does not depend on
-// the order —, converts exactly as k_sys_convert does (mirroring the lower triangle) and STORES the
-// float value into every rank's float system (peer-to-peer stores).  One kernel replaces
-// ncclAllReduce(int64) + k_sys_convert: per rank (N-1)/N of the slice's 8-byte partials come in and
-// (N-1)/N of its 4-byte results go out, against 2 (N-1)/N x 8 bytes per element for the all-reduce.
-// Work is split by SOURCE: a rank takes a range of pattern entries and of gradient rows; 16 lanes per
-// upper-triangle entry load its 16 fixed-point words from every rank (128 contiguous bytes per rank),
-// and store the float block where it belongs and, transposed, where its mirror belongs — every
-// partial sum crosses NVLink once.
+// ------------------------------------------------------------------ all-reduce + conversion over peer memory
+// Vertex-sharded solve over NVLink (comm.cuh), reads only — every transfer is a coalesced peer-to-peer
+// LOAD of contiguous memory:
+//   1. reduce-scatter: rank r owns the slice [lo, hi) of the fixed-point words; it loads that slice of
+//      every rank's partial system (16 bytes per lane), adds — integers: the total does not depend on
+//      the order — and writes the float value (the conversion k_sys_convert applies) into its own
+//      slice of `redf`;
+//   2. all-gather: after a barrier every rank copies the other ranks' slices of `redf` into its own;
+//   3. the float system [B | rhs] is expanded locally from `redf` (lower triangle mirrored).
+// Per rank and iteration (N-1)/N x (8 + 4) bytes per fixed-point word cross NVLink, against
+// 2 (N-1)/N x 8 for ncclAllReduce(int64) followed by a conversion pass.
 __global__ void __launch_bounds__(256)
-    k_peer_reduce_convert(PeerLinkDev L, int64_t e_lo, int64_t e_hi, int64_t r_lo, int64_t r_hi,
-                          int64_t nnz16, int64_t nup16, const int* __restrict__ tslot,
-                          const int* __restrict__ uidx, float inv_scale) {
-  const int el = threadIdx.x & 15;
-  const int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
-  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) >> 4;
-  for (int64_t e = e_lo + g0; e < e_hi; e += gstride) {
-    const int et = __ldg(tslot + e);
-    if (et < e) continue;  // lower-triangle entry: written by the lanes of its mirror
-    const int64_t src = (int64_t)__ldg(uidx + e) * 16 + el;
-    long long sum = 0;
-    for (int r = 0; r < L.nranks; ++r) sum += __ldcg(L.sys64[r] + src);
-    const float v = (float)((double)sum * (double)inv_scale);
-    const int64_t o1 = e * 16 + el, o2 = (int64_t)et * 16 + (((el & 3) << 2) | (el >> 2));
+    k_peer_reduce(PeerLinkDev L, int64_t lo, int64_t hi, float inv_scale) {
+  // lo, hi are even: two words per lane
+  int64_t i = lo + 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+  const int64_t stride = 2 * (int64_t)gridDim.x * blockDim.x;
+  float* out = L.redf[L.rank];
+  for (; i < hi; i += stride) {
+    long long s0 = 0, s1 = 0;
     for (int r = 0; r < L.nranks; ++r) {
-      __stcg(L.sysf[r] + o1, v);
-      if (et != e) __stcg(L.sysf[r] + o2, v);
+      const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(L.sys64[r] + i));
+      s0 += v.x;
+      s1 += v.y;
     }
+    *reinterpret_cast<float2*>(out + i) =
+        make_float2((float)((double)s0 * (double)inv_scale), (float)((double)s1 * (double)inv_scale));
   }
-  // gradient: 12 words per node row, one lane per word
-  for (int64_t i = r_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < r_hi;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    long long sum = 0;
-    for (int r = 0; r < L.nranks; ++r) sum += __ldcg(L.sys64[r] + nup16 + i);
-    const float v = (float)((double)sum * (double)inv_scale);
-    for (int r = 0; r < L.nranks; ++r) __stcg(L.sysf[r] + nnz16 + i, v);
+}
+
+__global__ void __launch_bounds__(256)
+    k_peer_gather(PeerLinkDev L, int64_t per, int64_t n) {
+  // words [r per, (r + 1) per) belong to rank r; per is a multiple of 4
+  int64_t i = 4 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+  const int64_t stride = 4 * (int64_t)gridDim.x * blockDim.x;
+  float* out = L.redf[L.rank];
+  for (; i < n; i += stride) {
+    const int owner = (int)(i / per);
+    if (owner == L.rank) continue;
+    *reinterpret_cast<float4*>(out + i) = __ldcg(reinterpret_cast<const float4*>(L.redf[owner] + i));
   }
-  __threadfence_system();  // the stores into the peers' memory are visible before this rank signals
+}
+
+// [U: nup x 16 | rhs] in float -> float system [B: nnz x 16 | rhs] (k_sys_convert's index map)
+__global__ void k_sys_expand(const float* __restrict__ in, float* __restrict__ out, int64_t n,
+                             int64_t nnz16, int64_t nup16, const int* __restrict__ tslot,
+                             const int* __restrict__ uidx) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int64_t src;
+    if (i < nnz16) {
+      int e = (int)(i >> 4), el = (int)(i & 15);
+      bool lower = __ldg(tslot + e) < e;
+      src = (int64_t)__ldg(uidx + e) * 16 + (lower ? (((el & 3) << 2) | (el >> 2)) : el);
+    } else {
+      src = nup16 + (i - nnz16);
+    }
+    out[i] = __ldg(in + src);
+  }
 }
 
 // fixed-point scale: the largest power of two that cannot overflow int64 for this problem (every
@@ -818,19 +836,27 @@ int gn_assemble(mvs_deform* h) {
       ProfScope ps(ctx, "gn_peer_barrier_in");
       MVS_TRY(peer_barrier(ctx, h->peer));  // every rank's partial system is complete
     }
+    const int64_t n64 = (int64_t)h->sys64_count();
+    // slice per rank: a multiple of 4 words (16-byte lanes in both kernels)
+    const int64_t per = ((n64 + ctx->nranks - 1) / ctx->nranks + 3) / 4 * 4;
+    const int64_t lo = std::min<int64_t>(n64, per * ctx->rank), hi = std::min<int64_t>(n64, lo + per);
     {
-      ProfScope ps(ctx, "gn_peer_exchange");
-      const int64_t pe = (h->nnz + ctx->nranks - 1) / ctx->nranks;
-      const int64_t e_lo = std::min<int64_t>(h->nnz, pe * ctx->rank), e_hi = std::min<int64_t>(h->nnz, e_lo + pe);
-      const int64_t nr = h->m * 12, pr = (nr + ctx->nranks - 1) / ctx->nranks;
-      const int64_t r_lo = std::min<int64_t>(nr, pr * ctx->rank), r_hi = std::min<int64_t>(nr, r_lo + pr);
-      k_peer_reduce_convert<<<grid_for(ctx, (e_hi - e_lo) * 16 + 1, 256, 8), 256, 0, st>>>(
-          h->peer->dev, e_lo, e_hi, r_lo, r_hi, h->nnz * 16, h->nup * 16, h->tslot.p, h->uidx.p,
-          inv_scale);
+      ProfScope ps(ctx, "gn_peer_reduce");
+      if (hi > lo)
+        k_peer_reduce<<<grid_for(ctx, (hi - lo + 1) / 2, 256, 8), 256, 0, st>>>(h->peer->dev, lo, hi,
+                                                                              inv_scale);
     }
     {
-      ProfScope ps(ctx, "gn_peer_barrier_out");
-      MVS_TRY(peer_barrier(ctx, h->peer));  // nobody still reads this rank's partials or writes its floats
+      ProfScope ps(ctx, "gn_peer_barrier_mid");
+      MVS_TRY(peer_barrier(ctx, h->peer));  // every slice is reduced; nobody reads the partials any more
+    }
+    {
+      ProfScope ps(ctx, "gn_peer_gather", 2);
+      k_peer_gather<<<grid_for(ctx, (n64 + 3) / 4, 256, 8), 256, 0, st>>>(h->peer->dev, per, n64);
+      const int64_t nout = h->nnz * 16 + h->m * 12;
+      k_sys_expand<<<grid_for(ctx, nout, 256, 4), 256, 0, st>>>(
+          h->peer->dev.redf[ctx->rank], h->sys.p, nout, h->nnz * 16, h->nup * 16, h->tslot.p,
+          h->uidx.p);
     }
     {
       ProfScope ps(ctx, "gn_precond");
