@@ -73,6 +73,9 @@ struct mvs_ctx {
   // two pinned chunks + events for large device -> pageable-host copies (d2h_sync)
   void* stage[2] = {nullptr, nullptr};
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  // one pinned, device-visible word the solver kernels raise when a PCG partial sum is not finite or
+  // leaves the fixed-point range (a diverging solve); read by the host after its stream synchronise
+  int* solver_flag = nullptr;
   // NCCL communicator (opaque here; see comm.cu)
   void* comm = nullptr;
   int nranks = 1;

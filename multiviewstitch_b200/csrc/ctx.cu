@@ -132,6 +132,7 @@ int ensure_dyn_smem(const void* kernel, int device, int bytes) {
 int pinned_reserve(mvs_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->pinned_bytes) return MVS_OK;
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->solver_flag) cudaFreeHost(ctx->solver_flag);
   ctx->pinned = nullptr;
   ctx->pinned_bytes = 0;
   size_t want = bytes < 4096 ? 4096 : bytes;
@@ -309,6 +310,11 @@ int mvs_ctx_create(mvs_ctx** out, int device, void* stream) {
     }
     cudaGetLastError();
   }
+  if (cudaHostAlloc((void**)&c->solver_flag, 64, cudaHostAllocMapped) == cudaSuccess && c->solver_flag)
+    *c->solver_flag = 0;
+  else
+    c->solver_flag = nullptr;
+  cudaGetLastError();
   *out = c;
   return MVS_OK;
 }

@@ -142,6 +142,18 @@ static int gn_begin_impl(mvs_deform* h, const mvs_gn_params* p) {
   return MVS_OK;
 }
 
+// after a stream synchronise: did a solver kernel raise the context's divergence flag?
+static int check_solver_flag(mvs_deform* h) {
+  int* f = h->ctx->solver_flag;
+  if (f && *reinterpret_cast<volatile int*>(f)) {
+    *f = 0;
+    set_error("Gauss-Newton solve diverged: a PCG partial sum was not finite or left the fixed-point "
+              "range (check the inputs and weights)");
+    return MVS_ERR_DEGENERATE;
+  }
+  return MVS_OK;
+}
+
 static int gn_step_impl(mvs_deform* h) {
   MVS_TRY(gn_node_terms_forked(h));  // side stream, overlaps the correspondence pass
   int rc = gn_deform_and_correspond(h);
@@ -535,7 +547,7 @@ int mvs_deform_solve(mvs_deform* h, const mvs_gn_params* params) {
   MVS_TRY(gn_final_vertices(h));
   MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   h->gn_active = false;
-  return MVS_OK;
+  return check_solver_flag(h);
 }
 
 int mvs_deform_get_correspondences(mvs_deform* h, int32_t* out_idx) {
@@ -566,7 +578,7 @@ int mvs_deform_gn_end(mvs_deform* h) {
   MVS_TRY(gn_final_vertices(h));
   MVS_CUDA(cudaStreamSynchronize(h->ctx->stream));
   h->gn_active = false;
-  return MVS_OK;
+  return check_solver_flag(h);
 }
 
 int mvs_deform_run(mvs_deform* h, double proj_len_err, double proj_dist_err,

@@ -250,9 +250,12 @@ __device__ __forceinline__ int find_slot(const int* __restrict__ row_ptr,
 }
 
 // order-independent accumulation: value * 2^k rounded to int64, summed with integer atomics
-__device__ __forceinline__ void fx_add(long long* addr, float v, float scale) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(addr),
-            (unsigned long long)__float2ll_rn(v * scale));
+// `flag` (the context's pinned solver flag, may be null): raised when a value is not finite or does not
+// fit the fixed-point range — the bound behind gn_fx_scale assumes targets within reach of the mesh
+__device__ __forceinline__ void fx_add(long long* addr, float v, float scale, int* flag = nullptr) {
+  const float sv = v * scale;
+  if (flag && !(fabsf(sv) < 4.0e18f)) *reinterpret_cast<volatile int*>(flag) = 1;
+  atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__float2ll_rn(sv));
 }
 
 // The kernel is bound by the issue rate of the global reductions (RED: ~1.3 cycles per lane per SM),
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32, kAsmCtasPerSm)
                    const unsigned char* __restrict__ run_local, const int* __restrict__ run_start,
                    const int* __restrict__ grp_n, const int* __restrict__ grp_dst,
                    long long* __restrict__ sys64, int nup16, int nruns, ShardRanges R, float w_fit,
-                   float fx_scale, unsigned* __restrict__ next_group) {
+                   float fx_scale, unsigned* __restrict__ next_group, int* flag) {
   __shared__ __align__(16) float rec[kAsmWarps][32][kRecStride];
   __shared__ __align__(16) float accs[kAsmWarps][kGrpMax][16];
   const unsigned full = 0xffffffffu;
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(kAsmWarps * 32, kAsmCtasPerSm)
     for (int k = lane; k < L * 16; k += 32) {
       const int tile = k >> 4, e = k & 15;
       const int d = __ldg(gd + tile);
-      if (e < (d >= nup16 ? 12 : 16)) fx_add(sys64 + d + e, accs[warp][tile][e], fx_scale);
+      if (e < (d >= nup16 ? 12 : 16)) fx_add(sys64 + d + e, accs[warp][tile][e], fx_scale, flag);
     }
     __syncwarp();
   }
@@ -822,7 +825,7 @@ int gn_assemble(mvs_deform* h) {
     k_assemble_fit<<<grid, kAsmWarps * 32, 0, st>>>(
         h->v.p, h->vw.p, h->resid.p, h->run_g.p, h->run_local.p, h->run_start.p, h->grp_n.p,
         h->grp_dst.p, h->sys64.p, (int)(h->nup * 16), (int)h->nruns, R, (float)h->prm.w_fit, fxs,
-        group_counter);
+        group_counter, ctx->solver_flag);
   }
   MVS_CUDA(cudaGetLastError());
   const float inv_scale = (float)(1.0 / h->fx_scale);

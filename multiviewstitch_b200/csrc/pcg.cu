@@ -62,6 +62,7 @@ struct PcgArgs {
   double tol;
   int rows_per_cta;
   int stage_smem;  // 1: matrix slice staged in shared memory
+  int* diverged;   // pinned host word raised when a partial sum leaves the representable range
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -200,9 +201,16 @@ __device__ __forceinline__ FxUnit fx_unit_for(double magnitude) {
   u.inv_hi = ldexp(1.0, -(E + kLimbBits));
   return u;
 }
-__device__ __forceinline__ long long fx_limb(double v, const FxUnit& u, int limb) {
-  if (!(fabs(v) < INFINITY)) v = 0.0;  // a non-finite partial contributes nothing
-  double h = fmin(fmax(rint(v * u.inv_hi), (double)-kLimbMax), (double)kLimbMax);
+__device__ __forceinline__ long long fx_limb(double v, const FxUnit& u, int limb, int* flag) {
+  // a non-finite partial contributes nothing and one beyond the fixed-point range is clamped: either
+  // way the solve is diverging — raise the context's flag so the host call returns an error
+  if (!(fabs(v) < INFINITY)) {
+    v = 0.0;
+    if (flag) *reinterpret_cast<volatile int*>(flag) = 1;
+  }
+  double hr = rint(v * u.inv_hi);
+  if (flag && fabs(hr) > (double)kLimbMax) *reinterpret_cast<volatile int*>(flag) = 1;
+  double h = fmin(fmax(hr, (double)-kLimbMax), (double)kLimbMax);
   if (limb == 0) return (long long)h;
   double rem = v - h * u.hi;  // exact
   double l = fmin(fmax(rint(rem * u.inv_lo), (double)-kLimbMax), (double)kLimbMax);
@@ -219,7 +227,7 @@ template <int N, int T, bool FENCE = true, class Post>
 __device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
                                                  unsigned long long* words, unsigned& wi, int ncta,
                                                  const FxUnit (&unit)[N], double (&out)[N],
-                                                 Post&& post) {
+                                                 Post&& post, int* flag = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int W = T / 32;
   double* red1 = red;                     // W x 2: CTA partial
@@ -236,7 +244,7 @@ __device__ __forceinline__ void grid_exchange_fx(double (&v)[N], double* red,
     for (int w = 0; w < W; ++w) s += red1[w * 2 + j];
     FxUnit u = unit[0];
     if (N > 1 && j == 1) u = unit[N - 1];
-    long long fxv = fx_limb(s, u, limb);
+    long long fxv = fx_limb(s, u, limb, flag);
     unsigned long long enc = (unsigned long long)(fxv + kLimbBias) + (1ull << kCountShift);
     if (FENCE && threadIdx.x == 0) fence_acq_rel();  // publish what this CTA wrote before the call
     __syncwarp((1u << (2 * N)) - 1u);
@@ -469,7 +477,8 @@ __global__ void __launch_bounds__(T, 512 / T) k_pcg_persistent(PcgArgs a) {
       grid_exchange_fx<1, T, false>(pq, red, a.words, wi, ncta, unit_a, pqa,
                                  [&](const double (&tot)[1], double* ex) {
                                    ex[0] = (tot[0] > 0.0 && rz > 0.0) ? (double)(float)(rz / tot[0]) : 0.0;
-                                 });
+                                 },
+                                 a.diverged);
       alpha = (float)extra[2];
     }
     // ---- phase B: delta += alpha p ; r -= alpha q ; z = M^-1 r ; r.z, |r|^2
@@ -500,7 +509,8 @@ __global__ void __launch_bounds__(T, 512 / T) k_pcg_persistent(PcgArgs a) {
       grid_exchange_fx<2, T>(acc, red, a.words, wi, ncta, unit_b, tot,
                           [&](const double (&t2)[2], double* ex) {
                             ex[0] = rz_old > 0.0 ? (double)(float)(t2[0] / rz_old) : 0.0;
-                          });
+                          },
+                          a.diverged);
       rz = tot[0];
       rn2 = tot[1];
       beta_next = (float)extra[4];
@@ -872,6 +882,7 @@ int pcg_solve(mvs_deform* h) {
   a.tol = h->prm.pcg_tol;
   a.rows_per_cta = h->pcg_rs * (h->pcg_threads / kRowLanes);
   a.stage_smem = h->pcg_stage;
+  a.diverged = ctx->solver_flag;
   ProfScope ps(ctx, "pcg_solve");
   switch (h->pcg_rs) {
     case 1: MVS_TRY(launch_pcg<1>(h, a, h->pcg_grid, h->pcg_smem)); break;

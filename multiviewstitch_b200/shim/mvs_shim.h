@@ -357,5 +357,75 @@ class Model2Depth {
   }
 };
 
+// [ref: Processor/Processor.cpp:629-826] the independent iterations of the sequence-pair loop in one
+// call: per pair the matched pixels are unprojected, RemoveOutliers + SRTSolver give (s, R, t), the
+// Depth2Model mesh of view A is moved into the frame of view B, deformed onto the valid points of
+// view B and re-projected with Model2Depth.  Inputs stay where Processor keeps them (host vectors).
+struct ViewPair {
+  const std::vector<float>* depth_a = nullptr;  // w*h inverse depths (the `.raw` layout)
+  const std::vector<float>* depth_b = nullptr;
+  Camera cam_a, cam_b;
+  std::vector<int> matches;  // 4 ints per match: u_a, v_a, u_b, v_b
+  unsigned long long seed = 0;
+};
+struct ViewPairResult {
+  double scale = 1.0, err = 0.0, residual = 0.0;
+  Matrix3d R;
+  Vector3d t;
+  std::vector<int> kept;             // indices of the matches that survive RemoveOutliers
+  std::vector<Vector3d> points;      // view-A mesh in the frame of view B
+  std::vector<Vector3d> deformed;    // after the deformation onto view B
+  std::vector<int> facets;
+  std::vector<float> render;         // Model2Depth of the deformed mesh in camera B
+};
+inline std::vector<ViewPairResult> StitchPairs(const std::vector<ViewPair>& pairs,
+                                               const mvs_pair_params* params = nullptr) {
+  const size_t n = pairs.size();
+  std::vector<mvs_pair_job> jobs(n);
+  std::vector<mvs_pair_result> res(n);
+  std::vector<ViewPairResult> out(n);
+  std::vector<mvs_camera> cams(2 * n);
+  for (size_t k = 0; k < n; ++k) {
+    const ViewPair& p = pairs[k];
+    cams[2 * k] = p.cam_a.c();
+    cams[2 * k + 1] = p.cam_b.c();
+    const size_t px = (size_t)p.cam_a.W() * p.cam_a.H();
+    ViewPairResult& o = out[k];
+    o.kept.resize(p.matches.size() / 4);
+    o.points.resize(px);
+    o.deformed.resize(px);
+    o.facets.resize(6 * (size_t)(p.cam_a.W() - 1) * (p.cam_a.H() - 1));
+    o.render.resize(px);
+    mvs_pair_job& j = jobs[k];
+    std::memset(&j, 0, sizeof(j));
+    j.depth_a = p.depth_a ? p.depth_a->data() : nullptr;
+    j.depth_b = p.depth_b ? p.depth_b->data() : nullptr;
+    j.cam_a = &cams[2 * k];
+    j.cam_b = &cams[2 * k + 1];
+    j.matches = p.matches.data();
+    j.n_matches = (int64_t)(p.matches.size() / 4);
+    j.seed = p.seed;
+    j.kept_idx = o.kept.data();
+    j.template_xyz = o.points[0].data();
+    j.facets = o.facets.data();
+    j.deformed_xyz = o.deformed[0].data();
+    j.render = o.render.data();
+  }
+  check(mvs_stitch_pairs(context(), jobs.data(), (int64_t)n, params, res.data()));
+  for (size_t k = 0; k < n; ++k) {
+    ViewPairResult& o = out[k];
+    o.scale = res[k].scale;
+    o.err = res[k].err;
+    o.residual = res[k].residual;
+    std::memcpy(o.R.data(), res[k].R, sizeof(res[k].R));
+    std::memcpy(o.t.data(), res[k].t, sizeof(res[k].t));
+    o.kept.resize((size_t)res[k].n_kept);
+    o.points.resize((size_t)res[k].n_template);
+    o.deformed.resize((size_t)res[k].n_template);
+    o.facets.resize(3 * (size_t)res[k].n_facets);
+  }
+  return out;
+}
+
 }  // namespace mvs
 #endif  // MVS_SHIM_H

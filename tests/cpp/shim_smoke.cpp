@@ -108,6 +108,70 @@ int main() {
     for (float v : img)
       if (v != 0.25f) return 1;
     std::printf("Model2Depth plane ok (%zu px = 0.25)\n", img.size());
+    // ---- StitchPairs (Processor.cpp:629-826 pair loop): two views of a sphere 5 units away, view B's
+    // frame = planted similarity of view A's; lattice matches; both pairs must recover (s, R, t)
+    {
+      const int W = 640, H = 480;
+      auto render_sphere = [&](const Matrix3d& Rw, const Vector3d& tw, double sw, const Camera& c) {
+        // sphere of radius sw centred at sw * Rw * (0,0,5) + tw in the camera's world frame, camera
+        // [I | 0]: inverse depth of the front intersection per pixel
+        std::vector<float> d((size_t)W * H, 0.f);
+        double ctr[3];
+        for (int a = 0; a < 3; ++a) ctr[a] = sw * Rw(a, 2) * 5.0 + tw[a];
+        for (int v = 0; v < H; ++v)
+          for (int u = 0; u < W; ++u) {
+            double dir[3] = {(u - 319.5) / 525.0, (v - 239.5) / 525.0, 1.0};
+            double a2 = dir[0] * dir[0] + dir[1] * dir[1] + 1.0;
+            double b = dir[0] * ctr[0] + dir[1] * ctr[1] + ctr[2];
+            double c2 = ctr[0] * ctr[0] + ctr[1] * ctr[1] + ctr[2] * ctr[2] - sw * sw;
+            double disc = b * b - a2 * c2;
+            if (disc <= 0) continue;
+            double z = (b - std::sqrt(disc)) / a2;
+            if (z > 0) d[(size_t)v * W + u] = (float)(1.0 / z);
+          }
+        (void)c;
+        return d;
+      };
+      Matrix3d I3;
+      I3(0, 0) = I3(1, 1) = I3(2, 2) = 1.0;
+      Camera ca;
+      ca.SetK(K); ca.SetRT(I3, Vector3d()); ca.SetW(W); ca.SetH(H);
+      const double sp = 1.1;
+      Matrix3d Rp = axis_angle(0, 1, 0, 0.05);
+      Vector3d tp(0.05, -0.03, 0.2);
+      std::vector<float> da = render_sphere(I3, Vector3d(), 1.0, ca);
+      std::vector<float> db = render_sphere(Rp, tp, sp, ca);
+      ViewPair vp;
+      vp.depth_a = &da; vp.depth_b = &db; vp.cam_a = ca; vp.cam_b = ca;
+      for (int v = 10; v < H; v += 20)
+        for (int u = 10; u < W; u += 20) {
+          float d = da[(size_t)v * W + u];
+          if (!(d >= 0.0025f && d <= 0.3f)) continue;
+          double z = 1.0 / d, x = (u - 319.5) / 525.0 * z, y = (v - 239.5) / 525.0 * z, q[3];
+          for (int a = 0; a < 3; ++a) q[a] = sp * (Rp(a, 0) * x + Rp(a, 1) * y + Rp(a, 2) * z) + tp[a];
+          int u2 = (int)(525.0 * q[0] / q[2] + 319.5 + 0.5), v2 = (int)(525.0 * q[1] / q[2] + 239.5 + 0.5);
+          if (u2 < 0 || v2 < 0 || u2 >= W || v2 >= H) continue;
+          float d2 = db[(size_t)v2 * W + u2];
+          if (!(d2 >= 0.0025f && d2 <= 0.3f)) continue;
+          vp.matches.insert(vp.matches.end(), {u, v, u2, v2});
+        }
+      std::vector<ViewPair> pairs(2, vp);
+      pairs[1].seed = 7;
+      mvs_pair_params pp;
+      mvs_pair_default_params(&pp);
+      pp.n_nodes = 128;
+      pp.workers = 2;
+      auto res = StitchPairs(pairs, &pp);
+      for (const auto& r : res) {
+        if (std::fabs(r.scale - sp) > 0.03 * sp || r.points.empty() || r.deformed.size() != r.points.size())
+          return 1;
+        size_t covered = 0;
+        for (float v : r.render) covered += v > 0.f;
+        if (covered < 1000) return 1;
+      }
+      std::printf("StitchPairs ok: %zu matches, scale %.4f (planted %.2f), %zu vertices\n",
+                  vp.matches.size() / 4, res[0].scale, sp, res[0].points.size());
+    }
     return 0;
   } catch (const Error& e) {
     std::printf("error: %s\n", e.what());

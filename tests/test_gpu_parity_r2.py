@@ -245,3 +245,23 @@ def test_reference_sampling_rule_on_a_large_mesh_launch_per_phase_pcg(ctx):
     err = np.abs(out - oo).max() / diag(pts)
     assert err <= POS_TOL, err
     assert np.abs(out - targets).max() < 0.5 * np.abs(pts - targets).max()
+
+
+def test_diverging_solve_is_an_error(ctx):
+    """a PCG partial sum that is not finite (or leaves the fixed-point range of the
+    exchange words) used to be dropped silently; the solver kernel now raises a flag and the host
+    call returns an error code instead of a plausible-looking result."""
+    verts, faces = synth.uv_sphere(32, 24)
+    pts = verts.astype(np.float32)
+    d = api.Deformation(pts, None, faces, ctx)
+    d.SampleFPS(40, 0)
+    bad = pts.astype(np.float64) * 1e30  # the fit residuals overflow float32 when squared
+    d.SetTargets(bad)
+    with pytest.raises(api.MvsError):
+        d.Solve(api.gn_params(gn_iters=2, pcg_iters=10, corr_mode=2))
+    # the context stays usable and the next well-posed solve succeeds
+    d2 = api.Deformation(pts, None, faces, ctx)
+    d2.SampleFPS(40, 0)
+    d2.SetTargets(pts.astype(np.float64) * 1.01)
+    d2.Solve(api.gn_params(gn_iters=2, pcg_iters=10, corr_mode=2))
+    assert np.isfinite(d2.Vertices()).all()
