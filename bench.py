@@ -661,6 +661,8 @@ def c5_shard(args, api, local, stream, world, rank, dist, peak, side, nodes, ste
             d1.Solve(prm)
             equal = bool(np.array_equal(d1.Vertices(), out_dev) and np.array_equal(d1.NodeState(), x_dev))
             d1.close()
+        if world > 1:
+            dist.barrier()  # the ranks map each other's exchange blocks: release them together
         d.close()
         del flush, tgt4
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -1020,6 +1022,8 @@ def run_b200(args):
 
     # ---- release the headline workload before the two partitions
     with torch.cuda.stream(stream):
+        if world > 1:
+            dist.barrier()  # sharded handles map each other's exchange blocks: release them together
         d.close()
         del tgt4, flush
     torch.cuda.empty_cache()

@@ -439,6 +439,11 @@ int mvs_comm_destroy(mvs_ctx* ctx);
  * of the assembly group (4 runs of equal node tuples) that contains it, so ranks that split [0, n) at
  * common points tile it exactly and the all-reduced system is BITWISE the unsharded one. */
 int mvs_deform_set_shard(mvs_deform* h, int64_t v_begin, int64_t v_end);
+/* On a context with a communicator the partial systems are summed over NVLink peer memory (each
+ * rank's system lives in a block the other ranks map through CUDA IPC; ncclAllReduce is the fallback,
+ * also forced with MVS_NO_PEER=1).  Build the graph AFTER mvs_comm_init, run the same sequence of
+ * solves on every rank, and destroy sharded handles on all ranks together (after a barrier of the
+ * launcher): a rank must not free a block its peers still map. */
 /* Interleaved sharding: [0, n) is cut into nranks x chunks_per_rank chunks (boundaries snapped like
  * set_shard) and this rank owns chunks rank, rank + nranks, ...  The correspondence pass costs more
  * where the template is far from the scan, so contiguous ranges do not balance the ranks; a few

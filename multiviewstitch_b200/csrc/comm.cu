@@ -180,22 +180,22 @@ int peer_link_connect(mvs_ctx* ctx, PeerLink* L) {
   MVS_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerHello) * n, cudaMemcpyDeviceToHost, ctx->stream));
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_all);
-  for (int k = 0; k < n; ++k) {
+  int bad = 0;
+  for (int k = 0; k < n && !bad; ++k) {
     char* base = nullptr;
     if (k == ctx->rank) {
       base = (char*)L->block;
     } else {
       if (all[k].block_bytes != L->block_bytes) {
-        set_error("peer link: rank %d holds a different system (%llu vs %zu bytes)", k,
-                  all[k].block_bytes, L->block_bytes);
-        return MVS_ERR_COMM;
+        bad = 1;
+        break;
       }
       void* p = nullptr;
       cudaError_t e = cudaIpcOpenMemHandle(&p, all[k].handle, cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) {
         cudaGetLastError();
-        set_error("peer link: cudaIpcOpenMemHandle(rank %d): %s", k, cudaGetErrorString(e));
-        return MVS_ERR_COMM;
+        bad = 1;
+        break;
       }
       L->opened[k] = p;
       base = (char*)p + all[k].offset;
@@ -204,6 +204,27 @@ int peer_link_connect(mvs_ctx* ctx, PeerLink* L) {
     L->dev.sysf[k] = reinterpret_cast<float*>(base + L->off_sysf);
     L->dev.redf[k] = reinterpret_cast<float*>(base + L->off_redf);
     L->dev.flags[k] = reinterpret_cast<unsigned*>(base + L->off_flags);
+  }
+  // every rank must take the same path: agree on the outcome (sum of failures over the ranks)
+  double* d_bad = nullptr;
+  MVS_CUDA(cudaMalloc((void**)&d_bad, sizeof(double)));
+  double hb = (double)bad;
+  MVS_CUDA(cudaMemcpyAsync(d_bad, &hb, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = comm_allreduce_sum_f64(ctx, d_bad, 1);
+  if (rc == MVS_OK) {
+    MVS_CUDA(cudaMemcpyAsync(&hb, d_bad, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(d_bad);
+  MVS_TRY(rc);
+  if (hb > 0.0) {
+    for (int k = 0; k < kPeerMaxRanks; ++k)
+      if (L->opened[k]) {
+        cudaIpcCloseMemHandle(L->opened[k]);
+        L->opened[k] = nullptr;
+      }
+    L->failed = true;  // stay on ncclAllReduce (the systems simply live in the exchange block)
+    return MVS_OK;
   }
   L->ready = true;
   return MVS_OK;

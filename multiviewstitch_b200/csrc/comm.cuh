@@ -27,6 +27,7 @@ struct PeerLink {
   void* opened[kPeerMaxRanks] = {nullptr};  // peers' blocks (cudaIpcOpenMemHandle), null for self
   unsigned epoch = 0;           // barriers issued so far
   bool ready = false;
+  bool failed = false;          // the ranks agreed to stay on the NCCL path (IPC unavailable somewhere)
 };
 // allocates the block (n64 long longs, nf floats, flags); no communication
 int peer_block_alloc(mvs_ctx* ctx, size_t n64, size_t nf, PeerLink** out);

@@ -829,11 +829,12 @@ int gn_assemble(mvs_deform* h) {
   }
   MVS_CUDA(cudaGetLastError());
   const float inv_scale = (float)(1.0 / h->fx_scale);
-  if (ctx->comm && ctx->nranks > 1 && h->peer) {
+  if (ctx->comm && ctx->nranks > 1 && h->peer && !h->peer->ready && !h->peer->failed)
+    MVS_TRY(peer_link_connect(ctx, h->peer));  // collective; the ranks agree on ready / failed
+  if (ctx->comm && ctx->nranks > 1 && h->peer && h->peer->ready) {
     // vertex-sharded solve over peer memory: the node terms enter the sum once (rank 0; every rank
     // still needs the rotation blocks, which are node-local), then barrier -> fused reduce + convert
     // -> barrier, and the preconditioner reads the converted float system
-    if (!h->peer->ready) MVS_TRY(peer_link_connect(ctx, h->peer));
     MVS_TRY(gn_launch_node_terms(h, fxs, st, ctx->rank == 0 ? 1 : 0));
     {
       ProfScope ps(ctx, "gn_peer_barrier_in");
