@@ -132,7 +132,6 @@ int ensure_dyn_smem(const void* kernel, int device, int bytes) {
 int pinned_reserve(mvs_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->pinned_bytes) return MVS_OK;
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  if (ctx->solver_flag) cudaFreeHost(ctx->solver_flag);
   ctx->pinned = nullptr;
   ctx->pinned_bytes = 0;
   size_t want = bytes < 4096 ? 4096 : bytes;
@@ -220,6 +219,7 @@ static void ctx_free(mvs_ctx* ctx) {
   }
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->solver_flag) cudaFreeHost(ctx->solver_flag);
   for (int k = 0; k < 2; ++k) {
     if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
     if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
@@ -311,7 +311,7 @@ int mvs_ctx_create(mvs_ctx** out, int device, void* stream) {
     cudaGetLastError();
   }
   if (cudaHostAlloc((void**)&c->solver_flag, 64, cudaHostAllocMapped) == cudaSuccess && c->solver_flag)
-    *c->solver_flag = 0;
+    memset(c->solver_flag, 0, 64);
   else
     c->solver_flag = nullptr;
   cudaGetLastError();

@@ -146,9 +146,18 @@ static int gn_begin_impl(mvs_deform* h, const mvs_gn_params* p) {
 static int check_solver_flag(mvs_deform* h) {
   int* f = h->ctx->solver_flag;
   if (f && *reinterpret_cast<volatile int*>(f)) {
-    *f = 0;
-    set_error("Gauss-Newton solve diverged: a PCG partial sum was not finite or left the fixed-point "
-              "range (check the inputs and weights)");
+    const int why = *f;
+    float dv = 0.f, ds = 0.f;
+    memcpy(&dv, f + 1, 4);
+    memcpy(&ds, f + 2, 4);
+    f[0] = f[1] = f[2] = 0;
+    if (why == 1)
+      set_error("Gauss-Newton solve diverged: a PCG partial sum is not finite (check the inputs and weights)");
+    else if (why == 2)
+      set_error("Gauss-Newton solve diverged: a PCG partial sum left the range of the exchange words");
+    else
+      set_error("Gauss-Newton solve diverged: a normal-equation entry (%g at fixed-point scale %g) is not "
+                "finite or leaves the fixed-point range (targets far outside the mesh's reach?)", dv, ds);
     return MVS_ERR_DEGENERATE;
   }
   return MVS_OK;

@@ -254,7 +254,12 @@ __device__ __forceinline__ int find_slot(const int* __restrict__ row_ptr,
 // fit the fixed-point range — the bound behind gn_fx_scale assumes targets within reach of the mesh
 __device__ __forceinline__ void fx_add(long long* addr, float v, float scale, int* flag = nullptr) {
   const float sv = v * scale;
-  if (flag && !(fabsf(sv) < 4.0e18f)) *reinterpret_cast<volatile int*>(flag) = 1;
+  if (flag && !(fabsf(sv) < 4.0e18f)) {
+    volatile int* f = reinterpret_cast<volatile int*>(flag);
+    f[0] = 3;
+    f[1] = __float_as_int(v);      // diagnostics for the error text
+    f[2] = __float_as_int(scale);
+  }
   atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__float2ll_rn(sv));
 }
 

@@ -209,7 +209,7 @@ __device__ __forceinline__ long long fx_limb(double v, const FxUnit& u, int limb
     if (flag) *reinterpret_cast<volatile int*>(flag) = 1;
   }
   double hr = rint(v * u.inv_hi);
-  if (flag && fabs(hr) > (double)kLimbMax) *reinterpret_cast<volatile int*>(flag) = 1;
+  if (flag && fabs(hr) > (double)kLimbMax) *reinterpret_cast<volatile int*>(flag) = 2;
   double h = fmin(fmax(hr, (double)-kLimbMax), (double)kLimbMax);
   if (limb == 0) return (long long)h;
   double rem = v - h * u.hi;  // exact
