@@ -495,7 +495,7 @@ def c4_pairs(args, api, ctx, stream, world, rank, dist, steps, warmup, clocks_in
         for da, ca, db, cb, mt, _, u in work:
             batch.add(da, ca, db, cb, mt, seed=u)
         cores = os.cpu_count() or 1
-        want = args.pair_workers if args.pair_workers > 0 else max(1, min(12, cores // max(world, 1)))
+        want = args.pair_workers if args.pair_workers > 0 else max(1, min(16, cores // max(world, 1)))
         nw = max(1, min(want, len(work))) if work else 1
         prm = api.pair_params(n_nodes=512, gn_iters=4, workers=nw)
 

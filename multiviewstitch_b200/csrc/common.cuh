@@ -116,6 +116,12 @@ int ctx_side_join(mvs_ctx* ctx);
 struct AllocStream {
   cudaStream_t stream = nullptr;
   bool valid = false;
+  // bump arena of the calling thread (mvs_stitch_pairs: one per worker, reset per pair): while it is
+  // set, device buffers are carved from it without any driver call — a pair allocates and frees
+  // ~150 temporaries, and every cudaMallocAsync / cudaFreeAsync takes the process-wide driver lock
+  // the workers' launches contend for
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0, arena_missed = 0;
 };
 AllocStream& alloc_stream();
 
@@ -131,6 +137,7 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   bool external = false;      // points into memory owned elsewhere (adopt): never freed here
+  bool from_arena = false;    // carved from the thread's bump arena: never freed, may be re-carved
   void release() {
     if (p && !external) {
       if (async)
@@ -141,6 +148,7 @@ struct DevBuf {
     p = nullptr;
     cap = 0;
     external = false;
+    from_arena = false;
   }
   // view of `n` elements inside a block somebody else owns (the IPC exchange block of a sharded solve)
   void adopt(T* ptr, size_t n) {
@@ -151,13 +159,25 @@ struct DevBuf {
   }
   int reserve(size_t n) {
     if (n <= cap) return MVS_OK;
-    if (external) {
+    if (external && !from_arena) {
       set_error("internal: an adopted buffer of %zu elements cannot grow to %zu", cap, n);
       return MVS_ERR_STATE;
     }
     release();
     size_t bytes = (n ? n : 1) * sizeof(T);
     AllocStream& as = alloc_stream();
+    if (as.arena) {
+      size_t off = (as.arena_off + 255) & ~(size_t)255;
+      if (off + bytes <= as.arena_cap) {
+        p = reinterpret_cast<T*>(as.arena + off);
+        as.arena_off = off + bytes;
+        cap = n ? n : 1;
+        external = true;
+        from_arena = true;
+        return MVS_OK;
+      }
+      as.arena_missed += bytes;  // does not fit: fall through to the pool (the arena grows next time)
+    }
     cudaError_t e;
     if (as.valid) {
       e = cudaMallocAsync((void**)&p, bytes, as.stream);

@@ -777,9 +777,10 @@ int mvs_deform_set_node_state(mvs_deform* h, const float* A_t) {
 
 static int get_f4_as_xyz(mvs_deform* h, const float4* src, int64_t n, double* out64, float* out32) {
   mvs_ctx* ctx = h->ctx;
-  void* tmp = nullptr;
   size_t bytes = (out64 ? sizeof(double) : sizeof(float)) * 3 * n;
-  MVS_CUDA(cudaMallocAsync(&tmp, bytes, ctx->stream));
+  DevBuf<char> tmp_buf;
+  MVS_TRY(tmp_buf.reserve(bytes));
+  void* tmp = tmp_buf.p;
   {
     ProfScope ps(ctx, "unpack_xyz");
     if (out64)
@@ -788,7 +789,6 @@ static int get_f4_as_xyz(mvs_deform* h, const float4* src, int64_t n, double* ou
       k_f4_to_f32xyz<<<div_up(n, 256), 256, 0, ctx->stream>>>(src, (float*)tmp, n);
   }
   int rc = d2h_async(ctx, out64 ? (void*)out64 : (void*)out32, tmp, bytes);
-  cudaFreeAsync(tmp, ctx->stream);
   if (rc != MVS_OK) return rc;
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   return MVS_OK;

@@ -531,8 +531,9 @@ int mvs_srt_set_input(mvs_srt* h, const double* p, const double* q, int64_t n,
   srt_set_cams(h, cam1, cam2);
   if (n == 0) return MVS_OK;
   MVS_TRY(h->planes.reserve((size_t)6 * n));
-  double* staging = nullptr;
-  MVS_CUDA(cudaMallocAsync((void**)&staging, sizeof(double) * 6 * n, ctx->stream));
+  DevBuf<double> staging_buf;  // stream-ordered (or the worker's arena): released behind the pack kernel
+  MVS_TRY(staging_buf.reserve((size_t)6 * n));
+  double* staging = staging_buf.p;
   int st = h2d(ctx, staging, p, sizeof(double) * 3 * n);
   if (st == MVS_OK) st = h2d(ctx, staging + 3 * n, q, sizeof(double) * 3 * n);
   if (st == MVS_OK) {
@@ -540,7 +541,6 @@ int mvs_srt_set_input(mvs_srt* h, const double* p, const double* q, int64_t n,
     k_pack_planes<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(staging, staging + 3 * n,
                                                                      h->planes.p, n);
   }
-  cudaFreeAsync(staging, ctx->stream);
   MVS_TRY(st);
   MVS_CUDA(cudaGetLastError());
   // SetInput COPIES (Solver/SRTSolver.h:16-19): the caller may reuse or free p/q as soon as this

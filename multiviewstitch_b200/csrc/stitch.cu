@@ -34,7 +34,40 @@ namespace mvs {
 struct PairScratch {
   std::vector<int32_t> uv, okf, keep;
   std::vector<double> p, q, pk, qk;
+  // device bump arena of this worker (common.cuh AllocStream): every temporary of a pair
+  char* arena = nullptr;
+  size_t arena_cap = 0;
 };
+
+constexpr size_t kArenaStart = (size_t)96 << 20;
+
+// every device buffer created by this thread until arena_off() comes from the worker's arena
+static int arena_on(mvs_ctx* ctx, PairScratch& S) {
+  if (getenv("MVS_NO_ARENA")) return MVS_OK;
+  AllocStream& as = alloc_stream();
+  size_t want = std::max(S.arena_cap, kArenaStart);
+  if (as.arena_missed > 0) want = std::max(want, S.arena_cap + 2 * as.arena_missed + (kArenaStart >> 1));
+  as.arena_missed = 0;
+  if (want > S.arena_cap) {
+    if (S.arena) cudaFree(S.arena);
+    S.arena = nullptr;
+    S.arena_cap = 0;
+    if (cudaMalloc((void**)&S.arena, want) != cudaSuccess) {
+      cudaGetLastError();
+      return MVS_OK;  // no arena: the stream-ordered pool serves the pair
+    }
+    S.arena_cap = want;
+  }
+  as.arena = S.arena;
+  as.arena_cap = S.arena_cap;
+  as.arena_off = 0;
+  return MVS_OK;
+}
+static void arena_off() {
+  AllocStream& as = alloc_stream();
+  as.arena = nullptr;
+  as.arena_cap = as.arena_off = 0;
+}
 
 struct StitchPool {
   std::mutex mu;
@@ -70,7 +103,10 @@ void stitch_pool_release(mvs_ctx* parent) {
     g_pools.erase(it);
   }
   for (mvs_ctx* w : p->workers) mvs_ctx_destroy(w);
-  for (PairScratch* sc : p->scratch) delete sc;
+  for (PairScratch* sc : p->scratch) {
+    if (sc->arena) cudaFree(sc->arena);
+    delete sc;
+  }
   delete p;
 }
 
@@ -279,7 +315,9 @@ int mvs_stitch_pairs(mvs_ctx* ctx, const mvs_pair_job* jobs, int64_t n_jobs,
     for (;;) {
       int64_t i = next.fetch_add(1);
       if (i >= n_jobs) break;
+      arena_on(w, *pool->scratch[k]);
       int rc = run_pair(w, *pool->scratch[k], jobs[i], *params, results[i], trace ? &stage_ms[(size_t)k * 2 * ST_COUNT] : nullptr);
+      arena_off();  // run_pair destroyed everything it created; the stream is idle
       results[i].status = rc;
       if (rc != MVS_OK && errs[k].empty()) errs[k] = mvs_last_error();
     }
