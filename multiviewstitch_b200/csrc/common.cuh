@@ -215,6 +215,9 @@ inline int grid_for(const mvs_ctx* ctx, int64_t work_items, int block, int ctas_
 int ensure_dyn_smem(const void* kernel, int device, int bytes);
 
 int pinned_reserve(mvs_ctx* ctx, size_t bytes);
+// true for ordinary (unregistered) host memory: cudaMemcpyAsync from it has staged the data when it
+// returns, so the caller's buffer may be reused at once; pinned memory is read by the DMA engine later
+bool host_is_pageable(const void* p);
 
 // Host <-> device helpers on the context stream.
 int h2d(mvs_ctx* ctx, void* dst, const void* src, size_t bytes);

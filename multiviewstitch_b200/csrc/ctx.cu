@@ -154,7 +154,7 @@ int h2d(mvs_ctx* ctx, void* dst, const void* src, size_t bytes) {
 constexpr size_t kStageChunk = (size_t)1 << 20;
 constexpr size_t kStageMin = (size_t)1 << 19;
 
-static bool host_is_pageable(const void* p) {
+bool host_is_pageable(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();

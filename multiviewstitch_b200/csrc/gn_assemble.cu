@@ -764,6 +764,11 @@ __global__ void k_sys_expand(const float* __restrict__ in, float* __restrict__ o
   }
 }
 
+// Below this many vertices the node terms and the preconditioner run on the main stream: on a view
+// mesh (35K vertices) the kernels they would overlap last a few microseconds, while every fork/join
+// is four driver calls (8 per GN iteration) that the workers of mvs_stitch_pairs contend for.
+constexpr int64_t kSideStreamMinVerts = 200000;
+
 // fixed-point scale: the largest power of two that cannot overflow int64 for this problem (every
 // entry is bounded by w_fit omega_max n max(1, D^2) plus the node terms)
 static float gn_fx_scale(mvs_deform* h) {
@@ -798,6 +803,7 @@ int gn_node_terms_forked(mvs_deform* h) {
   mvs_ctx* ctx = h->ctx;
   h->node_terms_forked = false;
   if (ctx->comm && ctx->nranks > 1) return MVS_OK;
+  if (h->n < kSideStreamMinVerts) return MVS_OK;  // small mesh: the fork/join calls cost more than they hide
   float fxs = gn_fx_scale(h);
   MVS_TRY(ctx_side_fork(ctx));
   MVS_TRY(gn_zero_system(h, ctx->side));
@@ -885,10 +891,12 @@ int gn_assemble(mvs_deform* h) {
   if (!forked) MVS_TRY(gn_launch_node_terms(h, fxs, st));
   // conversion (main stream) and block-Jacobi inverses (side stream) both read the finished
   // fixed-point system
-  MVS_TRY(ctx_side_fork(ctx));
+  const bool side = h->n >= kSideStreamMinVerts;
+  cudaStream_t pst = side ? ctx->side : st;
+  if (side) MVS_TRY(ctx_side_fork(ctx));
   {
-    ProfScope ps(ctx, "gn_precond", 1, ctx->side);
-    k_precond<<<div_up(h->m * kNodeLanes, 128), 128, 0, ctx->side>>>(
+    ProfScope ps(ctx, "gn_precond", 1, pst);
+    k_precond<<<div_up(h->m * kNodeLanes, 128), 128, 0, pst>>>(
         h->row_ptr.p, h->col.p, h->uidx.p, h->B64(), inv_scale, h->Rot(), h->m, h->prm.lambda,
         h->Minv.p, nullptr);
   }
@@ -900,7 +908,7 @@ int gn_assemble(mvs_deform* h) {
         h->sys64.p, h->sys.p, nout, h->nnz * 16, h->nup * 16, h->tslot.p, h->uidx.p, inv_scale);
   }
   MVS_CUDA(cudaGetLastError());
-  MVS_TRY(ctx_side_join(ctx));
+  if (side) MVS_TRY(ctx_side_join(ctx));
   return MVS_OK;
 }
 

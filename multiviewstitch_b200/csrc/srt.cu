@@ -544,8 +544,9 @@ int mvs_srt_set_input(mvs_srt* h, const double* p, const double* q, int64_t n,
   MVS_TRY(st);
   MVS_CUDA(cudaGetLastError());
   // SetInput COPIES (Solver/SRTSolver.h:16-19): the caller may reuse or free p/q as soon as this
-  // returns, also when they are pinned (a pinned source is read by the DMA engine asynchronously)
-  MVS_CUDA(cudaStreamSynchronize(ctx->stream));
+  // returns.  Pageable sources are staged by the driver before cudaMemcpyAsync returns; a pinned
+  // source is read by the DMA engine asynchronously, so only then wait for the stream
+  if (!host_is_pageable(p) || !host_is_pageable(q)) MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   return MVS_OK;
 }
 
@@ -564,7 +565,8 @@ int mvs_srt_set_input_f32(mvs_srt* h, const float* p, const float* q, int64_t n,
   MVS_TRY(h2d(ctx, h->qf.p, q, sizeof(float4) * n));
   h->p4 = h->pf.p;
   h->q4 = h->qf.p;
-  MVS_CUDA(cudaStreamSynchronize(ctx->stream));  // copy semantics, see mvs_srt_set_input
+  if (!host_is_pageable(p) || !host_is_pageable(q))
+    MVS_CUDA(cudaStreamSynchronize(ctx->stream));  // copy semantics, see mvs_srt_set_input
   return MVS_OK;
 }
 
