@@ -104,7 +104,9 @@ int mvs_srt_create(mvs_ctx* ctx, mvs_srt** out);
 int mvs_srt_destroy(mvs_srt* h);
 /* [ref: Solver/SRTSolver.h:12-20 SetInput] p = matches[i].first, q = matches[i].second, n x 3
  * doubles each.  Kept in float64 on the device (matches come from double unprojection,
- * Processor.cpp:806-811). cameras may be NULL if residual/RANSAC are not used. */
+ * Processor.cpp:806-811). cameras may be NULL if residual/RANSAC are not used.  The callee COPIES:
+ * p/q may be reused or freed as soon as the call returns, pinned or pageable (for a pinned source the
+ * call waits for the transfer). */
 int mvs_srt_set_input(mvs_srt* h, const double* p_xyz, const double* q_xyz, int64_t n,
                       const mvs_camera* cam1, const mvs_camera* cam2);
 /* float32 xyzw (float4) variants: host or device resident (the C2 bandwidth sweep layout). */
@@ -412,7 +414,8 @@ typedef struct mvs_pair_params {
   mvs_outlier_params outliers;   /* seed is taken from the job */
   int64_t n_nodes;               /* deformation-graph nodes (farthest point sampling), 512 */
   mvs_gn_params gn;              /* corr_mode 1, 4 GN x 20 PCG by default */
-  int32_t workers;               /* host threads; 0 = min(8, hardware threads / 2) */
+  int32_t workers;               /* host threads; 0 = min(8, hardware threads / 2).  Each worker owns a
+                                    stream and a device arena for the temporaries of a pair */
   int32_t reserved;
 } mvs_pair_params;
 typedef struct mvs_pair_result {
