@@ -178,7 +178,10 @@ struct mvs_deform {
 
 namespace mvs {
 
-constexpr int kGrpRuns = 4;             // runs per assembly group
+#ifndef MVS_GRP_RUNS
+#define MVS_GRP_RUNS 4
+#endif
+constexpr int kGrpRuns = MVS_GRP_RUNS;  // runs per assembly group
 constexpr int kGrpMax = 14 * kGrpRuns;  // 10 upper-triangle block tiles + 4 gradient tiles per run
 
 // the sub-ranges of one launch of the per-vertex passes (a rank's interleaved chunks): up to 16, mapped
