@@ -453,7 +453,7 @@ int mvs_deform_set_shard(mvs_deform* h, int64_t v_begin, int64_t v_end);
  * chunks per rank spread over the mesh do.  Same bits as the unsharded solve.  nranks = 0 returns to
  * the plain range of mvs_deform_set_shard. */
 int mvs_deform_set_shard_interleaved(mvs_deform* h, int rank, int nranks, int chunks_per_rank);
-/* Work through this rank's vertex range as `parts` consecutive sub-ranges, one launch each: the
+/* Work through this rank's vertex range as `parts` consecutive sub-ranges (group-aligned): the
  * partial sums `parts` ranks would produce, added by the same commutative integer additions the
  * all-reduce performs — the sharded arithmetic checked on ONE GPU (result bitwise equal to
  * parts = 1).  Default 1. */
