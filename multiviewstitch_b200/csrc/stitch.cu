@@ -45,8 +45,13 @@ constexpr size_t kArenaStart = (size_t)96 << 20;
 static int arena_on(mvs_ctx* ctx, PairScratch& S) {
   if (getenv("MVS_NO_ARENA")) return MVS_OK;
   AllocStream& as = alloc_stream();
-  size_t want = std::max(S.arena_cap, kArenaStart);
-  if (as.arena_missed > 0) want = std::max(want, S.arena_cap + 2 * as.arena_missed + (kArenaStart >> 1));
+  size_t start = kArenaStart;
+  if (const char* env = getenv("MVS_ARENA_MB")) {  // test hook: a small arena exercises the fallback
+    long mb = atol(env);
+    if (mb > 0) start = (size_t)mb << 20;
+  }
+  size_t want = std::max(S.arena_cap, start);
+  if (as.arena_missed > 0) want = std::max(want, S.arena_cap + 2 * as.arena_missed + (start >> 1));
   as.arena_missed = 0;
   if (want > S.arena_cap) {
     if (S.arena) cudaFree(S.arena);

@@ -11,6 +11,9 @@ from tests import synth
 
 pytestmark = pytest.mark.gpu
 
+from pathlib import Path
+ROOT_DIR = Path(__file__).resolve().parents[1]
+
 
 def _cam(mod, w=64, h=48, f=60.0, R=None, t=None):
     K = np.array([[f, 0, w / 2 - 0.5], [0, f, h / 2 - 0.5], [0, 0, 1.0]])
@@ -200,3 +203,35 @@ def test_stitch_pairs_one_call_equals_stage_by_stage(ctx, workers):
     bad.add(np.zeros_like(da), ca, db, cb, mt)
     with pytest.raises(_capi.MvsError):
         bad.run(api.pair_params(workers=1))
+
+
+def test_stitch_pairs_arena_fallback_and_growth(ctx):
+    """The workers of mvs_stitch_pairs carve a pair's temporaries from a bump arena; a pair that does
+    not fit falls back to the stream-ordered pool for the rest and the arena grows for the next pair.
+    Same bits either way.  (Run in a subprocess: the arena size is read from the environment.)"""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        from multiviewstitch_b200 import api
+        from tests.test_gpu_pipeline import _pair_inputs
+        ctx = api.Context(0)
+        da, ca, db, cb, mt, _ = _pair_inputs(ctx, 0)
+        outs = []
+        for rep in range(3):
+            b = api.PairBatch(ctx)
+            b.add(da, ca, db, cb, mt, seed=1)
+            o = b.run(api.pair_params(n_nodes=150, gn_iters=2, workers=1))[0]
+            outs.append(o)
+        for o in outs[1:]:
+            assert np.array_equal(o["deformed"], outs[0]["deformed"]) and np.array_equal(o["render"], outs[0]["render"])
+        np.save(sys.argv[1], outs[0]["deformed"])
+    """ % str(ROOT_DIR))
+    outs = []
+    for mb in ("1", "96"):
+        path = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"mvs_arena_{mb}.npy")
+        env = dict(os.environ, MVS_ARENA_MB=mb)
+        r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1])
