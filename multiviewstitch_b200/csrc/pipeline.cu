@@ -277,10 +277,16 @@ int mvs_remove_outliers(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, 
   int64_t size = n;
   double e = HUGE_VAL, ratio = 1.0;
   std::vector<uint8_t> flags;
+  // one solver for all rounds (the reference constructs one per round, Processor.cpp:202; SetInput
+  // replaces the matches): its device buffers are reused and destroyed — one stream wait — once
+  mvs_srt* s = nullptr;
+  MVS_TRY(mvs_srt_create(ctx, &s));
+  struct Guard {
+    mvs_srt* s;
+    ~Guard() { mvs_srt_destroy(s); }
+  } guard{s};
   for (int k = 0; k < params->rounds; ++k) {
     if (size < 3) break;  // the reference would index an empty match list (:131-146)
-    mvs_srt* s = nullptr;
-    MVS_TRY(mvs_srt_create(ctx, &s));
     int rc = mvs_srt_set_iteration_num(s, params->iter_num);
     if (rc == MVS_OK) rc = mvs_srt_set_print(s, 0);
     if (rc == MVS_OK) rc = mvs_srt_set_input(s, p.data(), q.data(), size, cam1, cam2);
@@ -292,7 +298,6 @@ int mvs_remove_outliers(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, 
     int64_t nin = 0;
     if (rc == MVS_OK)
       rc = mvs_srt_inliers(s, sc, R, t, params->pixel_err * ratio, flags.data(), &err_all, &nin);
-    mvs_srt_destroy(s);
     MVS_TRY(rc);
     int64_t m = 0;
     for (int64_t i = 0; i < size; ++i) {
