@@ -15,8 +15,9 @@ A "step" is one such 10-iteration solve starting from the identity node state.
   e2e    = the same metric through the host-buffer C ABI a reference caller would use:
            mvs_deform_set_target_f32(host) -> mvs_deform_solve -> mvs_deform_get_vertices_f32(host),
            H2D/D2H inside the timed region
-  --gpus N: one process per GPU.  The headline line is N independent C3 meshes (the reference's
-           independent objects, no data-path collective, scaling "weak"); at EVERY N the line also
+  --gpus N: one process per GPU.  The headline line is N independent C3 solves, every rank on its own
+           copy of the same mesh (the reference's independent objects, no data-path collective,
+           scaling "weak"); at EVERY N the line also
            carries north_star's two partitions: secondary.c4_pairs (configs[3]: 28 view pairs sharded
            pair -> rank, one mvs_stitch_pairs call per rank) and secondary.c5_shard (configs[4]: ONE
            5M-vertex / 20K-node graph vertex-sharded over the ranks with an NCCL all-reduce of the
@@ -812,7 +813,10 @@ def run_b200(args):
         peaks = json.loads(pk_file.read_text())
     peak = float(peaks.get("hbm_gbs", 6650.0))
 
-    pts, nrm, faces, tgt = workload(args, 0 if (shard or world == 1) else rank)
+    # every rank solves ITS OWN copy of the same object (weak scaling: the per-GPU work is fixed; a
+    # different similarity per rank changes how the scan falls into search cells and with it the
+    # correspondence time by several per cent — that is object variance, not scaling)
+    pts, nrm, faces, tgt = workload(args, 0)
     n, nt = len(pts), len(tgt)
     if shard:
         uid = [api.Context.comm_unique_id() if rank == 0 else None]
