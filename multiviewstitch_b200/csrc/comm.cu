@@ -150,8 +150,16 @@ int peer_link_connect(mvs_ctx* ctx, PeerLink* L) {
   const int n = ctx->nranks;
   PeerHello mine;
   memset(&mine, 0, sizeof(mine));
-  MVS_CUDA(cudaIpcGetMemHandle(&mine.handle, L->block));
-  mine.block_bytes = L->block_bytes;
+  // a rank that cannot export its block still takes part in the exchanges below (an early return
+  // would leave the other ranks waiting in the all-gather): it announces 0 bytes, which every peer
+  // reads as a mismatch, and the ranks then agree to stay on ncclAllReduce
+  int bad = 0;
+  if (cudaIpcGetMemHandle(&mine.handle, L->block) != cudaSuccess) {
+    cudaGetLastError();
+    memset(&mine.handle, 0, sizeof(mine.handle));
+    bad = 1;
+  }
+  mine.block_bytes = bad ? 0 : L->block_bytes;
   // the handle names the whole underlying allocation: find the block's offset inside it
   mine.offset = 0;
   {
@@ -180,7 +188,6 @@ int peer_link_connect(mvs_ctx* ctx, PeerLink* L) {
   MVS_CUDA(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerHello) * n, cudaMemcpyDeviceToHost, ctx->stream));
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_all);
-  int bad = 0;
   for (int k = 0; k < n && !bad; ++k) {
     char* base = nullptr;
     if (k == ctx->rank) {

@@ -309,13 +309,17 @@ int mvs_stitch_pairs(mvs_ctx* ctx, const mvs_pair_job* jobs, int64_t n_jobs,
   MVS_CUDA(cudaStreamSynchronize(ctx->stream));
   std::atomic<int64_t> next{0};
   std::vector<std::string> errs((size_t)W);
+  for (int64_t i = 0; i < n_jobs; ++i) results[i].status = MVS_ERR_NO_DEVICE;  // until a worker ran it
   std::vector<int64_t> launches((size_t)W, 0);
   const char* trace_env = getenv("MVS_STITCH_TRACE");
   const bool trace = trace_env && trace_env[0] == '1';
   std::vector<double> stage_ms(trace ? (size_t)W * 2 * ST_COUNT : 0, 0.0);
   auto body = [&](int k) {
     mvs_ctx* w = pool->workers[k];
-    if (ctx_ensure_device(w) != MVS_OK) return;
+    if (ctx_ensure_device(w) != MVS_OK) {  // the other workers take the jobs; if none can, the
+      errs[k] = mvs_last_error();          // results keep the status set below
+      return;
+    }
     int64_t before = w->launch_count;
     for (;;) {
       int64_t i = next.fetch_add(1);
