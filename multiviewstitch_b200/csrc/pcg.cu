@@ -643,10 +643,10 @@ static int plan_pcg(mvs_deform* h) {
 // ------------------------------------------------------------------ launch-per-phase solver
 // Graphs whose rows are not co-resident in one cooperative grid (more than ~37,000 nodes: the
 // reference's own 16-NN sampling rule, Deformation.cpp:63-106, yields 60-100 K nodes on a 1M-vertex
-// mesh) run the same recurrences as three launches per iteration — product + p.q, update + r.z,
-// direction — with the scalars kept on the device (no host synchronisation) and the same fixed-order
-// float64 reductions (reduce.cuh), so the solve stays bit-reproducible.  At that size every launch
-// streams tens of MB, so launch latency no longer dominates.
+// mesh) run the same recurrences as four launches per iteration — product + p.q, update + r.z,
+// direction, one-thread scalar roll — with the scalars kept on the device (no host synchronisation)
+// and the same fixed-order float64 reductions (reduce.cuh), so the solve stays bit-reproducible.  At
+// that size every launch streams tens of MB, so launch latency no longer dominates.
 constexpr int kLThreads = 256;
 constexpr int kLGroups = kLThreads / kRowLanes;
 
