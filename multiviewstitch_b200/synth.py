@@ -189,6 +189,59 @@ def humanoid(n_per_part=400, seed=0, arm_angle=0.5, leg_angle=0.12, scale=1.0):
     return pts, np.concatenate(L, 0)
 
 
+def humanoid_mesh(nu=16, nv=12, arm_angle=0.5, leg_angle=0.12, ground=None):
+    """The layout of `humanoid` as ONE connected triangle mesh: every part an ellipsoid mesh, joined to
+    the previous part by a bridging facet (connectivity is all Alignment::RetainConnectRegion looks
+    at).  ground = (radius, n): a flat grid patch under the feet, joined to a foot the same way — the
+    input shape of Alignment::Align's target.  Returns (verts, faces, labels); ground label = -1."""
+    sv, sf = uv_sphere(nu, nv, bumps=0.0)
+    V, F, L = [], [], []
+    off = 0
+
+    def add(center, radii, label, axis=None):
+        nonlocal off
+        v = sv[:, [0, 2, 1]] * np.asarray(radii)  # the sphere's pole axis -> y
+        f = sf[:, [0, 2, 1]]
+        if axis is not None:
+            a = np.asarray(axis, np.float64)
+            a = a / np.linalg.norm(a)
+            yv = np.array([0, 1.0, 0])
+            c = np.cross(yv, a)
+            if np.linalg.norm(c) > 1e-12:
+                v = v @ axis_angle(c, np.arccos(np.clip(yv @ a, -1, 1))).T
+        V.append(v + np.asarray(center))
+        F.append(f + off)
+        if off:
+            F.append(np.array([[off - 1, off, off + 1]]))  # bridge to the previous part
+        L.append(np.full(len(v), label, np.int32))
+        off += len(v)
+
+    add([0, -0.78, 0], [0.10, 0.12, 0.10], 0)
+    add([0, -0.62, 0], [0.05, 0.05, 0.05], 1)
+    add([0, -0.35, 0], [0.20, 0.25, 0.11], 14)
+    add([0, -0.05, 0], [0.19, 0.10, 0.11], 15)
+    for side, (ua, la, ha) in ((+1, (2, 3, 4)), (-1, (5, 6, 7))):
+        d = np.array([side * np.sin(arm_angle), np.cos(arm_angle), 0.0])
+        sh = np.array([side * 0.24, -0.52, 0.0])
+        add(sh + 0.14 * d, [0.05, 0.15, 0.05], ua, axis=d)
+        add(sh + 0.42 * d, [0.04, 0.14, 0.04], la, axis=d)
+        add(sh + 0.62 * d, [0.04, 0.06, 0.03], ha, axis=d)
+    for side, (th, shk, ft) in ((+1, (8, 9, 10)), (-1, (11, 12, 13))):
+        d = np.array([side * np.sin(leg_angle), np.cos(leg_angle), 0.0])
+        hp = np.array([side * 0.10, 0.05, 0.0])
+        add(hp + 0.22 * d, [0.08, 0.22, 0.08], th, axis=d)
+        add(hp + 0.64 * d, [0.06, 0.21, 0.06], shk, axis=d)
+        add(hp + 0.90 * d + np.array([0, 0, 0.05]), [0.05, 0.04, 0.10], ft)
+    if ground is not None:
+        ymax = max(v[:, 1].max() for v in V)
+        gv, gf = grid_disk(ground[0], ground[1], y=ymax - 0.005)
+        V.append(gv)
+        F.append(gf + off)
+        F.append(np.array([[off - 1, off, off + 1]]))
+        L.append(np.full(len(gv), -1, np.int32))
+    return (np.concatenate(V, 0), np.concatenate(F, 0).astype(np.int32), np.concatenate(L, 0))
+
+
 def cube_sphere(n, radius=1.0, bumps=0.05, rot=None):
     """Closed genus-0 triangle mesh with near-uniform vertex density: the 6 faces of a cube, each an
     n x n quad grid (tangent-warped), projected onto the sphere, with the same low-frequency bumps as

@@ -429,6 +429,21 @@ def init_alignment(src, tgt, ground_ray, view_ray):
     return T.reshape(4, 4), sc.value
 
 
+def local_alignment_core(src, s_labels, tgt, t_labels, sel_labels, label):
+    s, t = _f64(src).reshape(-1, 3), _f64(tgt).reshape(-1, 3)
+    sl, tl = _i32(s_labels), _i32(t_labels)
+    mask = 0
+    for k in sel_labels:
+        mask |= 1 << int(k)
+    T = np.empty(16)
+    sc = C.c_double()
+    ok = lib().orc_local_alignment_core(_p(s, C.c_double), _p(sl, C.c_int32), C.c_int64(len(s)),
+                                        _p(t, C.c_double), _p(tl, C.c_int32), C.c_int64(len(t)),
+                                        C.c_uint(mask), C.c_int(label), _p(T, C.c_double),
+                                        C.byref(sc))
+    return T.reshape(4, 4), sc.value, bool(ok)
+
+
 def align(src, s_normals, s_labels, tgt, t_normals, t_facets, view_ray, dist_thres=0.8,
           ground_ratio=0.28, remove_ground=1, local_align=1, neck_label=1, ground_ray=None):
     s = _f64(src).reshape(-1, 3).copy()

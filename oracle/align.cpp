@@ -526,4 +526,22 @@ void orc_align(double* src, double* src_normals, int64_t ns, const int32_t* src_
   if (out_tgt_labels) std::memcpy(out_tgt_labels, tl.data(), sizeof(int32_t) * (size_t)*nt);
 }
 
+// Alignment.cpp:423-546 alone: the limb = the points whose label is in sel_mask; transform row-major
+// 4x4 = [R | translate] as the reference returns it.  Returns 0 when a subset is empty.
+int orc_local_alignment_core(const double* src, const int32_t* s_labels, int64_t ns,
+                             const double* tgt, const int32_t* t_labels, int64_t nt,
+                             unsigned sel_mask, int label, double transform[16], double* scale) {
+  double sc = 1.0;
+  M3 R = m3_identity();
+  V3 t{{0, 0, 0}};
+  bool ok = local_core(src, s_labels, ns, tgt, t_labels, nt, sel_mask, label, &sc, &R, &t);
+  for (int i = 0; i < 16; ++i) transform[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) transform[4 * i + j] = M(R)[3 * i + j];
+    transform[4 * i + 3] = t.x[i];
+  }
+  *scale = sc;
+  return ok ? 1 : 0;
+}
+
 }  // extern "C"

@@ -3,7 +3,10 @@
 ctypes front-end of oracle/_ref/libmvsref.so: the reference's own first-party sources
 (Solver/SRTSolver.cpp, Camera/Camera.cpp, SetUtils/PointSetUtils.cpp, SetUtils/UnionSetUtils.cpp,
 Depth2Model/Depth2Model.cpp, Common/Utils.h) compiled UNMODIFIED from /root/reference by
-`make -C oracle ref` against the stand-in headers in oracle/compat/ (see oracle/ref_shim.cpp).
+`make -C oracle ref` against the stand-in headers in oracle/compat/ (see oracle/ref_shim.cpp), and
+Alignment/Alignment.cpp, PartRecognition/PartRecognition.cpp, PlyObj/PlyObj.cpp,
+Parameter/ParamParser.cpp compiled from their source text with two headers passed through one sed
+rule (an MSVC-only default-argument form; see oracle/ref_shim_align.cpp and oracle/Makefile).
 Used to pin the restatement in oracle/*.cpp (tests/test_ref_parity.py), to generate the committed
 vectors tests/golden/ref_*.npz (tests/golden/make_ref_golden.py) and as the `kind: "reference"` CPU
 leg of bench.py's SRT line.  The product never loads it.
@@ -164,3 +167,124 @@ def load_depth(filename: str, w: int, h: int):
     d = np.empty(w * h)
     lib().ref_load_depth(str(filename).encode(), _p(d, C.c_double), C.c_int(w), C.c_int(h))
     return d
+
+
+# ----------------------------------------------------------------------------- Alignment / PlyObj
+# (oracle/ref_shim_align.cpp: the reference's Alignment, PartRecognition and Mesh classes)
+PART_NAMES = ["Head", "Neck", "LeftUpperArm", "LeftLowerArm", "LeftHand", "RightUpperArm",
+              "RightLowerArm", "RightHand", "LeftThigh", "LeftShank", "LeftFoot", "RightThigh",
+              "RightShank", "RightFoot", "Truncus", "Hip"]  # PartRecognition.h:13-30
+
+
+def write_parts_file(workdir, labels):
+    """The template's labels in the reference's own file format (`Head=1;5;9`,
+    PartRecognition/PartRecognition.cpp:7-48), where Alignment::Align looks for them."""
+    d = Path(workdir) / "Template" / "part"
+    d.mkdir(parents=True, exist_ok=True)
+    labels = np.asarray(labels)
+    with open(d / "parts", "w") as f:
+        for k, name in enumerate(PART_NAMES):
+            ids = np.nonzero(labels == k)[0]
+            if len(ids):
+                f.write(name + "=" + ";".join(str(int(i)) for i in ids) + "\n")
+
+
+def retain_connected(pts, normals, facets):
+    p = _f64(pts).reshape(-1, 3).copy()
+    nr = _f64(normals).reshape(-1, 3).copy()
+    f = _i32(facets).reshape(-1).copy()
+    n, nf = C.c_int64(len(p)), C.c_int64(len(f) // 3)
+    lib().ref_retain_connected(_p(p, C.c_double), _p(nr, C.c_double), C.byref(n), _p(f, C.c_int32),
+                               C.byref(nf))
+    return p[:n.value].copy(), nr[:n.value].copy(), f[:3 * nf.value].reshape(-1, 3).copy()
+
+
+def remove_ground(pts, normals, facets, dist_thres, workdir):
+    p = _f64(pts).reshape(-1, 3).copy()
+    nr = _f64(normals).reshape(-1, 3).copy()
+    f = _i32(facets).reshape(-1).copy()
+    n, nf = C.c_int64(len(p)), C.c_int64(len(f) // 3)
+    gr = np.zeros(3)
+    lib().ref_remove_ground(_p(p, C.c_double), _p(nr, C.c_double), C.byref(n), _p(f, C.c_int32),
+                            C.byref(nf), C.c_double(dist_thres), str(workdir).encode(),
+                            _p(gr, C.c_double))
+    return (p[:n.value].copy(), nr[:n.value].copy(), f[:3 * nf.value].reshape(-1, 3).copy(), gr)
+
+
+def init_alignment(src, tgt, ground_ray, view_ray):
+    s, t = _f64(src).reshape(-1, 3), _f64(tgt).reshape(-1, 3)
+    gr, vr = _f64(ground_ray).reshape(3), _f64(view_ray).reshape(3)
+    T = np.empty(16)
+    sc = C.c_double()
+    lib().ref_init_alignment(_p(s, C.c_double), C.c_int64(len(s)), _p(t, C.c_double),
+                             C.c_int64(len(t)), _p(gr, C.c_double), _p(vr, C.c_double),
+                             _p(T, C.c_double), C.byref(sc))
+    return T.reshape(4, 4), sc.value
+
+
+def local_alignment_core(src, s_labels, tgt, t_labels, slabel, tlabel):
+    s, t = _f64(src).reshape(-1, 3), _f64(tgt).reshape(-1, 3)
+    sl, tl = _i32(s_labels), _i32(t_labels)
+    T = np.empty(16)
+    sc = C.c_double()
+    lib().ref_local_alignment_core(_p(s, C.c_double), _p(sl, C.c_int32), C.c_int64(len(s)),
+                                   _p(t, C.c_double), _p(tl, C.c_int32), C.c_int64(len(t)),
+                                   C.c_int(slabel), C.c_int(tlabel), _p(T, C.c_double),
+                                   C.byref(sc))
+    return T.reshape(4, 4), sc.value
+
+
+def part_recog(tmpl, labels, query):
+    tm, q = _f64(tmpl).reshape(-1, 3), _f64(query).reshape(-1, 3)
+    lb = _i32(labels)
+    out = np.empty(len(q), np.int32)
+    lib().ref_part_recog(_p(tm, C.c_double), _p(lb, C.c_int32), C.c_int64(len(tm)),
+                         _p(q, C.c_double), C.c_int64(len(q)), _p(out, C.c_int32))
+    return out
+
+
+def align(src, s_normals, s_facets, s_labels, tgt, t_normals, t_facets, view_ray, dist_thres,
+          workdir):
+    """Alignment::Align as a whole; `workdir` receives Template/part/parts."""
+    write_parts_file(workdir, s_labels)
+    s, sn = _f64(src).reshape(-1, 3).copy(), _f64(s_normals).reshape(-1, 3).copy()
+    sf = _i32(s_facets).reshape(-1)
+    t, tn = _f64(tgt).reshape(-1, 3).copy(), _f64(t_normals).reshape(-1, 3).copy()
+    tf = _i32(t_facets).reshape(-1).copy()
+    nt, ntf = C.c_int64(len(t)), C.c_int64(len(tf) // 3)
+    vr = _f64(view_ray).reshape(3)
+    lib().ref_align(_p(s, C.c_double), _p(sn, C.c_double), C.c_int64(len(s)), _p(sf, C.c_int32),
+                    C.c_int64(len(sf) // 3), _p(t, C.c_double), _p(tn, C.c_double), C.byref(nt),
+                    _p(tf, C.c_int32), C.byref(ntf), _p(vr, C.c_double), C.c_double(dist_thres),
+                    str(workdir).encode())
+    n, f = nt.value, ntf.value
+    return s, sn, t[:n].copy(), tn[:n].copy(), tf[:3 * f].reshape(-1, 3).copy()
+
+
+def mesh_vertex_normals(pts, facets):
+    p = _f64(pts).reshape(-1, 3)
+    f = _i32(facets).reshape(-1)
+    out = np.empty_like(p)
+    lib().ref_mesh_vertex_normals(_p(p, C.c_double), C.c_int64(len(p)), _p(f, C.c_int32),
+                                  C.c_int64(len(f) // 3), _p(out, C.c_double))
+    return out
+
+
+def write_obj(filename, pts, normals, facets):
+    p = _f64(pts).reshape(-1, 3)
+    nr = _f64(normals).reshape(-1, 3) if normals is not None else None
+    f = _i32(facets).reshape(-1)
+    lib().ref_write_obj(str(filename).encode(), _p(p, C.c_double), _p(nr, C.c_double),
+                        C.c_int64(len(p)), _p(f, C.c_int32), C.c_int64(len(f) // 3))
+
+
+def read_obj(filename, cap_n: int, cap_f: int):
+    p, nr = np.empty((cap_n, 3)), np.empty((cap_n, 3))
+    f = np.empty((cap_f, 3), np.int32)
+    n, nf = C.c_int64(), C.c_int64()
+    rc = lib().ref_read_obj(str(filename).encode(), _p(p, C.c_double), _p(nr, C.c_double),
+                            C.c_int64(cap_n), _p(f, C.c_int32), C.c_int64(cap_f), C.byref(n),
+                            C.byref(nf))
+    if rc != 0:
+        raise RuntimeError("ref.read_obj: capacity too small or no normals")
+    return p[:n.value].copy(), nr[:n.value].copy(), f[:nf.value].copy()

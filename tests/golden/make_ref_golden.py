@@ -1,7 +1,8 @@
 """Generates tests/golden/ref_vectors.npz by running the seeded cases of tests/refcases.py through
 oracle/_ref/libmvsref.so — the REFERENCE'S OWN sources (Solver/SRTSolver.cpp, Camera/Camera.cpp,
 SetUtils/*.cpp, Depth2Model/Depth2Model.cpp, Common/Utils.h) compiled unmodified from
-/root/reference (`make -C oracle ref`).  These are outputs of the reference itself run here; they
+/root/reference (`make -C oracle ref`) — and tests/golden/ref_align_vectors.npz from the reference's
+Alignment.cpp, PartRecognition.cpp and PlyObj.cpp (oracle/ref_shim_align.cpp).  These are outputs of the reference itself run here; they
 travel to the GPU box, where /root/reference does not exist, and pin both the oracle restatement
 (tests/test_ref_parity.py) and the CUDA path (tests/test_gpu_ref_parity.py).
 Run (in the container that has /root/reference):  python tests/golden/make_ref_golden.py
@@ -34,10 +35,44 @@ class RefBackend:
         return ref.srt_ransac(p, q, c1, c2, iters, seed, array)  # draws `triples` itself: srand(seed)
 
 
+class RefAlignBackend:
+    """oracle.ref's Alignment / PartRecognition / PlyObj entry points with the call shapes
+    refcases.run_align expects.  The reference works in the current directory (it reads
+    ./Template/part/parts and writes debug meshes): a scratch directory per call."""
+
+    def __init__(self, workdir):
+        self.wd = Path(workdir)
+        self.wd.mkdir(parents=True, exist_ok=True)
+
+    retain_connected = staticmethod(ref.retain_connected)
+    init_alignment = staticmethod(ref.init_alignment)
+    part_recog = staticmethod(ref.part_recog)
+    vertex_normals = staticmethod(ref.mesh_vertex_normals)
+
+    def remove_ground(self, p, n, f, dist_thres):
+        return ref.remove_ground(p, n, f, dist_thres, self.wd)
+
+    @staticmethod
+    def local_core(src, sl, tgt, tl, sel, label):
+        # the reference is handed the limb's points only (Alignment.cpp:326-371)
+        sl, tl = np.asarray(sl), np.asarray(tl)
+        ms, mt = np.isin(sl, sel), np.isin(tl, sel)
+        return ref.local_alignment_core(src[ms], sl[ms], tgt[mt], tl[mt], label, label)
+
+    def align(self, sv, sn, sf, sl, tv, tn, tf, view_ray, dist_thres):
+        return ref.align(sv, sn, sf, sl, tv, tn, tf, view_ray, dist_thres, self.wd)
+
+
 def main():
+    import tempfile
     ref.build()
     out = refcases.run(RefBackend, oracle.make_camera)
     path = Path(__file__).resolve().parent / "ref_vectors.npz"
+    np.savez_compressed(path, **out)
+    print(path, path.stat().st_size, "bytes,", len(out), "arrays")
+    with tempfile.TemporaryDirectory() as wd:
+        out = refcases.run_align(RefAlignBackend(wd))
+    path = Path(__file__).resolve().parent / "ref_align_vectors.npz"
     np.savez_compressed(path, **out)
     print(path, path.stat().st_size, "bytes,", len(out), "arrays")
 

@@ -136,3 +136,68 @@ def run(mod, make_camera, d2m_size=(160, 120)):
     xyz, tex, fac = mod.depth2model(depth_map(w, h), cd, MIN_DSP, MAX_DSP, SMOOTH)
     out["d2m_xyz"], out["d2m_tex"], out["d2m_facets"] = xyz, tex, fac
     return out
+
+
+# ------------------------------------------------------------------ Alignment / PartRecognition / PlyObj
+# (oracle/ref_shim_align.cpp: the reference's Alignment.cpp, PartRecognition.cpp, PlyObj.cpp)
+DIST_THRES = 0.8  # config.txt: dist_thres
+LIMBS = (((2, 3, 4), 4), ((5, 6, 7), 7), ((8, 9), 9), ((11, 12), 12))  # Alignment.cpp:378-419
+
+
+def align_scene():
+    """Template = a small labelled humanoid mesh; target = the same figure in another pose, 1.6x
+    larger, turned and moved, standing on a ground patch — one connected mesh, as
+    Alignment::Align expects it (RemoveGround + RetainConnectRegion need the facets)."""
+    sv, sf, sl = synth.humanoid_mesh(10, 8, arm_angle=0.5, leg_angle=0.12)
+    sn = synth.vertex_normals(sv, sf)
+    tv0, tf, _ = synth.humanoid_mesh(14, 10, arm_angle=0.75, leg_angle=0.2, ground=(0.7, 36))
+    R = synth.axis_angle([0.1, 1.0, 0.2], 0.2)
+    tv = 1.6 * tv0 @ R.T + np.array([0.2, 0.1, 3.0])
+    tn = synth.vertex_normals(tv, tf)
+    return dict(sv=sv, sn=sn, sf=sf, sl=sl, tv=tv, tn=tn, tf=tf, view_ray=R @ [0, 0, 1.0],
+                ground_ray=R @ [0, 1.0, 0])
+
+
+def run_align(mod):
+    """Every alignment case through `mod` (oracle.ref = the reference, or an adapter)."""
+    out = {}
+    # A7 RetainConnectRegion, full outputs
+    v1, f1 = synth.uv_sphere(10, 7)
+    v2, f2 = synth.uv_sphere(14, 9)
+    v = np.concatenate([v1, v2 + 5.0], 0)
+    f = np.concatenate([f1, f2 + len(v1)], 0)
+    p, n, ff = mod.retain_connected(v, v.copy(), f)
+    out["rc_pts"], out["rc_normals"], out["rc_facets"] = p, n, ff
+    # A4 RemoveGround
+    bv, bn, bf, nb = synth.body_on_ground()
+    p, n, ff, gr = mod.remove_ground(bv, bn, bf, DIST_THRES)
+    out["rg_pts"], out["rg_normals"], out["rg_facets"], out["rg_ground_ray"] = p, n, ff, gr
+    # A2 InitAlignment: a planted similarity, and two different poses
+    src, sl = synth.humanoid(200, seed=1)
+    R = synth.axis_angle([0.1, 1.0, 0.2], 0.25)
+    tgt = 1.8 * src @ R.T + np.array([0.5, -0.3, 4.0])
+    out["ia_planted_T"], s = mod.init_alignment(src, tgt, R @ [0, 1.0, 0], R @ [0, 0, 1.0])
+    out["ia_planted_s"] = np.float64(s)
+    sc = align_scene()
+    body = sc["tv"][: -len(synth.grid_disk(0.7, 36, 0.0)[0])]
+    T, s = mod.init_alignment(sc["sv"], body, sc["ground_ray"], sc["view_ray"])
+    out["ia_pose_T"], out["ia_pose_s"] = T, np.float64(s)
+    # A5 PartRecog on the initially aligned template, then A6 LocalAlignmentCore per limb
+    s1 = s * sc["sv"] @ T[:3, :3].T + T[:3, 3]
+    tl = mod.part_recog(s1, sc["sl"], body)
+    out["pr_labels"] = np.asarray(tl, np.int32)
+    for sel, lab in LIMBS:
+        Tl, sl_ = mod.local_core(s1, sc["sl"], body, tl, sel, lab)
+        out[f"lc_{lab}_T"], out[f"lc_{lab}_s"] = Tl, np.float64(sl_)
+    keep = np.asarray(tl) != 4  # the scan misses a hand: the label-set bookkeeping of :477-497
+    Tl, sl_ = mod.local_core(s1, sc["sl"], body[keep], np.asarray(tl)[keep], (2, 3, 4), 4)
+    out["lc_nohand_T"], out["lc_nohand_s"] = Tl, np.float64(sl_)
+    # Alignment::Align as a whole
+    a = mod.align(sc["sv"], sc["sn"], sc["sf"], sc["sl"], sc["tv"], sc["tn"], sc["tf"],
+                  sc["view_ray"], DIST_THRES)
+    out["al_src"], out["al_src_normals"], out["al_tgt"], out["al_tgt_normals"], out["al_tgt_facets"] = a
+    # PlyObj vertex normals
+    mv, mf = synth.uv_sphere(24, 18, bumps=0.08)
+    mv = mv.astype(np.float32).astype(np.float64)
+    out["vn_normals"] = mod.vertex_normals(mv, mf)
+    return out

@@ -127,3 +127,67 @@ def test_cuda_array_overload_equals_ransac(ctx):
     b = s.EstimateTransformRansac(api.srt_draw_triples(len(p), 64, 5))
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     s.close()
+
+
+# ------------------------------------------------------------------ Alignment / PartRecognition / OBJ
+GA = Path(__file__).resolve().parent / "golden" / "ref_align_vectors.npz"
+
+
+def test_cuda_alignment_matches_reference_vectors(ctx):
+    """Rows A2-A7 through the C ABI against tests/golden/ref_align_vectors.npz — outputs of the
+    reference's OWN Alignment.cpp / PartRecognition.cpp (oracle/ref_shim_align.cpp).  Kept point sets,
+    facets and labels exact; the transformed template within 1e-8 absolute (measured ~1e-13)."""
+    want = dict(np.load(GA))
+    from multiviewstitch_b200 import synth
+    al = api.Alignment(ctx, api.align_params(dist_thres=refcases.DIST_THRES))
+    # A7
+    v1, f1 = synth.uv_sphere(10, 7)
+    v2, f2 = synth.uv_sphere(14, 9)
+    v = np.concatenate([v1, v2 + 5.0], 0)
+    f = np.concatenate([f1, f2 + len(v1)], 0)
+    p, n, ff = al.RetainConnectRegion(v, v.copy(), f)
+    assert np.array_equal(p, want["rc_pts"]) and np.array_equal(n, want["rc_normals"])
+    assert np.array_equal(ff, want["rc_facets"])
+    # A4
+    bv, bn, bf, nb = synth.body_on_ground()
+    p, n, ff, gr = al.RemoveGround(bv, bn, bf)
+    assert np.array_equal(p, want["rg_pts"]) and np.array_equal(n, want["rg_normals"])
+    assert np.array_equal(ff, want["rg_facets"])
+    assert np.abs(gr - want["rg_ground_ray"]).max() <= 1e-9
+    # A5 on the reference's own initially aligned template
+    sc = refcases.align_scene()
+    body = sc["tv"][: -len(synth.grid_disk(0.7, 36, 0.0)[0])]
+    T, s = want["ia_pose_T"], float(want["ia_pose_s"])
+    s1 = s * sc["sv"] @ T[:3, :3].T + T[:3, 3]
+    pr = api.PartRecognition(ctx)
+    pr.SetInput(s1)
+    pr.SetLabels(sc["sl"])
+    assert np.array_equal(pr.PartRecog(body), want["pr_labels"])
+    # Alignment::Align as a whole: RemoveGround, InitAlignment, PartRecog, neck offset, four limbs
+    gs, gsn, gt, gtn, gtf, gtl, gg = al.Align(sc["sv"], sc["sn"], sc["sl"], sc["tv"], sc["tn"], sc["tf"],
+                                              sc["view_ray"])
+    assert np.array_equal(gt, want["al_tgt"]) and np.array_equal(gtn, want["al_tgt_normals"])
+    assert np.array_equal(gtf, want["al_tgt_facets"])
+    e_s, e_n = np.abs(gs - want["al_src"]).max(), np.abs(gsn - want["al_src_normals"]).max()
+    print(f"Align vs the reference: template {e_s:.3e}, normals {e_n:.3e}")
+    assert e_s <= 1e-8 and e_n <= 1e-8
+
+
+def test_export_obj_bytes_equal_reference_writer(ctx, tmp_path):
+    """§8(f)4: mvs_deform_export_obj against the reference's own Mesh::WriteObj (PlyObj.cpp:77-137)
+    fed with the library's vertices, normals and facets: the files agree byte for byte (apart from
+    the `# Object <name>` comment), and the reference's reader gets the mesh back."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not shipped")
+    from multiviewstitch_b200 import synth
+    v, f = synth.uv_sphere(16, 12, bumps=0.08)
+    pts = v.astype(np.float32)
+    d = api.Deformation(pts, synth.vertex_normals(v, f).astype(np.float32), f, ctx)
+    api.exportOBJ(str(tmp_path / "gpu.obj"), d)
+    ref.write_obj(tmp_path / "ref.obj", d.Vertices(), d.Normals(), d.Facets())
+    a = [l for l in (tmp_path / "gpu.obj").read_text().splitlines() if not l.startswith("# Object")]
+    b = [l for l in (tmp_path / "ref.obj").read_text().splitlines() if not l.startswith("# Object")]
+    assert a == b
+    p2, n2, f2 = ref.read_obj(tmp_path / "gpu.obj", len(pts), len(f))
+    assert np.array_equal(f2, f) and np.abs(p2 - pts).max() < 1e-5

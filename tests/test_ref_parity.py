@@ -7,6 +7,9 @@
   * test_live_ref_reproduces_golden — where oracle/_ref can be built or was shipped, the reference
     is run again and must reproduce the committed vectors bit for bit (the golden file is what the
     generator says it is).
+  * test_oracle_matches_ref_align_golden / test_live_ref_reproduces_align_golden — the same two
+    layers for the reference's Alignment.cpp, PartRecognition.cpp and PlyObj.cpp (rows A2-A7, f4;
+    tests/golden/ref_align_vectors.npz).
   * test_ref_* — further live checks at sizes too large to commit (640x480 Depth2Model), the `.raw`
     depth format against the product's host-side reader/writer, CalcRotation and the GL matrices.
 """
@@ -184,3 +187,99 @@ def test_ref_calc_rotation_and_gl_matrices():
     assert np.abs(mv[:3, 3] - (flip @ tm).astype(np.float32)).max() == 0
     # GetProjectGL fills the TRANSPOSE of the GL perspective matrix (row-vector convention)
     assert pr[2, 3] == -1 and pr[3, 2] == pytest.approx(-2 * 2000 * 0.01 / (2000 - 0.01), rel=1e-6)
+
+
+# ------------------------------------------------------------------ Alignment / PartRecognition / PlyObj
+GA = Path(__file__).resolve().parent / "golden" / "ref_align_vectors.npz"
+
+
+class OracleAlignBackend:
+    """oracle/align.cpp, oracle/nn.cpp, oracle/deform.cpp behind the call shapes of
+    tests/refcases.run_align"""
+    retain_connected = staticmethod(oracle.retain_connected)
+    init_alignment = staticmethod(oracle.init_alignment)
+    part_recog = staticmethod(oracle.part_recog)
+    vertex_normals = staticmethod(oracle.vertex_normals)
+
+    @staticmethod
+    def remove_ground(p, n, f, dist_thres):
+        return oracle.remove_ground(p, n, f, dist_thres, 0.28)  # 0.28: Alignment.cpp:187
+
+    @staticmethod
+    def local_core(src, sl, tgt, tl, sel, label):
+        T, s, ok = oracle.local_alignment_core(src, sl, tgt, tl, sel, label)
+        assert ok
+        return T, s
+
+    @staticmethod
+    def align(sv, sn, sf, sl, tv, tn, tf, view_ray, dist_thres):
+        s, sn2, t, tn2, tf2, _, _ = oracle.align(sv, sn, sl, tv, tn, tf, view_ray, dist_thres=dist_thres,
+                                                 remove_ground=1, local_align=1)
+        return s, sn2, t, tn2, tf2
+
+
+def compare_align(got, want, what="oracle", tol=1e-12):
+    """Kept point sets, facets and labels exact (the kept points are copies of input points);
+    transforms and transformed points within `tol` relative."""
+    exact = {"rc_pts", "rc_normals", "rg_pts", "rg_normals", "al_tgt", "al_tgt_normals"}
+    for k in want:
+        w, g = want[k], np.asarray(got[k])
+        assert g.shape == w.shape, f"{what}: {k} shape {g.shape} != {w.shape}"
+        if w.dtype.kind in "iub" or k in exact:
+            assert np.array_equal(g, w), f"{what}: {k} differs"
+        else:
+            t = tol * max(1.0, float(np.abs(w).max()))
+            assert np.abs(g - w).max() <= t, f"{what}: {k} off by {np.abs(g - w).max():.3e}"
+
+
+def test_oracle_matches_ref_align_golden():
+    """oracle/align.cpp against the committed outputs of the reference's OWN Alignment.cpp /
+    PartRecognition.cpp / PlyObj.cpp (rows A2-A7, f4): RetainConnectRegion, RemoveGround,
+    InitAlignment, PartRecog, LocalAlignmentCore per limb (incl. a missing label), Align as a whole,
+    vertex normals."""
+    want = dict(np.load(GA))
+    got = refcases.run_align(OracleAlignBackend)
+    compare_align(got, want)
+    # the cases are not vacuous: ground and a second component really were removed, the limbs moved
+    sc = refcases.align_scene()
+    assert len(want["al_tgt"]) < len(sc["tv"]) - 900 and len(want["rc_pts"]) < 200
+    assert abs(want["ia_pose_s"] - 1.6) < 0.2 and abs(np.linalg.det(want["ia_pose_T"][:3, :3]) - 1) < 1e-9
+    assert all(abs(want[f"lc_{lab}_s"] - 1.0) < 0.2 for _, lab in refcases.LIMBS)
+    assert len(np.unique(want["pr_labels"])) == 16
+
+
+@needs_ref
+def test_live_ref_reproduces_align_golden(tmp_path):
+    from tests.golden.make_ref_golden import RefAlignBackend
+    want = dict(np.load(GA))
+    got = refcases.run_align(RefAlignBackend(tmp_path))
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+
+
+@needs_ref
+def test_ref_obj_roundtrip_and_normals_convention(tmp_path):
+    """The reference's OBJ writer/reader (PlyObj.cpp:18-137): `vn` then `v` per vertex in float
+    text, `f a//a b//b c//c` 1-based; a mesh written without normals gets them recomputed by
+    Mesh::CalculateVertexNormals on reading — equal to the CGAL-path convention the oracle and
+    the CUDA path implement (Deformation.h:86-128) on a non-degenerate mesh."""
+    v, f = synth_mesh()
+    n = oracle.vertex_normals(v, f)
+    ref.write_obj(tmp_path / "a.obj", v, n, f)
+    text = (tmp_path / "a.obj").read_text().splitlines()
+    body = [l for l in text if l and not l.startswith("#")]
+    assert body[0].startswith("vn ") and body[1].startswith("v ")
+    assert body[2 * len(v)] == "f %d//%d %d//%d %d//%d" % tuple(int(x) + 1 for x in np.repeat(f[0], 2))
+    p2, n2, f2 = ref.read_obj(tmp_path / "a.obj", len(v), len(f))
+    assert np.array_equal(f2, f)
+    assert np.abs(p2 - v).max() < 1e-5 and np.abs(n2 - n).max() < 1e-5  # 6 significant digits
+    ref.write_obj(tmp_path / "b.obj", v, None, f)  # no normals: plain `f a b c`, normals recomputed
+    p3, n3, f3 = ref.read_obj(tmp_path / "b.obj", len(v), len(f))
+    assert np.array_equal(f3, f)
+    assert np.abs(n3 - oracle.vertex_normals(p3, f)).max() < 1e-12
+
+
+def synth_mesh():
+    from multiviewstitch_b200 import synth
+    v, f = synth.uv_sphere(16, 12, bumps=0.08)
+    return v.astype(np.float32).astype(np.float64), f
