@@ -1,0 +1,2 @@
+// oracle/compat/CGAL/Polyhedron_items_with_id_3.h — TEST INFRASTRUCTURE ONLY: forwards to the stand-in (CGAL is not in this image).
+#include <CGAL/mvs_cgal_standin.h>

@@ -4,14 +4,18 @@
 // output, not on the hot path) mention, so that the header parses; OpenCV's C++ headers are not in
 // this image.  Nothing on the compared path calls these.
 //
-// cv::flann::Index (PartRecognition/PartRecognition.cpp:50-77): the reference asks FLANN's randomised
-// kd-trees (checks = 200) for the nearest template vertex — an APPROXIMATE search whose contract is
-// the exact nearest neighbour.  The stand-in below IS that exact answer (float32 squared distances
-// summed in x, y, z order, lowest index on ties), so that Alignment::Align can be compiled and run
-// as a whole; it pins the alignment arithmetic around the search, not FLANN itself.
+// cv::flann::Index (PartRecognition/PartRecognition.cpp:50-77, Deformation/Deformation.cpp:63-153,
+// 155-230, 232-297): the reference asks FLANN's randomised kd-trees (checks = 32..200) for nearest
+// neighbours — an APPROXIMATE search whose contract is the exact answer.  The stand-in below IS that
+// exact answer (float32 squared distances summed in x, y, z order, ascending (distance, index)
+// order, radius search in squared units as FLANN's L2 functor defines it), so that
+// Alignment::Align and Deformation::Deform can be compiled and run as a whole; it pins the
+// arithmetic around the searches, not FLANN itself.
 #ifndef MVS_COMPAT_OPENCV_HPP
 #define MVS_COMPAT_OPENCV_HPP
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 typedef unsigned char uchar;
 #define CV_8UC1 0
@@ -46,34 +50,60 @@ struct KDTreeIndexParams {
 struct SearchParams {
   explicit SearchParams(int = 32, float = 0.f, bool = true) {}
 };
+// exact searches in the feature space of the matrix rows: float32 squared distances accumulated
+// dimension by dimension, results in ascending (distance, index) order
 class Index {
  public:
-  Index(const Mat& features, const KDTreeIndexParams&) : n_(features.rows), p_((size_t)features.rows * 3) {
+  Index(const Mat& features, const KDTreeIndexParams&)
+      : n_(features.rows), dim_(features.cols), p_((size_t)features.rows * features.cols) {
     for (int i = 0; i < n_; ++i)
-      for (int j = 0; j < 3; ++j) p_[(size_t)3 * i + j] = features.at<float>(i, j);
+      for (int j = 0; j < dim_; ++j) p_[(size_t)dim_ * i + j] = features.at<float>(i, j);
   }
   void knnSearch(const std::vector<float>& q, std::vector<int>& indices, std::vector<float>& dists,
                  int knn, const SearchParams&) const {
-    (void)knn;  // the reference only asks for one neighbour
-    int best = -1;
-    float bd = 0.f;
-    for (int i = 0; i < n_; ++i) {
-      volatile float dx = q[0] - p_[(size_t)3 * i], dy = q[1] - p_[(size_t)3 * i + 1],
-                     dz = q[2] - p_[(size_t)3 * i + 2];
-      volatile float xx = dx * dx, yy = dy * dy, zz = dz * dz;
-      volatile float xy = xx + yy;
-      float d = xy + zz;
-      if (best < 0 || d < bd) {
-        best = i;
-        bd = d;
-      }
+    std::vector<std::pair<float, int> > all = scan(q);
+    size_t k = std::min<size_t>((size_t)(knn > 0 ? knn : 0), all.size());
+    std::partial_sort(all.begin(), all.begin() + k, all.end());
+    if (indices.size() < (size_t)knn) indices.resize((size_t)knn, -1);
+    if (dists.size() < (size_t)knn) dists.resize((size_t)knn, 0.f);
+    for (size_t j = 0; j < k; ++j) {
+      indices[j] = all[j].second;
+      dists[j] = all[j].first;
     }
-    indices.assign(1, best);
-    dists.assign(1, bd);
+  }
+  // radius in the units of the distances above (squared); writes the first min(count, maxResults)
+  // entries and leaves the rest of the output vectors as the caller filled them
+  int radiusSearch(const std::vector<float>& q, std::vector<int>& indices, std::vector<float>& dists,
+                   double radius, int maxResults, const SearchParams&) const {
+    std::vector<std::pair<float, int> > all = scan(q), in;
+    for (size_t j = 0; j < all.size(); ++j)
+      if (all[j].first <= (float)radius) in.push_back(all[j]);
+    std::sort(in.begin(), in.end());
+    size_t k = std::min<size_t>(in.size(), (size_t)(maxResults > 0 ? maxResults : 0));
+    if (indices.size() < k) indices.resize(k, -1);
+    if (dists.size() < k) dists.resize(k, 0.f);
+    for (size_t j = 0; j < k; ++j) {
+      indices[j] = in[j].second;
+      dists[j] = in[j].first;
+    }
+    return (int)k;
   }
 
  private:
-  int n_;
+  std::vector<std::pair<float, int> > scan(const std::vector<float>& q) const {
+    std::vector<std::pair<float, int> > all((size_t)n_);
+    for (int i = 0; i < n_; ++i) {
+      float d = 0.f;
+      for (int j = 0; j < dim_; ++j) {
+        float e = q[(size_t)j] - p_[(size_t)dim_ * i + j];
+        float ee = e * e;
+        d = j ? d + ee : ee;
+      }
+      all[(size_t)i] = std::make_pair(d, i);
+    }
+    return all;
+  }
+  int n_, dim_;
   std::vector<float> p_;
 };
 }  // namespace flann

@@ -5,8 +5,10 @@ ctypes front-end of oracle/_ref/libmvsref.so: the reference's own first-party so
 Depth2Model/Depth2Model.cpp, Common/Utils.h) compiled UNMODIFIED from /root/reference by
 `make -C oracle ref` against the stand-in headers in oracle/compat/ (see oracle/ref_shim.cpp), and
 Alignment/Alignment.cpp, PartRecognition/PartRecognition.cpp, PlyObj/PlyObj.cpp,
-Parameter/ParamParser.cpp compiled from their source text with two headers passed through one sed
-rule (an MSVC-only default-argument form; see oracle/ref_shim_align.cpp and oracle/Makefile).
+Parameter/ParamParser.cpp, Deformation/Deformation.cpp compiled from their source text with their
+headers passed through sed (MSVC-only forms; see oracle/ref_shim_align.cpp, ref_shim_deform.cpp and
+oracle/Makefile) — Deformation against a CGAL stand-in that records the constraints handed to the
+solver (oracle/compat/CGAL/mvs_cgal_standin.h).
 Used to pin the restatement in oracle/*.cpp (tests/test_ref_parity.py), to generate the committed
 vectors tests/golden/ref_*.npz (tests/golden/make_ref_golden.py) and as the `kind: "reference"` CPU
 leg of bench.py's SRT line.  The product never loads it.
@@ -288,3 +290,81 @@ def read_obj(filename, cap_n: int, cap_f: int):
     if rc != 0:
         raise RuntimeError("ref.read_obj: capacity too small or no normals")
     return p[:n.value].copy(), nr[:n.value].copy(), f[:nf.value].copy()
+
+
+# ----------------------------------------------------------------------------- Deformation (D2-D5, D10)
+# (oracle/ref_shim_deform.cpp: the reference's Deformation class against the CGAL stand-in that
+# records the constraints handed to Surface_mesh_deformation)
+def _mesh(pts, normals, facets):
+    p = _f64(pts).reshape(-1, 3)
+    nr = _f64(normals).reshape(-1, 3) if normals is not None else np.zeros_like(p)
+    f = _i32(facets).reshape(-1)
+    return p, nr, f
+
+
+def deform_uniform_sampling(pts, normals, facets, workdir):
+    p, nr, f = _mesh(pts, normals, facets)
+    out = np.empty(len(p), np.int32)
+    lib().ref_deform_uniform_sampling.restype = C.c_int64
+    m = lib().ref_deform_uniform_sampling(_p(p, C.c_double), _p(nr, C.c_double), C.c_int64(len(p)),
+                                          _p(f, C.c_int32), C.c_int64(len(f) // 3),
+                                          str(workdir).encode(), _p(out, C.c_int32))
+    return out[:m].copy()
+
+
+def deform_node_graph(pts, normals, facets, ids, K=8):
+    p, nr, f = _mesh(pts, normals, facets)
+    ids = _i32(ids)
+    out = np.empty((len(ids), K + 1), np.int32)
+    w = np.empty((len(ids), K + 1))
+    lib().ref_deform_node_graph(_p(p, C.c_double), _p(nr, C.c_double), C.c_int64(len(p)),
+                                _p(f, C.c_int32), C.c_int64(len(f) // 3), _p(ids, C.c_int32),
+                                C.c_int64(len(ids)), C.c_int(K), _p(out, C.c_int32), _p(w, C.c_double))
+    return out, w
+
+
+def deform_node_targets(pts, normals, facets, ids, tpts, tnormals, proj_len_err, proj_dist_err,
+                        workdir):
+    """-> (vertex ids, target positions): what Deform(tpts, tnormals, projLenErr, projDistErr) hands
+    to CGAL (Deformation.cpp:383-391), one constraint per node."""
+    p, nr, f = _mesh(pts, normals, facets)
+    ids = _i32(ids)
+    tp, tn = _f64(tpts).reshape(-1, 3), _f64(tnormals).reshape(-1, 3)
+    ov = np.empty(len(p), np.int32)
+    ot = np.empty((len(p), 3))
+    lib().ref_deform_node_targets.restype = C.c_int64
+    k = lib().ref_deform_node_targets(_p(p, C.c_double), _p(nr, C.c_double), C.c_int64(len(p)),
+                                      _p(f, C.c_int32), C.c_int64(len(f) // 3), _p(ids, C.c_int32),
+                                      C.c_int64(len(ids)), _p(tp, C.c_double), _p(tn, C.c_double),
+                                      C.c_int64(len(tp)), C.c_double(proj_len_err),
+                                      C.c_double(proj_dist_err), str(workdir).encode(),
+                                      _p(ov, C.c_int32), _p(ot, C.c_double))
+    return ov[:k].copy(), ot[:k].copy()
+
+
+def deform_node_targets_threshold(pts, normals, facets, ids, tpts, tnormals, threshold):
+    p, nr, f = _mesh(pts, normals, facets)
+    ids = _i32(ids)
+    tp, tn = _f64(tpts).reshape(-1, 3), _f64(tnormals).reshape(-1, 3)
+    ov = np.empty(len(p), np.int32)
+    ot = np.empty((len(p), 3))
+    lib().ref_deform_node_targets_threshold.restype = C.c_int64
+    k = lib().ref_deform_node_targets_threshold(
+        _p(p, C.c_double), _p(nr, C.c_double), C.c_int64(len(p)), _p(f, C.c_int32),
+        C.c_int64(len(f) // 3), _p(ids, C.c_int32), C.c_int64(len(ids)), _p(tp, C.c_double),
+        _p(tn, C.c_double), C.c_int64(len(tp)), C.c_double(threshold), _p(ov, C.c_int32),
+        _p(ot, C.c_double))
+    return ov[:k].copy(), ot[:k].copy()
+
+
+def deform_export_obj(filename, pts, normals, facets):
+    p, nr, f = _mesh(pts, normals, facets)
+    lib().ref_deform_export_obj(str(filename).encode(), _p(p, C.c_double), _p(nr, C.c_double),
+                                C.c_int64(len(p)), _p(f, C.c_int32), C.c_int64(len(f) // 3))
+
+
+def deform_mesh_is_valid(pts, facets) -> bool:
+    p = _f64(pts).reshape(-1, 3)
+    f = _i32(facets).reshape(-1)
+    return bool(lib().ref_deform_mesh_is_valid(_p(p, C.c_double), C.c_int64(len(p)), _p(f, C.c_int32),
+                                               C.c_int64(len(f) // 3)))

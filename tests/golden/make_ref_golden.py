@@ -2,7 +2,8 @@
 oracle/_ref/libmvsref.so — the REFERENCE'S OWN sources (Solver/SRTSolver.cpp, Camera/Camera.cpp,
 SetUtils/*.cpp, Depth2Model/Depth2Model.cpp, Common/Utils.h) compiled unmodified from
 /root/reference (`make -C oracle ref`) — and tests/golden/ref_align_vectors.npz from the reference's
-Alignment.cpp, PartRecognition.cpp and PlyObj.cpp (oracle/ref_shim_align.cpp).  These are outputs of the reference itself run here; they
+Alignment.cpp, PartRecognition.cpp and PlyObj.cpp (oracle/ref_shim_align.cpp), and
+tests/golden/ref_deform_vectors.npz from its Deformation.cpp (oracle/ref_shim_deform.cpp).  These are outputs of the reference itself run here; they
 travel to the GPU box, where /root/reference does not exist, and pin both the oracle restatement
 (tests/test_ref_parity.py) and the CUDA path (tests/test_gpu_ref_parity.py).
 Run (in the container that has /root/reference):  python tests/golden/make_ref_golden.py
@@ -63,6 +64,38 @@ class RefAlignBackend:
         return ref.align(sv, sn, sf, sl, tv, tn, tf, view_ray, dist_thres, self.wd)
 
 
+class RefDeformBackend:
+    """oracle.ref's Deformation entry points with the call shapes refcases.run_deform expects"""
+
+    def __init__(self, workdir):
+        self.wd = Path(workdir)
+        self.wd.mkdir(parents=True, exist_ok=True)
+
+    @staticmethod
+    def _m(sc):
+        return sc["pts"].astype(np.float64), sc["nrm"].astype(np.float64), sc["faces"]
+
+    def uniform_sampling(self, sc):
+        return ref.deform_uniform_sampling(*self._m(sc), self.wd)
+
+    def node_graph(self, sc, ids, K):
+        return ref.deform_node_graph(*self._m(sc), ids, K)[0]
+
+    def node_targets(self, sc, ids, graph, pl, pd):
+        v, t = ref.deform_node_targets(*self._m(sc), ids, sc["tv"].astype(np.float64),
+                                       sc["tn"].astype(np.float64), pl, pd, self.wd)
+        assert np.array_equal(v, ids)  # one constraint per node, in node order (:383-391)
+        return t
+
+    def node_targets_threshold(self, sc, ids, thr):
+        return ref.deform_node_targets_threshold(*self._m(sc), ids, sc["tv"].astype(np.float64),
+                                                 sc["tn"].astype(np.float64), thr)
+
+    @staticmethod
+    def mesh_is_valid(pts, faces):
+        return int(ref.deform_mesh_is_valid(pts.astype(np.float64), faces))
+
+
 def main():
     import tempfile
     ref.build()
@@ -73,6 +106,11 @@ def main():
     with tempfile.TemporaryDirectory() as wd:
         out = refcases.run_align(RefAlignBackend(wd))
     path = Path(__file__).resolve().parent / "ref_align_vectors.npz"
+    np.savez_compressed(path, **out)
+    print(path, path.stat().st_size, "bytes,", len(out), "arrays")
+    with tempfile.TemporaryDirectory() as wd:
+        out = refcases.run_deform(RefDeformBackend(wd))
+    path = Path(__file__).resolve().parent / "ref_deform_vectors.npz"
     np.savez_compressed(path, **out)
     print(path, path.stat().st_size, "bytes,", len(out), "arrays")
 

@@ -201,3 +201,40 @@ def run_align(mod):
     mv = mv.astype(np.float32).astype(np.float64)
     out["vn_normals"] = mod.vertex_normals(mv, mf)
     return out
+
+
+# ------------------------------------------------------------------ Deformation (rows D1-D5, D10)
+# (oracle/ref_shim_deform.cpp: the reference's Deformation.h / Deformation.cpp; CGAL's solver is a
+# recorder there, so the outputs are the constraints the reference hands to it)
+def deform_scene():
+    """Template: a 9.6K-vertex cube-sphere (float32-representable: the reference reads its meshes
+    through float OBJ text, PlyObj.cpp:44-55); target: a larger bumpy UV sphere with normals."""
+    verts, faces = synth.cube_sphere(40)
+    pts = verts.astype(np.float32)
+    nrm = synth.vertex_normals(pts.astype(np.float64), faces).astype(np.float32)
+    tv, tf = synth.uv_sphere(150, 110, radius=1.08, bumps=0.03)
+    tv = tv.astype(np.float32)
+    tn = synth.vertex_normals(tv.astype(np.float64), tf).astype(np.float32)
+    return dict(pts=pts, nrm=nrm, faces=faces, tv=tv, tn=tn)
+
+
+DEFORM_THRESHOLDS = ((100.0, 100.0), (0.085, 100.0), (100.0, 0.012))  # (projLenErr, projDistErr)
+DEFORM_D4P_THRESHOLDS = (0.004, 0.0075, 1.0)                          # squared distances
+
+
+def run_deform(mod):
+    out = {}
+    sc = deform_scene()
+    ids = mod.uniform_sampling(sc)                      # D2, Deformation.cpp:63-106
+    out["d2_ids"] = np.asarray(ids, np.int32)
+    out["d3_graph"] = mod.node_graph(sc, ids, 8)        # D3, :108-153
+    for k, (pl, pd) in enumerate(DEFORM_THRESHOLDS):    # D4 + D5, :232-391
+        out[f"d4_controls_{k}"] = mod.node_targets(sc, ids, out["d3_graph"], pl, pd)
+    for k, thr in enumerate(DEFORM_D4P_THRESHOLDS):     # D4', :155-208
+        v, t = mod.node_targets_threshold(sc, ids, thr)
+        out[f"d4p_vertices_{k}"], out[f"d4p_targets_{k}"] = np.asarray(v, np.int32), t
+    # D1: the reference accepts only meshes CGAL calls valid (:42-45); a facet listed twice is not
+    bad = np.concatenate([sc["faces"], sc["faces"][:1]], 0)
+    out["d1_valid"] = np.array([mod.mesh_is_valid(sc["pts"], sc["faces"]),
+                                mod.mesh_is_valid(sc["pts"], bad)], np.int32)
+    return out

@@ -1,7 +1,9 @@
 """CUDA path (through the C ABI) against tests/golden/ref_vectors.npz — outputs of the REFERENCE'S
 OWN code (oracle/_ref: Solver/SRTSolver.cpp, Camera/Camera.cpp, SetUtils/*.cpp,
 Depth2Model/Depth2Model.cpp compiled unmodified; generator tests/golden/make_ref_golden.py) on the
-seeded inputs of tests/refcases.py.  Rows S1-S6, A1, A7, §8(f)3 of SURVEY.md §8."""
+seeded inputs of tests/refcases.py.  Rows S1-S6, A1, A7, §8(f)3 of SURVEY.md §8; further down the
+same for the reference's Alignment / PartRecognition / PlyObj (ref_align_vectors.npz: rows A2-A7, f4)
+and Deformation (ref_deform_vectors.npz: rows D2-D5, D4')."""
 from pathlib import Path
 
 import numpy as np
@@ -191,3 +193,32 @@ def test_export_obj_bytes_equal_reference_writer(ctx, tmp_path):
     assert a == b
     p2, n2, f2 = ref.read_obj(tmp_path / "gpu.obj", len(pts), len(f))
     assert np.array_equal(f2, f) and np.abs(p2 - pts).max() < 1e-5
+
+
+# ------------------------------------------------------------------ Deformation D2-D5, D4'
+GD = Path(__file__).resolve().parent / "golden" / "ref_deform_vectors.npz"
+
+
+def test_cuda_deformation_graph_matches_reference_vectors(ctx):
+    """Rows D2-D5 and D4' through the C ABI against tests/golden/ref_deform_vectors.npz — outputs of
+    the reference's OWN Deformation.cpp (oracle/ref_shim_deform.cpp; exact nearest neighbours in place
+    of FLANN, CGAL's solver replaced by a recorder of the constraints it is handed): sampled node
+    ids and node graph exact; control positions after the correspondence rule and the two smoothing
+    sweeps within 1e-12; the Deform(threshold) constraints exact."""
+    want = dict(np.load(GD))
+    sc = refcases.deform_scene()
+    d = api.Deformation(sc["pts"], sc["nrm"], sc["faces"], ctx)
+    ids = d.UniformSampling()
+    assert np.array_equal(ids, want["d2_ids"])
+    assert np.array_equal(d.KNearestNeighbor(8), want["d3_graph"])
+    d.SetTarget(sc["tv"], sc["tn"])
+    worst = 0.0
+    for k, (pl, pd) in enumerate(refcases.DEFORM_THRESHOLDS):
+        c, v = d.NodeTargets(pl, pd, 2)
+        worst = max(worst, float(np.abs(c - want[f"d4_controls_{k}"]).max()))
+    print(f"node control positions vs the reference: max abs diff {worst:.3e}")
+    assert worst <= 1e-12
+    for k, thr in enumerate(refcases.DEFORM_D4P_THRESHOLDS):
+        c, v = d.NodeTargetsThreshold(thr)
+        assert np.array_equal(ids[v > 0], want[f"d4p_vertices_{k}"])
+        assert np.array_equal(c[v > 0], want[f"d4p_targets_{k}"])
