@@ -513,6 +513,20 @@ def remove_outliers(p, q, cam1, cam2, rounds=3, iter_num=200, pixel_err=55.0, ad
     return keep[:nk.value].copy(), err.value, ir.value
 
 
+def remove_outliers_cb(p, q, cam1, cam2, rounds, iter_num, pixel_err, adapt_ratio, draw):
+    """remove_outliers with the hypothesis samples of each round supplied by `draw`, a C function
+    pointer or ctypes callback of type orc_triples_fn (size, iter_num, out_triples, user)."""
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    keep = np.empty(len(p), np.int32)
+    nk = C.c_int64()
+    err, ir = C.c_double(), C.c_double()
+    lib().orc_remove_outliers_cb(_p(p, C.c_double), _p(q, C.c_double), C.c_int64(len(p)),
+                                 C.byref(cam1), C.byref(cam2), C.c_int(rounds), C.c_int(iter_num),
+                                 C.c_double(pixel_err), C.c_double(adapt_ratio), draw, None,
+                                 _p(keep, C.c_int32), C.byref(nk), C.byref(err), C.byref(ir))
+    return keep[:nk.value].copy(), err.value, ir.value
+
+
 def depth2model(inv_depth, cam, min_dsp, max_dsp, smooth_threshold):
     a = _f32(inv_depth).reshape(cam.h, cam.w)
     npx = cam.h * cam.w

@@ -15,4 +15,8 @@ struct WIN32_FIND_DATA {
 static inline HANDLE FindFirstFile(const char*, WIN32_FIND_DATA*) { return INVALID_HANDLE_VALUE; }
 static inline int FindNextFile(HANDLE, WIN32_FIND_DATA*) { return 0; }
 static inline int FindClose(HANDLE) { return 1; }
+// Processor/Processor.cpp:925-1014 renames result files
+#include <stdio.h>
+#define MOVEFILE_REPLACE_EXISTING 0x1
+static inline int MoveFileEx(const char* from, const char* to, DWORD) { return rename(from, to) == 0; }
 #endif

@@ -10,6 +10,7 @@
 // headers MSVC's own standard headers pull in transitively (Alignment.cpp uses std::numeric_limits,
 // PlyObj.cpp std::find, without including <limits> / <algorithm>)
 #include <algorithm>
+#include <iomanip>
 #include <limits>
 #include <cstdio>
 #include <cstring>
@@ -28,6 +29,17 @@ inline T& msvc_default_arg() {
 // the "secure" CRT variants used with plain numeric formats only (PlyObj/PlyObj.cpp:46-67)
 #ifndef sscanf_s
 #define sscanf_s sscanf
+#endif
+#ifdef __cplusplus
+// sprintf_s(char (&)[N], fmt, ...) — the array-size-deducing overload Processor/Processor.cpp uses
+template <size_t N, class... A>
+inline int sprintf_s(char (&buf)[N], const char* fmt, A... a) {
+  return snprintf(buf, N, fmt, a...);
+}
+template <class... A>
+inline int sprintf_s(char* buf, size_t n, const char* fmt, A... a) {
+  return snprintf(buf, n, fmt, a...);
+}
 #endif
 #ifndef __min
 #define __min(a, b) (((a) < (b)) ? (a) : (b))

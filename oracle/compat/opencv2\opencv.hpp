@@ -35,6 +35,8 @@ class Mat {
   Mat(const Mat& m, const Rect& roi) : rows(roi.height), cols(roi.width), type_(m.type_),
                                        d_((size_t)roi.height * roi.width * 4, 0) {}
   static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
+  int type() const { return type_; }
+  void copyTo(Mat& dst) const { dst = *this; }
   template <typename T>
   T& at(int i, int j) { return *reinterpret_cast<T*>(&d_[((size_t)i * cols + j) * 4]); }
   template <typename T>
@@ -107,6 +109,24 @@ class Index {
   std::vector<float> p_;
 };
 }  // namespace flann
+// debug drawing / display of Processor/Processor.cpp (match and key-point pictures): no-ops
+struct Point2f {
+  float x, y;
+  Point2f(float x_ = 0.f, float y_ = 0.f) : x(x_), y(y_) {}
+};
+struct Scalar {
+  double v[4];
+  Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { v[0] = a; v[1] = b; v[2] = c; v[3] = d; }
+};
+struct RNG {
+  double uniform(double a, double) { return a; }
+};
+static inline Mat imread(const std::string&, int = 1) { return Mat(); }
+static inline void vconcat(const Mat&, const Mat&, Mat&) {}
+static inline void circle(Mat&, Point2f, int, const Scalar&, int = 1) {}
+static inline void line(Mat&, Point2f, Point2f, const Scalar&, int = 1) {}
+static inline void imshow(const std::string&, const Mat&) {}
+static inline int waitKey(int = 0) { return -1; }
 enum { COLOR_RGB2GRAY = 7 };
 static inline void cvtColor(const Mat& src, Mat& dst, int) { dst = src; }
 static inline bool imwrite(const std::string&, const Mat&) { return false; }

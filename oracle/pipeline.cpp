@@ -43,10 +43,24 @@ double orc_srt_inliers(const double* p, const double* q, int64_t n, const orc_ca
   return err_all;
 }
 
-void orc_remove_outliers(const double* p_in, const double* q_in, int64_t n, const orc_camera* c1,
-                         const orc_camera* c2, int rounds, int iter_num, double pixel_err,
-                         double adapt_ratio, uint64_t seed, int32_t* keep_idx, int64_t* n_keep,
-                         double* err, double* inlier_ratio) {
+namespace {
+struct SeededDraw {
+  uint64_t seed;
+  int round;
+};
+void seeded_triples(int64_t size, int iter_num, int32_t* out, void* user) {
+  SeededDraw* d = static_cast<SeededDraw*>(user);
+  orc_draw_triples(size, iter_num, d->seed + (uint64_t)d->round++, out);
+}
+}  // namespace
+
+// the round loop with the hypothesis samples of every round supplied by `draw` (called once per round
+// with the number of matches still in play) — the reference draws them from the C library's rand()
+// stream, which only the reference itself can replay (tests/test_ref_parity.py hands it over)
+void orc_remove_outliers_cb(const double* p_in, const double* q_in, int64_t n, const orc_camera* c1,
+                            const orc_camera* c2, int rounds, int iter_num, double pixel_err,
+                            double adapt_ratio, orc_triples_fn draw, void* user, int32_t* keep_idx,
+                            int64_t* n_keep, double* err, double* inlier_ratio) {
   std::vector<double> p(p_in, p_in + 3 * n), q(q_in, q_in + 3 * n);
   std::vector<int32_t> idx((size_t)n);
   for (int64_t i = 0; i < n; ++i) idx[i] = (int32_t)i;
@@ -55,7 +69,7 @@ void orc_remove_outliers(const double* p_in, const double* q_in, int64_t n, cons
   for (int k = 0; k < rounds; ++k) {
     if (size < 3) break;
     std::vector<int32_t> triples((size_t)iter_num * 3);
-    orc_draw_triples(size, iter_num, seed + (uint64_t)k, triples.data());
+    draw(size, iter_num, triples.data(), user);
     double sc, R[9], t[3];
     int32_t best;
     orc_srt_ransac(p.data(), q.data(), size, c1, c2, triples.data(), iter_num, &sc, R, t, &best,
@@ -81,6 +95,15 @@ void orc_remove_outliers(const double* p_in, const double* q_in, int64_t n, cons
   *n_keep = size;
   if (err) *err = e;
   if (inlier_ratio) *inlier_ratio = 0.0;
+}
+
+void orc_remove_outliers(const double* p_in, const double* q_in, int64_t n, const orc_camera* c1,
+                         const orc_camera* c2, int rounds, int iter_num, double pixel_err,
+                         double adapt_ratio, uint64_t seed, int32_t* keep_idx, int64_t* n_keep,
+                         double* err, double* inlier_ratio) {
+  SeededDraw d{seed, 0};
+  orc_remove_outliers_cb(p_in, q_in, n, c1, c2, rounds, iter_num, pixel_err, adapt_ratio,
+                         seeded_triples, &d, keep_idx, n_keep, err, inlier_ratio);
 }
 
 void orc_depth2model(const float* dsp, const orc_camera* cam, double min_dsp, double max_dsp,

@@ -5,8 +5,9 @@ ctypes front-end of oracle/_ref/libmvsref.so: the reference's own first-party so
 Depth2Model/Depth2Model.cpp, Common/Utils.h) compiled UNMODIFIED from /root/reference by
 `make -C oracle ref` against the stand-in headers in oracle/compat/ (see oracle/ref_shim.cpp), and
 Alignment/Alignment.cpp, PartRecognition/PartRecognition.cpp, PlyObj/PlyObj.cpp,
-Parameter/ParamParser.cpp, Deformation/Deformation.cpp compiled from their source text with their
-headers passed through sed (MSVC-only forms; see oracle/ref_shim_align.cpp, ref_shim_deform.cpp and
+Parameter/ParamParser.cpp, Deformation/Deformation.cpp, Processor/Processor.cpp compiled from their source text with their
+headers passed through sed (MSVC-only forms; see oracle/ref_shim_align.cpp, ref_shim_deform.cpp,
+ref_shim_processor.cpp and
 oracle/Makefile) — Deformation against a CGAL stand-in that records the constraints handed to the
 solver (oracle/compat/CGAL/mvs_cgal_standin.h).
 Used to pin the restatement in oracle/*.cpp (tests/test_ref_parity.py), to generate the committed
@@ -368,3 +369,47 @@ def deform_mesh_is_valid(pts, facets) -> bool:
     f = _i32(facets).reshape(-1)
     return bool(lib().ref_deform_mesh_is_valid(_p(p, C.c_double), C.c_int64(len(p)), _p(f, C.c_int32),
                                                C.c_int64(len(f) // 3)))
+
+
+# ----------------------------------------------------------------------------- Processor (§8(f)1)
+# (oracle/ref_shim_processor.cpp: Processor::RemoveOutliers and Processor::CheckConsistencyCore)
+def remove_outliers(p, q, cam1: Camera, cam2: Camera, pixel_err, adapt_ratio, seed: int):
+    """Processor::RemoveOutliers after srand(seed) -> (kept original indices, err, inlier_ratio)."""
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    keep = np.empty(len(p), np.int32)
+    err, ir = C.c_double(), C.c_double()
+    lib().ref_remove_outliers.restype = C.c_int64
+    k = lib().ref_remove_outliers(_p(p, C.c_double), _p(q, C.c_double), C.c_int64(len(p)), _cam(cam1),
+                                  _cam(cam2), C.c_double(pixel_err), C.c_double(adapt_ratio),
+                                  C.c_uint(seed), _p(keep, C.c_int32), C.byref(err), C.byref(ir))
+    return keep[:k].copy(), err.value, ir.value
+
+
+def oracle_remove_outliers_with_ref_samples(p, q, cam1: Camera, cam2: Camera, pixel_err, adapt_ratio,
+                                            seed: int, rounds=3, iter_num=200):
+    """The ORACLE's round loop (oracle/pipeline.cpp) fed with the hypothesis samples the reference
+    draws: srand(seed), then per round iter_num calls of the reference's Shuffle on the C library's
+    rand() stream (the oracle calls straight into libmvsref.so for them)."""
+    import oracle
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    keep = np.empty(len(p), np.int32)
+    nk = C.c_int64()
+    err, ir = C.c_double(), C.c_double()
+    lib().ref_srand(C.c_uint(seed))
+    draw = C.cast(lib().ref_srt_triples_next, C.c_void_p)
+    oracle.lib().orc_remove_outliers_cb(_p(p, C.c_double), _p(q, C.c_double), C.c_int64(len(p)),
+                                        C.byref(cam1), C.byref(cam2), C.c_int(rounds),
+                                        C.c_int(iter_num), C.c_double(pixel_err),
+                                        C.c_double(adapt_ratio), draw, None, _p(keep, C.c_int32),
+                                        C.byref(nk), C.byref(err), C.byref(ir))
+    return keep[:nk.value].copy(), err.value, ir.value
+
+
+def check_consistency(depth, cam: Camera, ref_depths, ref_cams, min_dsp, max_dsp, reproj_err: int):
+    d = _f64(depth).reshape(-1).copy()
+    rd = _f64(ref_depths).reshape(len(ref_cams), -1)
+    arr = (Camera * max(1, len(ref_cams)))(*ref_cams)
+    lib().ref_check_consistency(_p(d, C.c_double), _cam(cam), _p(rd, C.c_double), arr,
+                                C.c_int(len(ref_cams)), C.c_double(min_dsp), C.c_double(max_dsp),
+                                C.c_int(int(reproj_err)))
+    return d.reshape(cam.h, cam.w)

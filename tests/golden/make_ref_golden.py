@@ -3,7 +3,9 @@ oracle/_ref/libmvsref.so — the REFERENCE'S OWN sources (Solver/SRTSolver.cpp, 
 SetUtils/*.cpp, Depth2Model/Depth2Model.cpp, Common/Utils.h) compiled unmodified from
 /root/reference (`make -C oracle ref`) — and tests/golden/ref_align_vectors.npz from the reference's
 Alignment.cpp, PartRecognition.cpp and PlyObj.cpp (oracle/ref_shim_align.cpp), and
-tests/golden/ref_deform_vectors.npz from its Deformation.cpp (oracle/ref_shim_deform.cpp).  These are outputs of the reference itself run here; they
+tests/golden/ref_deform_vectors.npz from its Deformation.cpp (oracle/ref_shim_deform.cpp), and
+tests/golden/ref_processor_vectors.npz from Processor::RemoveOutliers / CheckConsistencyCore
+(oracle/ref_shim_processor.cpp).  These are outputs of the reference itself run here; they
 travel to the GPU box, where /root/reference does not exist, and pin both the oracle restatement
 (tests/test_ref_parity.py) and the CUDA path (tests/test_gpu_ref_parity.py).
 Run (in the container that has /root/reference):  python tests/golden/make_ref_golden.py
@@ -96,6 +98,38 @@ class RefDeformBackend:
         return int(ref.deform_mesh_is_valid(pts.astype(np.float64), faces))
 
 
+def oracle_model2depth(verts, faces, poses, K, w, h):
+    """the synthetic depth maps of the consistency case (inputs, not reference outputs)"""
+    return oracle.model2depth(verts, faces, [oracle.make_camera(K, R, t, w, h) for R, t in poses])
+
+
+class RefProcessorBackend:
+    """oracle.ref's Processor entry points with the call shapes refcases.run_processor expects"""
+
+    @staticmethod
+    def remove_outliers(p, q, c1, c2, pixel_err, adapt_ratio, seed):
+        keep, err, _ = ref.remove_outliers(p, q, c1, c2, pixel_err, adapt_ratio, seed)
+        # the samples the reference drew, round by round: replay its rand() stream through the round
+        # loop (the number of matches left after each round decides how the next ones are drawn)
+        import ctypes as C
+        rounds = []
+
+        @C.CFUNCTYPE(None, C.c_int64, C.c_int, C.POINTER(C.c_int32), C.c_void_p)
+        def draw(size, iters, out, user):
+            ref.lib().ref_srt_triples_next(C.c_int64(size), C.c_int(iters), out, None)
+            rounds.append(np.ctypeslib.as_array(out, shape=(iters, 3)).copy())
+
+        ref.lib().ref_srand(C.c_uint(seed))
+        k2, e2, _ = oracle.remove_outliers_cb(p, q, c1, c2, 3, 200, pixel_err, adapt_ratio, draw)
+        assert np.array_equal(k2, keep) and e2 == err, "oracle round loop left the reference's path"
+        return keep, err, rounds
+
+    @staticmethod
+    def check_consistency(depth, cam, ref_depths, ref_cams, min_dsp, max_dsp, reproj_err):
+        return ref.check_consistency(np.asarray(depth, np.float64), cam, np.asarray(ref_depths, np.float64),
+                                     ref_cams, min_dsp, max_dsp, reproj_err)
+
+
 def main():
     import tempfile
     ref.build()
@@ -111,6 +145,10 @@ def main():
     with tempfile.TemporaryDirectory() as wd:
         out = refcases.run_deform(RefDeformBackend(wd))
     path = Path(__file__).resolve().parent / "ref_deform_vectors.npz"
+    np.savez_compressed(path, **out)
+    print(path, path.stat().st_size, "bytes,", len(out), "arrays")
+    out = refcases.run_processor(RefProcessorBackend, oracle.make_camera, oracle_model2depth)
+    path = Path(__file__).resolve().parent / "ref_processor_vectors.npz"
     np.savez_compressed(path, **out)
     print(path, path.stat().st_size, "bytes,", len(out), "arrays")
 

@@ -238,3 +238,47 @@ def run_deform(mod):
     out["d1_valid"] = np.array([mod.mesh_is_valid(sc["pts"], sc["faces"]),
                                 mod.mesh_is_valid(sc["pts"], bad)], np.int32)
     return out
+
+
+# ------------------------------------------------------------------ Processor (§8(f)1)
+# (oracle/ref_shim_processor.cpp: Processor::RemoveOutliers, Processor::CheckConsistencyCore)
+REMOVE_OUTLIER_CASES = ((1, 20.0, 0.6), (5, 60.0, 0.75), (77, 3.0, 0.5))  # (seed, pixel_err, adapt ratio)
+
+
+def outlier_inputs():
+    p, q = synth.planted_pairs(400, seed=3, noise=5e-4)
+    rng = np.random.default_rng(0)
+    bad = rng.choice(400, 40, replace=False)
+    q = q.copy()
+    q[bad] += rng.normal(scale=0.4, size=(40, 3))
+    return p, q, bad
+
+
+def consistency_inputs(make_camera, model2depth):
+    """Three 160x120 views of a sphere, the middle one checked against its neighbours; one neighbour
+    carries an inconsistent patch.  Depth maps are float32 inverse depths (the `.raw` format)."""
+    w, h = 160, 120
+    verts, faces = synth.cube_sphere(48)
+    verts = (verts + np.array([0, 0, 4.0])).astype(np.float32)
+    K = np.array([[150.0, 0, w / 2 - 0.5], [0, 150.0, h / 2 - 0.5], [0, 0, 1.0]])
+    poses = [(synth.axis_angle([0, 1, 0], 0.06 * (k - 1)), np.array([0.15 * (k - 1), 0, 0.0])) for k in range(3)]
+    cams = [make_camera(K, R, t, w, h) for R, t in poses]
+    maps = model2depth(verts, faces, poses, K, w, h)
+    maps = np.array(maps, np.float32)
+    maps[2][40:60, 70:90] *= 1.3
+    return cams, maps
+
+
+def run_processor(mod, make_camera, model2depth):
+    out = {}
+    p, q, _ = outlier_inputs()
+    c1, c2 = cams(make_camera)
+    for seed, pe, ar in REMOVE_OUTLIER_CASES:
+        keep, err, rounds = mod.remove_outliers(p, q, c1, c2, pe, ar, seed)
+        out[f"ro_{seed}_keep"], out[f"ro_{seed}_err"] = np.asarray(keep, np.int32), np.float64(err)
+        for k, tr in enumerate(rounds):
+            out[f"ro_{seed}_round{k}_triples"] = np.asarray(tr, np.int32)
+    cs, maps = consistency_inputs(make_camera, model2depth)
+    out["cc_depth"] = np.asarray(mod.check_consistency(maps[1], cs[1], maps[[0, 2]], [cs[0], cs[2]],
+                                                       MIN_DSP, 0.5, 4), np.float32)
+    return out

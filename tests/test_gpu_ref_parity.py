@@ -222,3 +222,20 @@ def test_cuda_deformation_graph_matches_reference_vectors(ctx):
         c, v = d.NodeTargetsThreshold(thr)
         assert np.array_equal(ids[v > 0], want[f"d4p_vertices_{k}"])
         assert np.array_equal(c[v > 0], want[f"d4p_targets_{k}"])
+
+
+# ------------------------------------------------------------------ Processor::CheckConsistencyCore
+def test_cuda_check_consistency_matches_reference_vectors(ctx):
+    """§8(f)1: mvs_check_consistency against the depth map the reference's own
+    Processor::CheckConsistencyCore (Processor.cpp:66-115) leaves — identical.  (RemoveOutliers is
+    pinned through the oracle: tests/test_ref_parity.py feeds the oracle the reference's rand()
+    samples, tests/test_gpu_pipeline.py compares the CUDA path with the oracle on shared seeds.)"""
+    import oracle
+    want = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_processor_vectors.npz"))
+
+    def m2d(verts, faces, poses, K, w, h):
+        return oracle.model2depth(verts, faces, [oracle.make_camera(K, R, t, w, h) for R, t in poses])
+
+    cs, maps = refcases.consistency_inputs(api.make_camera, m2d)
+    g = api.check_consistency(maps[1], cs[1], maps[[0, 2]], [cs[0], cs[2]], refcases.MIN_DSP, 0.5, 4.0, ctx)
+    assert np.array_equal(np.asarray(g, np.float32), want["cc_depth"])

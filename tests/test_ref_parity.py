@@ -12,6 +12,8 @@
     tests/golden/ref_align_vectors.npz).
   * test_oracle_matches_ref_deform_golden / test_live_ref_reproduces_deform_golden — and for the
     reference's Deformation.cpp (rows D1-D5, D4'; tests/golden/ref_deform_vectors.npz): bit-identical.
+  * test_oracle_matches_ref_processor_golden / test_live_ref_reproduces_processor_golden — and for
+    Processor::RemoveOutliers / CheckConsistencyCore (§8(f)1; ref_processor_vectors.npz).
   * test_ref_* — further live checks at sizes too large to commit (640x480 Depth2Model), the `.raw`
     depth format against the product's host-side reader/writer, CalcRotation and the GL matrices.
 """
@@ -388,3 +390,67 @@ def test_ref_literal_comparator_and_cgal_path_normals(tmp_path):
     assert all(tuple(a) in {tuple(np.roll(b, k)) for k in range(3)} for a, b in zip(f2[:50], faces[:50]))
     assert np.abs(p2 - pts).max() < 1e-5
     assert np.abs(n2 - oracle.vertex_normals(pts.astype(np.float64), faces)).max() < 2e-6
+
+
+# ------------------------------------------------------------------ Processor (§8(f)1)
+GP = Path(__file__).resolve().parent / "golden" / "ref_processor_vectors.npz"
+
+
+def _oracle_model2depth(verts, faces, poses, K, w, h):
+    return oracle.model2depth(verts, faces, [oracle.make_camera(K, R, t, w, h) for R, t in poses])
+
+
+class OracleProcessorBackend:
+    """oracle/pipeline.cpp; the RANSAC samples of every round are the ones the reference drew (stored
+    next to its results: the C library's rand() stream cannot be replayed by other code)."""
+
+    def __init__(self, golden):
+        self.g = golden
+
+    def remove_outliers(self, p, q, c1, c2, pixel_err, adapt_ratio, seed):
+        import ctypes as C
+        stored = [self.g[k] for k in sorted(self.g) if k.startswith(f"ro_{seed}_round")]
+        served = []
+
+        @C.CFUNCTYPE(None, C.c_int64, C.c_int, C.POINTER(C.c_int32), C.c_void_p)
+        def draw(size, iters, out, user):
+            tr = stored[len(served)]
+            assert tr.shape == (iters, 3) and tr.max() < size
+            np.ctypeslib.as_array(out, shape=(iters, 3))[:] = tr
+            served.append(tr)
+
+        keep, err, _ = oracle.remove_outliers_cb(p, q, c1, c2, 3, 200, pixel_err, adapt_ratio, draw)
+        assert len(served) == len(stored)  # the oracle ran as many rounds as the reference
+        return keep, err, served
+
+    @staticmethod
+    def check_consistency(depth, cam, ref_depths, ref_cams, min_dsp, max_dsp, reproj_err):
+        return oracle.check_consistency(depth, cam, ref_depths, ref_cams, min_dsp, max_dsp, float(reproj_err))
+
+
+def test_oracle_matches_ref_processor_golden():
+    """oracle/pipeline.cpp against the committed outputs of the reference's OWN
+    Processor::RemoveOutliers (three rounds of 200-hypothesis RANSAC + the symmetric pixel test with
+    the shrinking threshold, Processor.cpp:177-269) and Processor::CheckConsistencyCore (:66-115):
+    the surviving match indices, the mean pixel error (to the last bit) and the filtered depth map
+    are identical."""
+    want = dict(np.load(GP))
+    got = refcases.run_processor(OracleProcessorBackend(want), oracle.make_camera, _oracle_model2depth)
+    for k, w in want.items():
+        assert np.array_equal(np.asarray(got[k]), w), k
+    _, _, bad = refcases.outlier_inputs()
+    for seed, pe, _ in refcases.REMOVE_OUTLIER_CASES:
+        keep = want[f"ro_{seed}_keep"]
+        assert 300 < len(keep) < 400  # every case drops matches
+        if pe <= 20.0:  # a tight pixel threshold removes the planted outliers
+            assert len(set(keep.tolist()) & set(bad.tolist())) <= 4
+    assert 0.1 < (want["cc_depth"] > 0).mean() < 0.4
+
+
+@needs_ref
+def test_live_ref_reproduces_processor_golden():
+    from tests.golden.make_ref_golden import RefProcessorBackend
+    want = dict(np.load(GP))
+    got = refcases.run_processor(RefProcessorBackend, oracle.make_camera, _oracle_model2depth)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
