@@ -275,7 +275,9 @@ def test_deform_reference_signature(ctx):
     assert np.linalg.norm(out, axis=1).mean() > 1.04
     # normals recomputed as in exportOBJ (Deformation.h:86-128)
     no = oracle.vertex_normals(out, faces)
-    assert np.abs(d.Normals() - no).max() < 2e-3
+    en = float(np.abs(d.Normals() - no).max())
+    print(f"vertex normals vs oracle: max abs diff {en:.3e}")
+    assert en < 2e-6  # float32 cross products and atomics against float64: 1.2e-7 measured
     assert np.array_equal(d.Facets(), faces)
 
 
