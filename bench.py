@@ -108,55 +108,114 @@ def workload_name(args, n):
 
 # ------------------------------------------------------------------------- clocks sampler
 class Clocks:
+    """SM clock, power and throttle reasons of one GPU while the timed region runs.  Polls NVML (the
+    library behind nvidia-smi) every 5 ms from a thread started BEFORE the warm-up, so the samples
+    reported are the ones whose time stamp lies inside the timed region (`window`); falls back to an
+    `nvidia-smi -lms` loop when the NVML binding is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits (nvml.h)
+    MASKS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20),
+             ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []  # (time, sm MHz, max sm MHz, power W or None, set of reasons)
         self.proc = None
+        self.source = None
+        self.t0 = self.t1 = None
+        self._halt = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._nv = pynvml
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                  "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self._nv, self._h
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self._halt.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((time.perf_counter(), sm, mx, pw,
+                                     {n for n, m in self.MASKS if bits & m}))
+            except Exception:
+                pass
+            self._halt.wait(0.005)
+
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
-            if len(f) >= 8:
-                self.samples.append(f)
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for f in self.samples:
+            if len(f) < 8:
+                continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                self.samples.append((time.perf_counter(), float(f[1]), float(f[2]), float(f[3]),
+                                     {n for k, n in enumerate(names) if f[4 + k].lower().startswith("active")}))
             except ValueError:
                 continue
-            for k, nme in enumerate(names):
-                if f[4 + k].lower().startswith("active"):
-                    reasons.add(nme)
+
+    def window(self, t0, t1):
+        """the timed region, in time.perf_counter() seconds"""
+        self.t0, self.t1 = t0, t1
+
+    def stop(self):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.source == "nvml":
+            self._halt.set()
+            self.thread.join(timeout=1)
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        rows = list(self.samples)
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        use = inside or rows
+        sm = [r[1] for r in use]
+        mx = [r[2] for r in use if r[2] is not None]
+        pw = [r[3] for r in use if r[3] is not None]
+        reasons = set()
+        for r in use:
+            reasons |= r[4]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "in_timed_region": len(inside), "source": self.source,
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------- reference (CPU) arm
@@ -527,6 +586,8 @@ def c4_pairs(args, api, ctx, stream, world, rank, dist, steps, warmup, clocks_in
         wall = time.perf_counter() - t0
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         launches = ctx.launch_count()
+        if clocks:
+            clocks.window(t0, t0 + wall)
         clk = clocks.stop() if clocks else None
     worst = 0.0
     for o, wk in zip(outs, work):  # every pair must recover its planted similarity
@@ -847,15 +908,15 @@ def run_b200(args):
         prm = api.gn_params(gn_iters=args.gn_iters, pcg_iters=args.pcg_iters, corr_mode=1)
         flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
+        clocks = Clocks(local)
+        if rank == 0:
+            clocks.start()  # polling runs through the warm-up; the samples inside the timed region count
         for _ in range(max(3, args.warmup)):
             d.Solve(prm)
         # ---- timed: device-resident, one library call per step, profiling off
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(args.steps)]
         ctx.launch_count_reset()
-        clocks = Clocks(local)
-        if rank == 0:
-            clocks.start()
         barrier()
         t_wall0 = time.perf_counter()
         for s in range(args.steps):
@@ -867,6 +928,7 @@ def run_b200(args):
         t_wall = time.perf_counter() - t_wall0
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         launches = ctx.launch_count()
+        clocks.window(t_wall0, t_wall0 + t_wall)
         clk = clocks.stop() if rank == 0 else None
         out_dev = d.Vertices()
         x_dev = d.NodeState()

@@ -39,3 +39,45 @@ def test_config_object_is_shared_by_both_arms():
     c = bench.base_config(a, 1003688, 1058402)
     assert c["verts"] == 1003688 and c["target_points"] == 1058402 and c["mode"] == "objects"
     assert "1003688-vertex" in c["workload"]
+
+
+def test_clock_sampler_polls_nvml_and_keeps_the_timed_region(monkeypatch):
+    """bench.Clocks: NVML polling thread, samples filtered to the timed region, throttle-reason bits
+    decoded; without any NVML / nvidia-smi it reports itself unavailable instead of failing."""
+    import sys
+    import time
+    import types
+    import bench
+    fake = types.ModuleType("pynvml")
+    fake.NVML_CLOCK_SM = 1
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: ("gpu", i)
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, k: 1965
+    fake.nvmlDeviceGetClockInfo = lambda h, k: 1950
+    fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: 0x4 | 0x1  # sw_power_cap + gpu_idle
+    fake.nvmlDeviceGetPowerUsage = lambda h: 250000
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    c = bench.Clocks(0)
+    c.start()
+    time.sleep(0.05)
+    t0 = time.perf_counter()
+    time.sleep(0.06)
+    t1 = time.perf_counter()
+    time.sleep(0.03)
+    c.window(t0, t1)
+    r = c.stop()
+    assert r["source"] == "nvml" and r["sm_mhz"] == 1950.0 and r["sm_max_mhz"] == 1965.0
+    assert r["reasons"] == ["sw_power_cap"] and r["power_w_max"] == 250.0
+    assert 3 <= r["in_timed_region"] == r["samples"] <= 20  # ~5 ms period over a 60 ms window
+    # no NVML, no nvidia-smi
+    broken = types.ModuleType("pynvml")
+
+    def boom():
+        raise RuntimeError("no driver")
+    broken.nvmlInit = boom
+    monkeypatch.setitem(sys.modules, "pynvml", broken)
+    monkeypatch.setenv("PATH", "/nonexistent")
+    c2 = bench.Clocks(0)
+    c2.start()
+    r2 = c2.stop()
+    assert r2["sm_mhz"] is None and r2["reasons"] == ["nvidia-smi unavailable"]
