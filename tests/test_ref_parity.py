@@ -454,3 +454,55 @@ def test_live_ref_reproduces_processor_golden():
     got = refcases.run_processor(RefProcessorBackend, oracle.make_camera, _oracle_model2depth)
     for k in want:
         assert np.array_equal(got[k], want[k]), k
+
+
+# ------------------------------------------------------------------ more live draws (not committed)
+@needs_ref
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_ref_deformation_random_scenes(tmp_path, seed):
+    """Other meshes, noisy targets, other thresholds: the oracle still equals the reference's
+    Deformation code bit for bit (D2-D5), and the threshold variant (D4') exactly."""
+    from multiviewstitch_b200 import synth
+    rng = np.random.default_rng(seed)
+    verts, faces = synth.uv_sphere(int(rng.integers(30, 50)), int(rng.integers(24, 36)), bumps=0.06, seed=seed)
+    verts = verts * rng.uniform(0.6, 1.5, size=3)  # an ellipsoid: no accidental distance ties
+    pts = verts.astype(np.float32)
+    nrm = synth.vertex_normals(pts.astype(np.float64), faces).astype(np.float32)
+    tv, tf = synth.uv_sphere(110, 80, radius=1.05, bumps=0.04, seed=seed + 100)
+    tv = (tv * rng.uniform(0.6, 1.5, size=3) + rng.normal(scale=2e-3, size=tv.shape)).astype(np.float32)
+    tn = synth.vertex_normals(tv.astype(np.float64), tf).astype(np.float32)
+    p64, tv64, tn64 = pts.astype(np.float64), tv.astype(np.float64), tn.astype(np.float64)
+    ids = oracle.uniform_sampling(pts, 16)
+    assert np.array_equal(ids, ref.deform_uniform_sampling(p64, nrm, faces, tmp_path))
+    graph = oracle.node_graph(pts[ids], 8)
+    assert np.array_equal(graph, ref.deform_node_graph(p64, nrm, faces, ids, 8)[0])
+    pl, pd = float(rng.uniform(0.05, 0.3)), float(rng.uniform(0.01, 0.1))
+    ctrl, valid = oracle.node_targets(pts[ids], nrm[ids], tv, tn, graph, pl, pd, 2)
+    rv, rt = ref.deform_node_targets(p64, nrm, faces, ids, tv64, tn64, pl, pd, tmp_path)
+    assert np.array_equal(rv, ids) and np.array_equal(ctrl, rt)
+    assert 0 < valid.sum() < len(ids) or valid.sum() == len(ids)
+    thr = float(rng.uniform(1e-3, 2e-2))
+    c2, v2 = oracle.node_targets_threshold(pts[ids], nrm[ids], tv, thr)
+    rv, rt = ref.deform_node_targets_threshold(p64, nrm, faces, ids, tv64, tn64, thr)
+    assert np.array_equal(ids[v2 > 0], rv) and np.array_equal(c2[v2 > 0], rt)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [21, 22])
+def test_ref_alignment_random_scenes(tmp_path, seed):
+    """Other poses, scales and view directions through the whole Alignment::Align."""
+    from multiviewstitch_b200 import synth
+    rng = np.random.default_rng(seed)
+    sv, sf, sl = synth.humanoid_mesh(10, 8, arm_angle=float(rng.uniform(0.35, 0.6)),
+                                     leg_angle=float(rng.uniform(0.08, 0.18)))
+    sn = synth.vertex_normals(sv, sf)
+    tv0, tf, _ = synth.humanoid_mesh(12, 9, arm_angle=float(rng.uniform(0.55, 0.9)),
+                                     leg_angle=float(rng.uniform(0.1, 0.25)), ground=(0.7, 30))
+    R = synth.axis_angle(rng.normal(size=3) * [0.1, 1.0, 0.1], float(rng.uniform(-0.4, 0.4)))
+    tv = float(rng.uniform(0.7, 2.0)) * tv0 @ R.T + rng.normal(size=3)
+    tn = synth.vertex_normals(tv, tf)
+    vr = R @ [0, 0, 1.0]
+    a = oracle.align(sv, sn, sl, tv, tn, tf, vr, dist_thres=refcases.DIST_THRES, remove_ground=1, local_align=1)
+    b = ref.align(sv, sn, sf, sl, tv, tn, tf, vr, refcases.DIST_THRES, tmp_path)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert np.abs(a[0] - b[0]).max() <= 1e-11 and np.abs(a[1] - b[1]).max() <= 1e-11
