@@ -506,3 +506,23 @@ def test_ref_alignment_random_scenes(tmp_path, seed):
     b = ref.align(sv, sn, sf, sl, tv, tn, tf, vr, refcases.DIST_THRES, tmp_path)
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
     assert np.abs(a[0] - b[0]).max() <= 1e-11 and np.abs(a[1] - b[1]).max() <= 1e-11
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_ref_remove_outliers_random_scenes(seed):
+    """Other match sets, outlier fractions and thresholds through Processor::RemoveOutliers: the
+    oracle's round loop on the reference's rand() samples keeps the same matches, same error."""
+    from multiviewstitch_b200 import synth
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(60, 900))
+    p, q = synth.planted_pairs(n, seed=seed, noise=float(rng.uniform(1e-4, 3e-3)))
+    bad = rng.random(n) < rng.uniform(0.0, 0.35)
+    q = q.copy()
+    q[bad] += rng.normal(scale=0.3, size=(int(bad.sum()), 3))
+    c1, c2 = refcases.cams(oracle.make_camera)
+    pe, ar = float(rng.uniform(2.0, 80.0)), float(rng.uniform(0.4, 0.9))
+    kr, er, _ = ref.remove_outliers(p, q, c1, c2, pe, ar, seed)
+    ko, eo, _ = ref.oracle_remove_outliers_with_ref_samples(p, q, c1, c2, pe, ar, seed)
+    assert np.array_equal(kr, ko) and er == eo
+    assert 3 <= len(kr) <= n
