@@ -526,3 +526,32 @@ def test_ref_remove_outliers_random_scenes(seed):
     ko, eo, _ = ref.oracle_remove_outliers_with_ref_samples(p, q, c1, c2, pe, ar, seed)
     assert np.array_equal(kr, ko) and er == eo
     assert 3 <= len(kr) <= n
+
+
+@needs_ref
+@pytest.mark.parametrize("nt", [9990, 10000, 10050])
+def test_ref_radius_search_sentinel(tmp_path, nt):
+    """Deformation.cpp:286-297: the radius search fills at most 10000 slots and the code looks for the
+    first -1 to learn how many it got — with 10000 or more points inside the radius no -1 is left,
+    the count stays 0 and the node is skipped (kept, not fixed).  A target
+    cluster that lies inside every node's search ball, just under / at / over the limit."""
+    from multiviewstitch_b200 import synth
+    verts, faces = synth.uv_sphere(12, 9, bumps=0.0)
+    pts = verts.astype(np.float32)
+    nrm = (verts / np.linalg.norm(verts, axis=1, keepdims=True)).astype(np.float32)
+    rng = np.random.default_rng(nt)
+    tv = (rng.normal(size=(nt, 3)) * 0.01).astype(np.float32)          # a tight cluster at the centre
+    tn = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (nt, 1))
+    ids = np.arange(0, len(pts), 7, dtype=np.int32)
+    graph = oracle.node_graph(pts[ids], 8)
+    ctrl, valid = oracle.node_targets(pts[ids], nrm[ids], tv, tn, graph, 100.0, 100.0, 0)
+    rv, rt = ref.deform_node_targets(pts.astype(np.float64), nrm, faces, ids, tv.astype(np.float64),
+                                     tn.astype(np.float64), 100.0, 100.0, tmp_path)
+    # the reference always smooths twice; compare through the oracle's two-sweep output
+    ctrl2, _ = oracle.node_targets(pts[ids], nrm[ids], tv, tn, graph, 100.0, 100.0, 2)
+    assert np.array_equal(rv, ids) and np.array_equal(ctrl2, rt)
+    if nt >= 10000:
+        assert valid.sum() == 0          # every node saw >= 10000 candidates: all skipped
+    else:
+        assert valid.sum() > 0           # 9990 candidates: the -1 sentinel is found, nodes with
+                                         # compatible normals get a target
