@@ -436,3 +436,27 @@ def test_weighted_targets_and_large_coordinates(ctx):
     assert err <= POS_TOL * diag(pts), (err, diag(pts))
     with pytest.raises(api.MvsError):
         d.SetTargets(targets, -tw - 1.0)
+
+
+@pytest.mark.parametrize("nt", [9990, 10000, 10050])
+def test_radius_search_sentinel_quirk(ctx, nt):
+    """Deformation.cpp:286-297,315: 10000 or more target points inside a node's search ball leave no
+    -1 sentinel, the candidate count stays 0 and the node is skipped (replicated, SURVEY appendix
+    B.6).  Same scene as tests/test_ref_parity.py::test_ref_radius_search_sentinel, where the oracle is
+    checked against the reference's own code."""
+    verts, faces = synth.uv_sphere(12, 9, bumps=0.0)
+    pts = verts.astype(np.float32)
+    nrm = (verts / np.linalg.norm(verts, axis=1, keepdims=True)).astype(np.float32)
+    rng = np.random.default_rng(nt)
+    tv = (rng.normal(size=(nt, 3)) * 0.01).astype(np.float32)
+    tn = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (nt, 1))
+    ids = np.arange(0, len(pts), 7, dtype=np.int32)
+    d = api.Deformation(pts, nrm, faces, ctx)
+    d.SetNodes(ids)
+    graph = d.KNearestNeighbor(8)
+    d.SetTarget(tv, tn)
+    for sweeps in (0, 2):
+        c, v = d.NodeTargets(100.0, 100.0, sweeps)
+        co, vo = oracle.node_targets(pts[ids], nrm[ids], tv, tn, graph, 100.0, 100.0, sweeps)
+        assert np.array_equal(v, vo) and np.allclose(c, co, rtol=0, atol=1e-12)
+    assert (v.sum() == 0) == (nt >= 10000)
