@@ -160,6 +160,17 @@ int mvs_remove_outliers(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, 
                         const mvs_camera* cam1, const mvs_camera* cam2,
                         const mvs_outlier_params* params, int32_t* keep_idx, int64_t* n_keep,
                         double* err, double* inlier_ratio);
+/* The same round loop with the hypothesis samples of every round supplied by the caller:
+ * draw(size, iter_num, out_triples, user) is called once per round with the number of matches still
+ * in play and fills iter_num x 3 indices < size.  The reference draws them from the C library's
+ * rand() (Common/Utils.h:25-34 Shuffle, Solver/SRTSolver.cpp:152): a caller that wants the
+ * reference's exact result hands that stream over here.  draw == NULL: as mvs_remove_outliers. */
+typedef void (*mvs_triples_fn)(int64_t size, int iter_num, int32_t* out_triples, void* user);
+int mvs_remove_outliers_samples(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, int64_t n,
+                                const mvs_camera* cam1, const mvs_camera* cam2,
+                                const mvs_outlier_params* params, mvs_triples_fn draw, void* user,
+                                int32_t* keep_idx, int64_t* n_keep, double* err,
+                                double* inlier_ratio);
 
 /* ---------------------------------------------------------------- point-set utilities ------ */
 /* v = s R p + t ; n = R n. [ref: Alignment/Alignment.cpp:31-34, Processor/Processor.cpp:1025-1026]

@@ -333,6 +333,32 @@ def remove_outliers(p, q, cam1: Camera, cam2: Camera, rounds=3, iter_num=200, pi
     return keep[:nk.value].copy(), err.value, ir.value
 
 
+TRIPLES_FN = C.CFUNCTYPE(None, C.c_int64, C.c_int, C.POINTER(C.c_int32), C.c_void_p)
+
+
+def remove_outliers_samples(p, q, cam1: Camera, cam2: Camera, draw, rounds=3, iter_num=200,
+                            pixel_err=55.0, adapt_ratio=0.6, ctx: Context | None = None):
+    """RemoveOutliers with the RANSAC samples of every round supplied by `draw`: a TRIPLES_FN callback
+    (size, iter_num, out_triples, user) or a Python callable (size, iter_num) -> (iter_num, 3) int
+    array.  The reference draws them from rand(); handing that stream over reproduces its result."""
+    p, q = _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3)
+    prm = OutlierParams(rounds, iter_num, pixel_err, adapt_ratio, 0)
+    keep = np.empty(len(p), np.int32)
+    nk = C.c_int64()
+    err, ir = C.c_double(), C.c_double()
+    if not isinstance(draw, TRIPLES_FN):
+        fn = draw
+
+        def _draw(size, iters, out, user):
+            np.ctypeslib.as_array(out, shape=(iters, 3))[:] = np.asarray(fn(size, iters), np.int32)
+        draw = TRIPLES_FN(_draw)
+    check(lib().mvs_remove_outliers_samples(_ctxh(ctx), _ptr(p, C.c_double), _ptr(q, C.c_double),
+                                            C.c_int64(len(p)), C.byref(cam1), C.byref(cam2),
+                                            C.byref(prm), draw, None, _ptr(keep, C.c_int32),
+                                            C.byref(nk), C.byref(err), C.byref(ir)))
+    return keep[:nk.value].copy(), err.value, ir.value
+
+
 def srt_draw_triples(n: int, iter_num: int, seed: int):
     out = np.empty((iter_num, 3), np.int32)
     check(lib().mvs_srt_draw_triples(C.c_int64(n), C.c_int(iter_num), C.c_uint64(seed),

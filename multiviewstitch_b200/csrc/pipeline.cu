@@ -261,6 +261,15 @@ int mvs_remove_outliers(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, 
                         const mvs_camera* cam1, const mvs_camera* cam2,
                         const mvs_outlier_params* params, int32_t* keep_idx, int64_t* n_keep,
                         double* err, double* inlier_ratio) {
+  return mvs_remove_outliers_samples(ctx, p_xyz, q_xyz, n, cam1, cam2, params, nullptr, nullptr,
+                                     keep_idx, n_keep, err, inlier_ratio);
+}
+
+int mvs_remove_outliers_samples(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, int64_t n,
+                                const mvs_camera* cam1, const mvs_camera* cam2,
+                                const mvs_outlier_params* params, mvs_triples_fn draw, void* user,
+                                int32_t* keep_idx, int64_t* n_keep, double* err,
+                                double* inlier_ratio) {
   MVS_TRY(resolve(ctx));
   if (!p_xyz || !q_xyz || n < 0 || !cam1 || !cam2 || !keep_idx || !n_keep) {
     set_error("remove_outliers: bad argument");
@@ -277,6 +286,7 @@ int mvs_remove_outliers(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, 
   int64_t size = n;
   double e = HUGE_VAL, ratio = 1.0;
   std::vector<uint8_t> flags;
+  std::vector<int32_t> triples;
   // one solver for all rounds (the reference constructs one per round, Processor.cpp:202; SetInput
   // replaces the matches): its device buffers are reused and destroyed — one stream wait — once
   mvs_srt* s = nullptr;
@@ -291,8 +301,14 @@ int mvs_remove_outliers(mvs_ctx* ctx, const double* p_xyz, const double* q_xyz, 
     if (rc == MVS_OK) rc = mvs_srt_set_print(s, 0);
     if (rc == MVS_OK) rc = mvs_srt_set_input(s, p.data(), q.data(), size, cam1, cam2);
     double sc = 1.0, R[9], t[3];
+    const int32_t* samples = nullptr;  // null: the solver draws them from seed + round
+    if (draw && params->iter_num > 0) {
+      triples.resize((size_t)params->iter_num * 3);
+      draw(size, params->iter_num, triples.data(), user);
+      samples = triples.data();
+    }
     if (rc == MVS_OK)
-      rc = mvs_srt_estimate_ransac(s, nullptr, params->seed + (uint64_t)k, &sc, R, t, nullptr, nullptr);
+      rc = mvs_srt_estimate_ransac(s, samples, params->seed + (uint64_t)k, &sc, R, t, nullptr, nullptr);
     flags.resize((size_t)size);
     double err_all = 0.0;
     int64_t nin = 0;

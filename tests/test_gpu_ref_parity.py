@@ -227,9 +227,7 @@ def test_cuda_deformation_graph_matches_reference_vectors(ctx):
 # ------------------------------------------------------------------ Processor::CheckConsistencyCore
 def test_cuda_check_consistency_matches_reference_vectors(ctx):
     """§8(f)1: mvs_check_consistency against the depth map the reference's own
-    Processor::CheckConsistencyCore (Processor.cpp:66-115) leaves — identical.  (RemoveOutliers is
-    pinned through the oracle: tests/test_ref_parity.py feeds the oracle the reference's rand()
-    samples, tests/test_gpu_pipeline.py compares the CUDA path with the oracle on shared seeds.)"""
+    Processor::CheckConsistencyCore (Processor.cpp:66-115) leaves — identical."""
     import oracle
     want = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_processor_vectors.npz"))
 
@@ -239,3 +237,26 @@ def test_cuda_check_consistency_matches_reference_vectors(ctx):
     cs, maps = refcases.consistency_inputs(api.make_camera, m2d)
     g = api.check_consistency(maps[1], cs[1], maps[[0, 2]], [cs[0], cs[2]], refcases.MIN_DSP, 0.5, 4.0, ctx)
     assert np.array_equal(np.asarray(g, np.float32), want["cc_depth"])
+
+
+def test_cuda_remove_outliers_matches_reference_vectors(ctx):
+    """§8(f)1 directly: mvs_remove_outliers_samples, handed the hypothesis samples the reference drew
+    from rand() round by round (stored next to its results), keeps exactly the matches the reference's
+    own Processor::RemoveOutliers keeps and reports its mean pixel error."""
+    want = dict(np.load(Path(__file__).resolve().parent / "golden" / "ref_processor_vectors.npz"))
+    p, q, _ = refcases.outlier_inputs()
+    c1, c2 = refcases.cams(api.make_camera)
+    for seed, pe, ar in refcases.REMOVE_OUTLIER_CASES:
+        stored = [want[k] for k in sorted(want) if k.startswith(f"ro_{seed}_round")]
+        served = []
+
+        def draw(size, iters):
+            tr = stored[len(served)]
+            assert tr.shape == (iters, 3) and tr.max() < size
+            served.append(tr)
+            return tr
+
+        keep, err, _ = api.remove_outliers_samples(p, q, c1, c2, draw, 3, 200, pe, ar, ctx)
+        assert len(served) == len(stored)
+        assert np.array_equal(keep, want[f"ro_{seed}_keep"])
+        assert abs(err - float(want[f"ro_{seed}_err"])) <= 1e-9 * max(1.0, float(want[f"ro_{seed}_err"]))
